@@ -1,0 +1,503 @@
+// C ABI of libbpk.so (see include/bpk.h): context, staging of host buffers, error mapping.
+#include "internal.cuh"
+
+namespace bpk {
+
+int cuda_fail(bpk_ctx* ctx, cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s) at %s:%d", what, cudaGetErrorName(e), cudaGetErrorString(e), file, line);
+    if (ctx) ctx->last_error = buf;
+    cudaGetLastError();  // clear the sticky-less error state
+    return e == cudaErrorMemoryAllocation ? BPK_ERR_OOM : BPK_ERR_CUDA;
+}
+
+int ws_reserve(bpk_ctx* ctx, int slot, size_t bytes, void** out) {
+    DeviceBuffer& b = ctx->ws[slot];
+    if (bytes == 0) bytes = 16;
+    if (b.bytes < bytes) {
+        if (b.ptr) {
+            BPK_CUDA(cudaStreamSynchronize(ctx->stream));
+            BPK_CUDA(cudaFree(b.ptr));
+            b.ptr = nullptr;
+            b.bytes = 0;
+        }
+        size_t want = bytes + bytes / 8;  // a little slack so slowly growing sizes do not realloc every call
+        BPK_CUDA(cudaMalloc(&b.ptr, want));
+        b.bytes = want;
+    }
+    *out = b.ptr;
+    return BPK_OK;
+}
+
+StageTimer::StageTimer(bpk_ctx* c, const char* n) : ctx(c), name(n), launches_before(c->launches) {
+    if (!ctx->profiling) return;
+    if (cudaEventCreate(&start) != cudaSuccess || cudaEventCreate(&stop) != cudaSuccess) {
+        start = stop = nullptr;
+        return;
+    }
+    cudaEventRecord(start, ctx->stream);
+}
+void StageTimer::end() {
+    if (!ctx->profiling || !start) return;
+    cudaEventRecord(stop, ctx->stream);
+    PendingEvent pe;
+    pe.name = name;
+    pe.start = start;
+    pe.stop = stop;
+    pe.launches = ctx->launches - launches_before;
+    ctx->pending.push_back(pe);
+}
+int profile_collect(bpk_ctx* ctx) {
+    for (auto& pe : ctx->pending) {
+        float ms = 0;
+        cudaEventSynchronize(pe.stop);
+        cudaEventElapsedTime(&ms, pe.start, pe.stop);
+        StageStat& s = ctx->stats[pe.name];
+        s.ms += ms;
+        s.launches += pe.launches;
+        cudaEventDestroy(pe.start);
+        cudaEventDestroy(pe.stop);
+    }
+    ctx->pending.clear();
+    return BPK_OK;
+}
+
+// ---- IMAD throughput probe ---------------------------------------------------------------------
+// mode 0: 8 independent 32x32+64 multiply-adds per iteration (IMAD.WIDE.U32)
+// mode 1: two independent 12-limb carry chains (IMAD.WIDE.U32.X), the shape the Fp multiplier issues
+__global__ void __launch_bounds__(256) imad_probe_kernel(uint64_t* out, uint32_t iters, uint32_t seed, int mode) {
+    uint32_t a = seed + threadIdx.x * 2654435761u + blockIdx.x;
+    uint32_t b = a * 747796405u + 2891336453u;
+    if (mode == 0) {
+        uint64_t acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = a + i;
+        for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a + (uint32_t)i), "r"(b));
+        }
+        uint64_t s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) s ^= acc[i];
+        out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+    } else {
+        uint32_t x[12], y[12], m[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            x[i] = a + i;
+            y[i] = b + i;
+            m[i] = a * (i + 3);
+        }
+        for (uint32_t it = 0; it < iters; it++) {
+            detail::cmad_n<12>(x, m, b);
+            detail::cmad_n<12>(y, m, a);
+        }
+        uint64_t s = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) s ^= ((uint64_t)x[i] << 32) | y[i];
+        out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+    }
+}
+
+int imad_peak_run(bpk_ctx* ctx, double* rate, double* seconds) {
+    const int mode = (int)ctx->opt_imad_mode;
+    const uint32_t iters = 1u << 14;
+    const unsigned blocks = (unsigned)ctx->sm_count * 8;
+    uint64_t* d_out;
+    BPK_TRY(ws_reserve(ctx, 7, (size_t)blocks * 256 * sizeof(uint64_t), (void**)&d_out));
+    cudaEvent_t e0, e1;
+    BPK_CUDA(cudaEventCreate(&e0));
+    BPK_CUDA(cudaEventCreate(&e1));
+    imad_probe_kernel<<<blocks, 256, 0, ctx->stream>>>(d_out, iters / 16, 1, mode);  // warm-up
+    BPK_CUDA(cudaEventRecord(e0, ctx->stream));
+    imad_probe_kernel<<<blocks, 256, 0, ctx->stream>>>(d_out, iters, 2, mode);
+    BPK_CUDA(cudaEventRecord(e1, ctx->stream));
+    count_launch(ctx, 2);
+    BPK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    BPK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    double per_thread = mode == 0 ? 8.0 * iters : 12.0 * iters;  // mode 1: 2 chains x 6 wide IMADs
+    *rate = per_thread * 256.0 * blocks / (ms * 1e-3);
+    *seconds = ms * 1e-3;
+    return BPK_OK;
+}
+
+static fr_t fr_from_host(const uint64_t v[4]) {
+    fr_t r;
+    for (int i = 0; i < 4; i++) {
+        r.l[2 * i] = (uint32_t)v[i];
+        r.l[2 * i + 1] = (uint32_t)(v[i] >> 32);
+    }
+    return r;
+}
+
+}  // namespace bpk
+
+using namespace bpk;
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" int bpk_abi_version(void) { return 1; }
+
+extern "C" const char* bpk_strerror(int s) {
+    switch (s) {
+        case BPK_OK: return "ok";
+        case BPK_ERR_NO_DEVICE: return "no usable CUDA device (sm_100 required; there is no CPU fallback)";
+        case BPK_ERR_CUDA: return "CUDA runtime error (see bpk_last_error)";
+        case BPK_ERR_INVALID_ARG: return "invalid argument";
+        case BPK_ERR_NOT_POW2: return "NTT length is not a power of two";
+        case BPK_ERR_TOO_LARGE: return "size beyond the supported range";
+        case BPK_ERR_WINDOW: return "bucket_msm window parameters the reference panics on";
+        case BPK_ERR_OOM: return "out of device memory";
+        default: return "unknown status";
+    }
+}
+
+extern "C" int bpk_init(bpk_ctx** out, int device) {
+    if (!out) return BPK_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return BPK_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BPK_ERR_NO_DEVICE;
+    if (prop.major != 10) return BPK_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return BPK_ERR_NO_DEVICE;
+    bpk_ctx* ctx = new bpk_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->stream = nullptr;  // legacy default stream: ordered with torch's default stream
+    int s = ntt_init_tables(ctx);
+    if (s != BPK_OK) {
+        fprintf(stderr, "bpk_init: %s\n", ctx->last_error.c_str());
+        delete ctx;
+        return s;
+    }
+    *out = ctx;
+    return BPK_OK;
+}
+
+extern "C" void bpk_destroy(bpk_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    profile_collect(ctx);
+    for (auto& kv : ctx->srs) cudaFree(kv.second.points);
+    for (auto& b : ctx->ws)
+        if (b.ptr) cudaFree(b.ptr);
+    for (int d = 0; d < 2; d++) {
+        cudaFree(ctx->tw_lo[d]);
+        cudaFree(ctx->tw_hi[d]);
+        cudaFree(ctx->coset_lo[d]);
+        cudaFree(ctx->coset_hi[d]);
+    }
+    if (ctx->gen_table) cudaFree(ctx->gen_table);
+    delete ctx;
+}
+
+extern "C" const char* bpk_last_error(bpk_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+extern "C" int bpk_set_stream(bpk_ctx* ctx, void* s) {
+    if (!ctx) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = (cudaStream_t)s;
+    return BPK_OK;
+}
+
+extern "C" int bpk_synchronize(bpk_ctx* ctx) {
+    if (!ctx) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BPK_OK;
+}
+
+extern "C" int bpk_set_option(bpk_ctx* ctx, const char* key, long value) {
+    if (!ctx || !key) return BPK_ERR_INVALID_ARG;
+    std::string k(key);
+    if (k == "msm.window") ctx->opt_msm_window = value;
+    else if (k == "msm.chunk") ctx->opt_msm_chunk = value;
+    else if (k == "ntt.tile_log2") {
+        if (value < 1 || value > 12) return BPK_ERR_INVALID_ARG;
+        ctx->opt_ntt_tile_log2 = value;
+    } else if (k == "imad.mode") ctx->opt_imad_mode = value;
+    else return BPK_ERR_INVALID_ARG;
+    return BPK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SRS
+// ------------------------------------------------------------------------------------------------
+static int srs_register(bpk_ctx* ctx, affine_t* pts, size_t n, uint64_t* handle_out) {
+    uint64_t h = ctx->next_handle++;
+    SrsEntry e;
+    e.points = pts;
+    e.n = n;
+    ctx->srs[h] = e;
+    *handle_out = h;
+    return BPK_OK;
+}
+
+extern "C" int bpk_srs_load(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n, uint64_t* handle_out) {
+    if (!ctx || !handle_out || (n && !points_xyz)) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    affine_t* pts = nullptr;
+    BPK_CUDA(cudaMalloc(&pts, (n ? n : 1) * sizeof(affine_t)));
+    if (n) {
+        // stage in slices so the projective copy never needs more than 256 MiB of scratch
+        const size_t slice = (size_t)1 << 20;
+        uint64_t* d_xyz;
+        int s = ws_reserve(ctx, 8, (n < slice ? n : slice) * 18 * sizeof(uint64_t), (void**)&d_xyz);
+        if (s != BPK_OK) { cudaFree(pts); return s; }
+        for (size_t off = 0; off < n; off += slice) {
+            size_t cnt = n - off < slice ? n - off : slice;
+            cudaError_t e = cudaMemcpyAsync(d_xyz, points_xyz + 18 * off, cnt * 18 * sizeof(uint64_t),
+                                            cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) { cudaFree(pts); return cuda_fail(ctx, e, "srs upload", __FILE__, __LINE__); }
+            s = srs_from_projective(ctx, d_xyz, cnt, pts + off);
+            if (s != BPK_OK) { cudaFree(pts); return s; }
+            e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { cudaFree(pts); return cuda_fail(ctx, e, "srs convert", __FILE__, __LINE__); }
+        }
+    }
+    return srs_register(ctx, pts, n, handle_out);
+}
+
+extern "C" int bpk_srs_generate(bpk_ctx* ctx, const uint64_t tau_mont[4], size_t n, uint64_t* handle_out) {
+    if (!ctx || !handle_out || !tau_mont) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    affine_t* pts = nullptr;
+    BPK_CUDA(cudaMalloc(&pts, (n ? n : 1) * sizeof(affine_t)));
+    int s = srs_generate(ctx, fr_from_host(tau_mont), n, pts);
+    if (s == BPK_OK) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) s = cuda_fail(ctx, e, "srs generate", __FILE__, __LINE__);
+    }
+    if (s != BPK_OK) { cudaFree(pts); return s; }
+    return srs_register(ctx, pts, n, handle_out);
+}
+
+extern "C" int bpk_srs_len(bpk_ctx* ctx, uint64_t handle, size_t* n_out) {
+    if (!ctx || !n_out) return BPK_ERR_INVALID_ARG;
+    auto it = ctx->srs.find(handle);
+    if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
+    *n_out = it->second.n;
+    return BPK_OK;
+}
+
+extern "C" int bpk_srs_read(bpk_ctx* ctx, uint64_t handle, size_t first, size_t count, uint64_t* out_xyz) {
+    if (!ctx || (count && !out_xyz)) return BPK_ERR_INVALID_ARG;
+    auto it = ctx->srs.find(handle);
+    if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
+    if (first > it->second.n || count > it->second.n - first) return BPK_ERR_INVALID_ARG;
+    if (count == 0) return BPK_OK;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    uint64_t* d_xyz;
+    BPK_TRY(ws_reserve(ctx, 8, count * 18 * sizeof(uint64_t), (void**)&d_xyz));
+    BPK_TRY(srs_to_projective(ctx, it->second.points + first, count, d_xyz));
+    BPK_CUDA(cudaMemcpyAsync(out_xyz, d_xyz, count * 18 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    BPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BPK_OK;
+}
+
+extern "C" int bpk_srs_free(bpk_ctx* ctx, uint64_t handle) {
+    if (!ctx) return BPK_ERR_INVALID_ARG;
+    auto it = ctx->srs.find(handle);
+    if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(it->second.points);
+    ctx->srs.erase(it);
+    return BPK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// MSM
+// ------------------------------------------------------------------------------------------------
+static int window_to_shift(size_t b, size_t c, unsigned* rshift) {
+    if (c == 0) return BPK_ERR_WINDOW;        // division by zero panics in Rust
+    size_t k = b / c;
+    if (k == 0) return BPK_ERR_WINDOW;        // t_points[0] out of bounds (msm.rs:105)
+    if (k * c > 256) return BPK_ERR_WINDOW;   // bits[start..end] out of range (msm.rs:133)
+    if (c > 63) return BPK_ERR_WINDOW;        // 1 << c overflow / bools_to_u64 shift overflow
+    *rshift = (unsigned)(256 - k * c);
+    return BPK_OK;
+}
+
+static int msm_host_scalars(bpk_ctx* ctx, const affine_t* d_points, size_t n_points, const uint64_t* scalars,
+                            size_t n_scalars, unsigned rshift, uint64_t out_xyz[18]) {
+    size_t n = n_points < n_scalars ? n_points : n_scalars;  // zip truncation (msm.rs:29)
+    fr_t* d_scalars;
+    BPK_TRY(ws_reserve(ctx, 9, (n ? n : 1) * sizeof(fr_t), (void**)&d_scalars));
+    uint64_t* d_out;
+    BPK_TRY(ws_reserve(ctx, 10, 18 * sizeof(uint64_t), (void**)&d_out));
+    if (n) BPK_CUDA(cudaMemcpyAsync(d_scalars, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    BPK_TRY(msm_run(ctx, d_points, d_scalars, n, rshift, true, d_out));
+    BPK_CUDA(cudaMemcpyAsync(out_xyz, d_out, 18 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    BPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BPK_OK;
+}
+
+extern "C" int bpk_bucket_msm(bpk_ctx* ctx, uint64_t handle, const uint64_t* scalars_mont, size_t n_scalars,
+                              size_t b, size_t c, uint64_t out_xyz[18]) {
+    if (!ctx || !out_xyz || (n_scalars && !scalars_mont)) return BPK_ERR_INVALID_ARG;
+    unsigned rshift = 0;
+    BPK_TRY(window_to_shift(b, c, &rshift));
+    auto it = ctx->srs.find(handle);
+    if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    return msm_host_scalars(ctx, it->second.points, it->second.n, scalars_mont, n_scalars, rshift, out_xyz);
+}
+
+extern "C" int bpk_msm_g1(bpk_ctx* ctx, uint64_t handle, const uint64_t* scalars_mont, size_t n_scalars,
+                          uint64_t out_xyz[18]) {
+    return bpk_bucket_msm(ctx, handle, scalars_mont, n_scalars, 256, 4, out_xyz);
+}
+
+extern "C" int bpk_msm_g1_points(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n_points,
+                                 const uint64_t* scalars_mont, size_t n_scalars, uint64_t out_xyz[18]) {
+    if (!ctx || !out_xyz || (n_points && !points_xyz) || (n_scalars && !scalars_mont)) return BPK_ERR_INVALID_ARG;
+    size_t n = n_points < n_scalars ? n_points : n_scalars;
+    uint64_t h = 0;
+    BPK_TRY(bpk_srs_load(ctx, points_xyz, n, &h));
+    int s = bpk_bucket_msm(ctx, h, scalars_mont, n, 256, 4, out_xyz);
+    bpk_srs_free(ctx, h);
+    return s;
+}
+
+extern "C" int bpk_msm_g1_dev(bpk_ctx* ctx, uint64_t handle, size_t first, const void* d_scalars_mont, size_t n,
+                              int normalise, void* d_out_xyz) {
+    if (!ctx || !d_out_xyz || (n && !d_scalars_mont)) return BPK_ERR_INVALID_ARG;
+    auto it = ctx->srs.find(handle);
+    if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
+    if (first > it->second.n || n > it->second.n - first) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    return msm_run(ctx, it->second.points + first, (const fr_t*)d_scalars_mont, n, 0, normalise != 0,
+                   (uint64_t*)d_out_xyz);
+}
+
+extern "C" int bpk_g1_sum(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n, uint64_t out_xyz[18]) {
+    if (!ctx || !out_xyz || (n && !points_xyz) || n > (1u << 20)) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    uint64_t* d_in;
+    BPK_TRY(ws_reserve(ctx, 8, (n ? n : 1) * 18 * sizeof(uint64_t), (void**)&d_in));
+    uint64_t* d_out;
+    BPK_TRY(ws_reserve(ctx, 10, 18 * sizeof(uint64_t), (void**)&d_out));
+    if (n) BPK_CUDA(cudaMemcpyAsync(d_in, points_xyz, n * 18 * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    BPK_TRY(g1_sum_run(ctx, d_in, n, d_out));
+    BPK_CUDA(cudaMemcpyAsync(out_xyz, d_out, 18 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    BPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BPK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NTT
+// ------------------------------------------------------------------------------------------------
+static int ntt_host(bpk_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, size_t batch, bool inverse,
+                    const uint64_t* shift) {
+    if (!ctx || !in || !out) return BPK_ERR_INVALID_ARG;
+    if (n == 0 || (n & (n - 1)) != 0) return BPK_ERR_NOT_POW2;
+    if (n > ((size_t)1 << NTT_MAX_LOG)) return BPK_ERR_TOO_LARGE;
+    if (batch == 0) return BPK_OK;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    size_t bytes = n * batch * sizeof(fr_t);
+    fr_t* d_buf;
+    BPK_TRY(ws_reserve(ctx, 9, bytes, (void**)&d_buf));
+    BPK_CUDA(cudaMemcpyAsync(d_buf, in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    fr_t sh;
+    if (shift) sh = fr_from_host(shift);
+    BPK_TRY(ntt_run(ctx, d_buf, d_buf, n, batch, inverse, shift ? &sh : nullptr));
+    BPK_CUDA(cudaMemcpyAsync(out, d_buf, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    BPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BPK_OK;
+}
+
+extern "C" int bpk_ntt_fr(bpk_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, size_t batch) {
+    return ntt_host(ctx, in, out, n, batch, false, nullptr);
+}
+extern "C" int bpk_intt_fr(bpk_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, size_t batch) {
+    return ntt_host(ctx, in, out, n, batch, true, nullptr);
+}
+extern "C" int bpk_coset_ntt_fr(bpk_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, size_t batch,
+                                const uint64_t shift_mont[4]) {
+    if (!shift_mont) return BPK_ERR_INVALID_ARG;
+    return ntt_host(ctx, in, out, n, batch, false, shift_mont);
+}
+extern "C" int bpk_coset_intt_fr(bpk_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, size_t batch,
+                                 const uint64_t shift_mont[4]) {
+    if (!shift_mont) return BPK_ERR_INVALID_ARG;
+    return ntt_host(ctx, in, out, n, batch, true, shift_mont);
+}
+
+extern "C" int bpk_ntt_fr_dev(bpk_ctx* ctx, const void* d_in, void* d_out, size_t n, size_t batch, int flags,
+                              const uint64_t* shift_mont) {
+    if (!ctx || !d_in || !d_out) return BPK_ERR_INVALID_ARG;
+    if ((flags & 2) && !shift_mont) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    fr_t sh;
+    if (flags & 2) sh = fr_from_host(shift_mont);
+    return ntt_run(ctx, (const fr_t*)d_in, (fr_t*)d_out, n, batch, (flags & 1) != 0, (flags & 2) ? &sh : nullptr);
+}
+
+extern "C" int bpk_poly_mul_fr(bpk_ctx* ctx, const uint64_t* a, size_t la, const uint64_t* b, size_t lb,
+                               uint64_t* out) {
+    if (!ctx || !a || !b || !out || la == 0 || lb == 0) return BPK_ERR_INVALID_ARG;
+    // D = find_next_power_of_two(deg a, deg b) (utils.rs:54-61): smallest power of two >= la + lb - 1
+    size_t target = la + lb - 1;
+    size_t D = 1;
+    while (D < target) D <<= 1;
+    if (D > ((size_t)1 << NTT_MAX_LOG)) return BPK_ERR_TOO_LARGE;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    fr_t* d_buf;
+    BPK_TRY(ws_reserve(ctx, 9, 2 * D * sizeof(fr_t), (void**)&d_buf));
+    BPK_CUDA(cudaMemsetAsync(d_buf, 0, 2 * D * sizeof(fr_t), ctx->stream));
+    BPK_CUDA(cudaMemcpyAsync(d_buf, a, la * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    BPK_CUDA(cudaMemcpyAsync(d_buf + D, b, lb * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    BPK_TRY(ntt_run(ctx, d_buf, d_buf, D, 2, false, nullptr));      // both operands to evaluation form
+    BPK_TRY(pointwise_mul(ctx, d_buf, d_buf + D, D));               // polynomial.rs:262-266
+    BPK_TRY(ntt_run(ctx, d_buf, d_buf, D, 1, true, nullptr));       // i_ntt_381 (polynomial.rs:270)
+    BPK_CUDA(cudaMemcpyAsync(out, d_buf, target * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    BPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BPK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// instrumentation
+// ------------------------------------------------------------------------------------------------
+extern "C" int bpk_profile_enable(bpk_ctx* ctx, int on) {
+    if (!ctx) return BPK_ERR_INVALID_ARG;
+    profile_collect(ctx);
+    ctx->profiling = on != 0;
+    return BPK_OK;
+}
+extern "C" int bpk_profile_reset(bpk_ctx* ctx) {
+    if (!ctx) return BPK_ERR_INVALID_ARG;
+    profile_collect(ctx);
+    ctx->stats.clear();
+    ctx->launches = 0;
+    return BPK_OK;
+}
+extern "C" int bpk_profile_get(bpk_ctx* ctx, const char* name, double* ms_out, uint64_t* launches_out) {
+    if (!ctx || !name) return BPK_ERR_INVALID_ARG;
+    profile_collect(ctx);
+    auto it = ctx->stats.find(name);
+    double ms = 0;
+    uint64_t l = 0;
+    if (it != ctx->stats.end()) {
+        ms = it->second.ms;
+        l = it->second.launches;
+    }
+    if (ms_out) *ms_out = ms;
+    if (launches_out) *launches_out = l;
+    return BPK_OK;
+}
+extern "C" uint64_t bpk_launch_count(bpk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int bpk_imad_peak(bpk_ctx* ctx, double* rate, double* seconds) {
+    if (!ctx || !rate || !seconds) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    return imad_peak_run(ctx, rate, seconds);
+}

@@ -1,0 +1,132 @@
+// Internal declarations shared by the translation units of libbpk.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/bpk.h"
+#include "ec.cuh"
+
+namespace bpk {
+
+constexpr int NTT_MAX_LOG = 28;   // largest transform: 2^28 elements (8 GiB)
+constexpr int TW_LO_BITS = 13;    // two-level twiddle table split
+constexpr int TW_HI_BITS = NTT_MAX_LOG - TW_LO_BITS;
+
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct SrsEntry {
+    affine_t* points = nullptr;  // n affine points, Montgomery, (0,0) = infinity
+    size_t n = 0;
+};
+
+struct StageStat {
+    double ms = 0;
+    uint64_t launches = 0;
+};
+
+struct PendingEvent {
+    std::string name;
+    cudaEvent_t start, stop;
+    uint64_t launches;
+};
+
+}  // namespace bpk
+
+struct bpk_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+
+    // NTT tables: powers of the primitive 2^NTT_MAX_LOG-th root (forward / inverse)
+    bpk::fr_t* tw_lo[2] = {nullptr, nullptr};
+    bpk::fr_t* tw_hi[2] = {nullptr, nullptr};
+    // coset tables for the last shift used (lo: g^i, hi: g^(i << TW_LO_BITS)), forward / inverse
+    bpk::fr_t* coset_lo[2] = {nullptr, nullptr};
+    bpk::fr_t* coset_hi[2] = {nullptr, nullptr};
+    bpk::fr_t coset_shift[2];
+    bool coset_valid[2] = {false, false};
+    size_t coset_n = 0;
+
+    // workspaces (grown on demand, never shrunk)
+    bpk::DeviceBuffer ws[16];
+
+    std::map<uint64_t, bpk::SrsEntry> srs;
+    uint64_t next_handle = 1;
+
+    // fixed-base table for bpk_srs_generate (built lazily)
+    bpk::affine_t* gen_table = nullptr;
+
+    // options
+    long opt_msm_window = 0;
+    long opt_msm_chunk = 0;
+    long opt_ntt_tile_log2 = 11;
+    long opt_imad_mode = 0;
+
+    // instrumentation
+    bool profiling = false;
+    uint64_t launches = 0;
+    std::map<std::string, bpk::StageStat> stats;
+    std::vector<bpk::PendingEvent> pending;
+};
+
+namespace bpk {
+
+int cuda_fail(bpk_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
+
+#define BPK_CUDA(call)                                                          \
+    do {                                                                        \
+        cudaError_t _e = (call);                                                \
+        if (_e != cudaSuccess) return bpk::cuda_fail(ctx, _e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define BPK_TRY(call)            \
+    do {                         \
+        int _s = (call);         \
+        if (_s != BPK_OK) return _s; \
+    } while (0)
+
+// grow-only device workspace slot
+int ws_reserve(bpk_ctx* ctx, int slot, size_t bytes, void** out);
+
+// stage instrumentation: RAII-less begin/end because kernels are launched in between
+struct StageTimer {
+    bpk_ctx* ctx;
+    const char* name;
+    uint64_t launches_before;
+    cudaEvent_t start = nullptr, stop = nullptr;
+    StageTimer(bpk_ctx* c, const char* n);
+    void end();
+};
+int profile_collect(bpk_ctx* ctx);
+
+inline void count_launch(bpk_ctx* ctx, uint64_t n = 1) { ctx->launches += n; }
+
+// ---- ntt.cu ----
+int ntt_init_tables(bpk_ctx* ctx);
+int ntt_run(bpk_ctx* ctx, const fr_t* d_in, fr_t* d_out, size_t n, size_t batch, bool inverse,
+            const fr_t* shift /* host, Montgomery, or null */);
+int pointwise_mul(bpk_ctx* ctx, fr_t* d_a, const fr_t* d_b, size_t n);
+
+// ---- msm.cu ----
+int msm_run(bpk_ctx* ctx, const affine_t* d_points, const fr_t* d_scalars, size_t n, unsigned rshift,
+            bool normalise, uint64_t* d_out_xyz /* 18 u64 on device */);
+int g1_sum_run(bpk_ctx* ctx, const uint64_t* d_points_xyz, size_t n, uint64_t* d_out_xyz);
+
+// ---- srs.cu ----
+int srs_from_projective(bpk_ctx* ctx, const uint64_t* d_xyz, size_t n, affine_t* d_out);
+int srs_to_projective(bpk_ctx* ctx, const affine_t* d_pts, size_t n, uint64_t* d_xyz);
+int srs_generate(bpk_ctx* ctx, const fr_t& tau, size_t n, affine_t* d_out);
+
+// ---- misc ----
+int imad_peak_run(bpk_ctx* ctx, double* rate, double* seconds);
+
+}  // namespace bpk

@@ -1,0 +1,474 @@
+// BLS12-381 G1 multi-scalar multiplication (Pippenger) for sm_100a.
+//
+// Contract = BucketMSM::bucket_msm (src/msm.rs:76-118): sum_i (s_i >> rshift) * P_i, judged on the
+// affine image of the result (G1Affine::from, g1.rs:49-63).  The reference walks 64 4-bit windows
+// serially with complete projective additions; nothing of that structure is kept:
+//
+//   K1 recode      scalar: Montgomery -> canonical (scalar.rs:292-304 semantics), signed c-bit digits;
+//                  one (bucket key, point index | sign) pair per (scalar, window)
+//   K2 sort        radix sort of the pairs by bucket key  (replaces the serial scatter, msm.rs:29-35)
+//   K3 accumulate  equal-size chunks of the sorted pair list, one thread per chunk, XYZZ += affine;
+//                  a bucket whose run lies inside one chunk is written directly, runs that cross chunk
+//                  borders leave partial sums that K3b merges -> load balance is independent of the
+//                  scalar distribution
+//   K4 reduce      sum_b (b+1) B_b per window by a tree of running sums (msm.rs:42-46 is the serial form)
+//   K5 finalize    Horner over windows (msm.rs:107-115), affine normalisation, G1Projective limbs out
+//
+// Roofline: integer multiply pipe.  Algorithmic work per accumulated pair: one mixed addition
+// = 8 M + 2 S in Fp, each 300 32x32->64 products; HBM traffic per pair is 8 B of
+// sorted pair + 96 B point gather -- two orders of magnitude below the arithmetic time.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "internal.cuh"
+
+namespace bpk {
+
+static constexpr uint32_t INVALID_KEY = 0xffffffffu;
+
+__device__ __forceinline__ fp_t ld_fp(const fp_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1], c = q[2];
+    fp_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    r.l[8] = c.x; r.l[9] = c.y; r.l[10] = c.z; r.l[11] = c.w;
+    return r;
+}
+__device__ __forceinline__ void st_fp(fp_t* p, const fp_t& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    q[2] = make_uint4(v.l[8], v.l[9], v.l[10], v.l[11]);
+}
+__device__ __forceinline__ affine_t ld_affine(const affine_t* p) {
+    affine_t r;
+    r.x = ld_fp(&p->x);
+    r.y = ld_fp(&p->y);
+    return r;
+}
+__device__ __forceinline__ xyzz_t ld_xyzz(const xyzz_t* p) {
+    xyzz_t r;
+    r.X = ld_fp(&p->X);
+    r.Y = ld_fp(&p->Y);
+    r.ZZ = ld_fp(&p->ZZ);
+    r.ZZZ = ld_fp(&p->ZZZ);
+    return r;
+}
+__device__ __forceinline__ void st_xyzz(xyzz_t* p, const xyzz_t& v) {
+    st_fp(&p->X, v.X);
+    st_fp(&p->Y, v.Y);
+    st_fp(&p->ZZ, v.ZZ);
+    st_fp(&p->ZZZ, v.ZZZ);
+}
+__device__ __forceinline__ fr_t ld_fr_g(const fr_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    fr_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: signed-digit recoding
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) msm_recode_kernel(const fr_t* __restrict__ scalars, uint32_t n, uint32_t c,
+                                                          uint32_t W, uint32_t rshift, uint32_t* __restrict__ keys,
+                                                          uint32_t* __restrict__ vals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_t s = from_mont(ld_fr_g(scalars + i));  // canonical integer < q
+    uint32_t l[10];
+#pragma unroll
+    for (int k = 0; k < 8; k++) l[k] = s.l[k];
+    l[8] = 0;
+    l[9] = 0;
+    if (rshift) {  // value >> rshift (the c-does-not-divide-256 quirk of msm.rs:119-139)
+        uint32_t ws = rshift >> 5, bs = rshift & 31;
+        uint32_t t[10];
+#pragma unroll
+        for (int k = 0; k < 10; k++) {
+            uint32_t lo = (k + ws < 8) ? l[k + ws] : 0;
+            uint32_t hi = (k + ws + 1 < 8) ? l[k + ws + 1] : 0;
+            t[k] = bs ? ((lo >> bs) | (hi << (32 - bs))) : lo;
+        }
+#pragma unroll
+        for (int k = 0; k < 10; k++) l[k] = t[k];
+    }
+    const uint32_t half = 1u << (c - 1);
+    const uint32_t mask = (1u << c) - 1;
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < W; w++) {
+        uint32_t bit = w * c;
+        uint32_t limb = bit >> 5, off = bit & 31;
+        uint64_t two = 0;
+        if (limb < 9) two = (uint64_t)l[limb] | ((uint64_t)l[limb + 1] << 32);
+        uint32_t raw = ((uint32_t)(two >> off) & mask) + carry;
+        uint32_t d, neg;
+        if (raw > half) {
+            d = (1u << c) - raw;
+            neg = 1;
+            carry = 1;
+        } else {
+            d = raw;
+            neg = 0;
+            carry = 0;
+        }
+        size_t o = (size_t)w * n + i;
+        keys[o] = d ? (w * half + d - 1) : INVALID_KEY;
+        vals[o] = i | (neg << 31);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: chunked bucket accumulation
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __restrict__ keys,
+                                                              const uint32_t* __restrict__ vals, size_t M,
+                                                              uint32_t chunk, size_t num_chunks,
+                                                              const affine_t* __restrict__ points, uint32_t nb_total,
+                                                              xyzz_t* __restrict__ buckets,
+                                                              uint32_t* __restrict__ pkeys,
+                                                              xyzz_t* __restrict__ pvals) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_chunks) return;
+    const size_t a = t * chunk;
+    const size_t b = (a + chunk < M) ? a + chunk : M;
+    uint32_t pk0 = INVALID_KEY, pk1 = INVALID_KEY;
+
+    uint32_t cur = INVALID_KEY;
+    bool left_open = false;
+    xyzz_t acc = xyzz_t::inf();
+
+    // software pipeline: entry e+1 is fetched while entry e is added
+    uint32_t k_next = keys[a];
+    affine_t p_next = affine_t::inf();
+    if (k_next < nb_total) {
+        uint32_t v = vals[a];
+        p_next = ld_affine(points + (v & 0x7fffffffu));
+        if (v >> 31) p_next.y = neg(p_next.y);
+    }
+    size_t e = a;
+    for (; e < b; e++) {
+        uint32_t k = k_next;
+        if (k >= nb_total) break;
+        affine_t p = p_next;
+        if (e + 1 < b) {
+            k_next = keys[e + 1];
+            if (k_next < nb_total) {
+                uint32_t v = vals[e + 1];
+                p_next = ld_affine(points + (v & 0x7fffffffu));
+                if (v >> 31) p_next.y = neg(p_next.y);
+            }
+        }
+        if (k != cur) {
+            if (cur != INVALID_KEY) {  // close the previous run (cannot be right-open)
+                if (left_open) {
+                    pk0 = cur;
+                    st_xyzz(pvals + 2 * t, acc);
+                } else {
+                    st_xyzz(buckets + cur, acc);
+                }
+            }
+            cur = k;
+            left_open = (e == a) && (a > 0) && (keys[a - 1] == k);
+            acc = xyzz_t::from_affine(p);
+        } else {
+            xyzz_madd(acc, p);
+        }
+    }
+    if (cur != INVALID_KEY) {
+        bool right_open = (e == b) && (b < M) && (keys[b] == cur);
+        if (left_open) {
+            pk0 = cur;
+            st_xyzz(pvals + 2 * t, acc);
+        } else if (right_open) {
+            pk1 = cur;
+            st_xyzz(pvals + 2 * t + 1, acc);
+        } else {
+            st_xyzz(buckets + cur, acc);
+        }
+    }
+    pkeys[2 * t] = pk0;
+    pkeys[2 * t + 1] = pk1;
+}
+
+// K3b: a run that crosses chunk borders starts as slot 1 of some chunk and continues as slot 0 of the
+// following chunks; the thread that owns the head adds the run up and writes the bucket.
+__global__ void __launch_bounds__(128) msm_merge_partials_kernel(const uint32_t* __restrict__ pkeys,
+                                                                  const xyzz_t* __restrict__ pvals,
+                                                                  size_t num_chunks, xyzz_t* __restrict__ buckets) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_chunks) return;
+    uint32_t k = pkeys[2 * t + 1];
+    if (k == INVALID_KEY) return;
+    xyzz_t acc = ld_xyzz(pvals + 2 * t + 1);
+    for (size_t u = t + 1; u < num_chunks; u++) {
+        if (pkeys[2 * u] != k) break;
+        xyzz_t q = ld_xyzz(pvals + 2 * u);
+        xyzz_add(acc, q);
+    }
+    st_xyzz(buckets + k, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: bucket reduction tree.  Level input: per window `items` points A (and carried sums V);
+// each thread folds S consecutive items:  A' = sum A_r,  V' = 2^dbls * sum_r r A_r + sum_r V_r.
+// Invariant: sum_b b A0_b = S^level * sum_k k A'_k + sum_k V'_k.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) msm_reduce_level_kernel(const xyzz_t* __restrict__ A,
+                                                                const xyzz_t* __restrict__ V,
+                                                                xyzz_t* __restrict__ A2, xyzz_t* __restrict__ V2,
+                                                                uint32_t items, uint32_t S, uint32_t W,
+                                                                uint32_t dbls) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t groups = items / S;
+    if (t >= groups * W) return;
+    uint32_t w = t / groups, k = t % groups;
+    size_t base = (size_t)w * items + (size_t)k * S;
+    xyzz_t run = xyzz_t::inf(), acc = xyzz_t::inf();
+    for (uint32_t r = S - 1; r >= 1; r--) {
+        xyzz_t q = ld_xyzz(A + base + r);
+        xyzz_add(run, q);
+        xyzz_add(acc, run);
+    }
+    {
+        xyzz_t q = ld_xyzz(A + base);
+        xyzz_add(run, q);
+    }
+    for (uint32_t i = 0; i < dbls; i++) xyzz_dbl(acc);
+    if (V) {
+        for (uint32_t r = 0; r < S; r++) {
+            xyzz_t q = ld_xyzz(V + base + r);
+            xyzz_add(acc, q);
+        }
+    }
+    st_xyzz(A2 + (size_t)w * groups + k, run);
+    st_xyzz(V2 + (size_t)w * groups + k, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: window Horner + output
+// ------------------------------------------------------------------------------------------
+__device__ void write_projective(uint64_t* out, const xyzz_t& p, bool normalise) {
+    fp_t X, Y, Z;
+    if (p.is_inf()) {  // identity (0, 1, 0)  g1.rs:605-611
+        X = fp_t::zero();
+        Y = fp_t::one();
+        Z = fp_t::zero();
+    } else if (normalise) {
+        affine_t a = xyzz_to_affine(p);
+        X = a.x;
+        Y = a.y;
+        Z = fp_t::one();
+    } else {  // x = X/ZZ, y = Y/ZZZ  ->  (X ZZZ : Y ZZ : ZZ ZZZ)
+        X = mul(p.X, p.ZZZ);
+        Y = mul(p.Y, p.ZZ);
+        Z = mul(p.ZZ, p.ZZZ);
+    }
+    uint32_t* o = reinterpret_cast<uint32_t*>(out);
+    for (int i = 0; i < 12; i++) {
+        o[i] = X.l[i];
+        o[12 + i] = Y.l[i];
+        o[24 + i] = Z.l[i];
+    }
+}
+
+__global__ void msm_finalize_kernel(const xyzz_t* A, const xyzz_t* V, uint32_t W, uint32_t c, int normalise,
+                                    uint64_t* out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    xyzz_t acc = xyzz_t::inf();
+    for (int w = (int)W - 1; w >= 0; w--) {
+        for (uint32_t i = 0; i < c; i++) xyzz_dbl(acc);
+        xyzz_t tw = ld_xyzz(V + w);  // sum_b b B_b
+        xyzz_t g = ld_xyzz(A + w);   // sum_b B_b
+        xyzz_add(tw, g);
+        xyzz_add(acc, tw);
+    }
+    write_projective(out, acc, normalise != 0);
+}
+
+// sum of n homogeneous projective points (X:Y:Z), normalised output
+__global__ void g1_sum_kernel(const uint64_t* pts, uint32_t n, uint64_t* out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    xyzz_t acc = xyzz_t::inf();
+    for (uint32_t i = 0; i < n; i++) {
+        const fp_t* p = reinterpret_cast<const fp_t*>(pts + 18 * (size_t)i);
+        fp_t X = ld_fp(p), Y = ld_fp(p + 1), Z = ld_fp(p + 2);
+        if (Z.is_zero()) continue;
+        xyzz_t q;  // x = X/Z = XZ/Z^2, y = Y/Z = YZ^2/Z^3
+        q.ZZ = sqr(Z);
+        q.ZZZ = mul(q.ZZ, Z);
+        q.X = mul(X, Z);
+        q.Y = mul(Y, q.ZZ);
+        xyzz_add(acc, q);
+    }
+    write_projective(out, acc, true);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static uint32_t pick_window(bpk_ctx* ctx, size_t n) {
+    if (ctx->opt_msm_window >= 2 && ctx->opt_msm_window <= 22) return (uint32_t)ctx->opt_msm_window;
+    double best = 1e300;
+    uint32_t best_c = 4;
+    for (uint32_t c = 3; c <= 16; c++) {
+        uint32_t W = (256 + c - 1) / c;
+        // pair additions + bucket-tree additions (full adds ~1.5x a mixed add, 3 per bucket) + a latency
+        // term for the serial depth of the tree / Horner tail expressed in pair-addition equivalents
+        double cost = (double)W * ((double)n + 4.5 * (double)(1u << (c - 1))) + 2000.0 * c;
+        if (cost < best) {
+            best = cost;
+            best_c = c;
+        }
+    }
+    return best_c;
+}
+
+int msm_run(bpk_ctx* ctx, const affine_t* d_points, const fr_t* d_scalars, size_t n, unsigned rshift,
+            bool normalise, uint64_t* d_out) {
+    if (n >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
+    if (n == 0) {  // empty sum: identity (0, R, 0)
+        xyzz_t* zero;
+        BPK_TRY(ws_reserve(ctx, 5, 2 * sizeof(xyzz_t), (void**)&zero));
+        BPK_CUDA(cudaMemsetAsync(zero, 0, 2 * sizeof(xyzz_t), ctx->stream));
+        msm_finalize_kernel<<<1, 1, 0, ctx->stream>>>(zero, zero + 1, 1, 1, 1, d_out);
+        count_launch(ctx);
+        BPK_CUDA(cudaGetLastError());
+        return BPK_OK;
+    }
+    const uint32_t c = pick_window(ctx, n);
+    const uint32_t W = (256 + c - 1) / c;
+    const uint32_t half = 1u << (c - 1);
+    const uint32_t nb_total = W * half;
+    const size_t M = (size_t)W * n;
+    if (M >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
+
+    // workspace carve-up
+    uint32_t *keys_in, *vals_in, *keys_out, *vals_out;
+    {
+        void* base;
+        BPK_TRY(ws_reserve(ctx, 2, 4 * M * sizeof(uint32_t), &base));
+        keys_in = (uint32_t*)base;
+        vals_in = keys_in + M;
+        keys_out = vals_in + M;
+        vals_out = keys_out + M;
+    }
+    int end_bit = 1;
+    while (((uint64_t)1 << end_bit) <= nb_total) end_bit++;  // INVALID keys only need to sort last
+    // INVALID_KEY = 0xffffffff has all low bits set, so within end_bit bits it is >= every valid key
+    size_t sort_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_in, keys_out, vals_in, vals_out, (int)M, 0, end_bit,
+                                    ctx->stream);
+    void* sort_tmp;
+    BPK_TRY(ws_reserve(ctx, 3, sort_bytes, &sort_tmp));
+
+    uint32_t chunk = (uint32_t)ctx->opt_msm_chunk;
+    if (chunk == 0) {
+        size_t target = M / ((size_t)ctx->sm_count * 2048);
+        chunk = (uint32_t)(target < 16 ? 16 : (target > 256 ? 256 : target));
+    }
+    const size_t num_chunks = (M + chunk - 1) / chunk;
+
+    xyzz_t* buckets;
+    BPK_TRY(ws_reserve(ctx, 4, (size_t)nb_total * sizeof(xyzz_t), (void**)&buckets));
+    uint32_t* pkeys;
+    xyzz_t* pvals;
+    {
+        void* base;
+        size_t pv_bytes = 2 * num_chunks * sizeof(xyzz_t);
+        BPK_TRY(ws_reserve(ctx, 5, pv_bytes + 2 * num_chunks * sizeof(uint32_t), &base));
+        pvals = (xyzz_t*)base;
+        pkeys = (uint32_t*)((char*)base + pv_bytes);
+    }
+
+    {
+        StageTimer t(ctx, "msm.recode");
+        msm_recode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_scalars, (uint32_t)n, c, W, rshift,
+                                                                               keys_in, vals_in);
+        count_launch(ctx);
+        BPK_CUDA(cudaGetLastError());
+        t.end();
+    }
+    {
+        StageTimer t(ctx, "msm.sort");
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys_in, keys_out, vals_in, vals_out,
+                                                        (int)M, 0, end_bit, ctx->stream);
+        BPK_CUDA(e);
+        count_launch(ctx, 1 + (uint64_t)((end_bit + 7) / 8));
+        t.end();
+    }
+    {
+        StageTimer t(ctx, "msm.accumulate");
+        BPK_CUDA(cudaMemsetAsync(buckets, 0, (size_t)nb_total * sizeof(xyzz_t), ctx->stream));
+        msm_accumulate_kernel<<<(unsigned)((num_chunks + 127) / 128), 128, 0, ctx->stream>>>(
+            keys_out, vals_out, M, chunk, num_chunks, d_points, nb_total, buckets, pkeys, pvals);
+        count_launch(ctx);
+        BPK_CUDA(cudaGetLastError());
+        t.end();
+    }
+    {
+        StageTimer t(ctx, "msm.merge");
+        msm_merge_partials_kernel<<<(unsigned)((num_chunks + 127) / 128), 128, 0, ctx->stream>>>(pkeys, pvals,
+                                                                                              num_chunks, buckets);
+        count_launch(ctx);
+        BPK_CUDA(cudaGetLastError());
+        t.end();
+    }
+    // reduction tree: fold 2^5 items per thread per level
+    const xyzz_t* A = buckets;
+    const xyzz_t* V = nullptr;
+    {
+        StageTimer t(ctx, "msm.reduce");
+        xyzz_t* lvl;
+        // level outputs: items/32 (+ /1024 + ...) per window, A and V each; 2 * nb_total/16 is ample
+        size_t lvl_elems = (size_t)W * (half / 2 + 64);
+        BPK_TRY(ws_reserve(ctx, 6, 2 * lvl_elems * sizeof(xyzz_t), (void**)&lvl));
+        uint32_t items = half;
+        uint32_t dbls = 0;
+        size_t off = 0;
+        while (items > 1) {
+            uint32_t S = items >= 32 ? 32 : items;
+            uint32_t groups = items / S;
+            xyzz_t* A2 = lvl + off;
+            xyzz_t* V2 = lvl + off + (size_t)W * groups;
+            off += 2 * (size_t)W * groups;
+            uint32_t threads = W * groups;
+            msm_reduce_level_kernel<<<(threads + 127) / 128, 128, 0, ctx->stream>>>(A, V, A2, V2, items, S, W, dbls);
+            count_launch(ctx);
+            BPK_CUDA(cudaGetLastError());
+            A = A2;
+            V = V2;
+            uint32_t logS = 0;
+            while ((1u << logS) < S) logS++;
+            dbls += logS;
+            items = groups;
+        }
+        if (V == nullptr) {  // c == 1: a single bucket per window, weight 1, no tree level ran
+            xyzz_t* z = lvl + off;
+            BPK_CUDA(cudaMemsetAsync(z, 0, (size_t)W * sizeof(xyzz_t), ctx->stream));
+            V = z;
+        }
+        t.end();
+    }
+    {
+        StageTimer t(ctx, "msm.finalize");
+        msm_finalize_kernel<<<1, 1, 0, ctx->stream>>>(A, V, W, c, normalise ? 1 : 0, d_out);
+        count_launch(ctx);
+        BPK_CUDA(cudaGetLastError());
+        t.end();
+    }
+    return BPK_OK;
+}
+
+int g1_sum_run(bpk_ctx* ctx, const uint64_t* d_points_xyz, size_t n, uint64_t* d_out_xyz) {
+    StageTimer t(ctx, "g1.sum");
+    g1_sum_kernel<<<1, 1, 0, ctx->stream>>>(d_points_xyz, (uint32_t)n, d_out_xyz);
+    count_launch(ctx);
+    BPK_CUDA(cudaGetLastError());
+    t.end();
+    return BPK_OK;
+}
+
+}  // namespace bpk

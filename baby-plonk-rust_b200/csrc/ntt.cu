@@ -1,0 +1,319 @@
+// Fr NTT / iNTT / coset NTT for sm_100a.
+//
+// Contract = the reference's naive DFT (src/utils.rs:63-81 ntt_381, :106-129 i_ntt_381):
+//   out[i] = sum_j in[j] * w^(i j),  w = ROOT_OF_UNITY^(2^32 / n)  (inverse: w^-1 and a final n^-1),
+// natural order in and out.  Field values are canonical Montgomery residues, so any correct
+// algorithm is bit-identical to the O(n^2) reference.
+//
+// Algorithm: multi-pass Stockham autosort.  A pass with radix R = 2^logR and Ns = product of the
+// previous radices maps, for every column j < n/R,
+//     v[r]   = in[j + r n/R] * w_{Ns R}^{(j mod Ns) r}          (inter-pass twiddle)
+//     V      = DFT_R(v)                                          (shared memory, radix-2 DIT)
+//     out[(j / Ns) Ns R + (j mod Ns) + r Ns] = V[r]
+// A CTA owns a tile of C consecutive columns (R x C elements staged in shared memory, split into
+// two 16-byte planes so 128-bit shared accesses are conflict-free); global reads are C*32-byte
+// runs, global writes are C*32-byte runs (Ns >= C) or R*32-byte runs (first pass).  Inter-pass
+// twiddles come from a two-level table of the primitive 2^28-th root (2 x 8192.. entries, L2/L1
+// resident); sub-FFT twiddles w_R^i are staged in shared memory per CTA.
+// Algorithmic traffic: 64 n bytes per transform; this schedule moves 64 n bytes per pass.
+// (oracle/prototypes/stockham_proto.py is the CPU prototype of exactly this index logic.)
+#include "internal.cuh"
+
+namespace bpk {
+
+struct NttPassParams {
+    const fr_t* in;
+    fr_t* out;
+    const fr_t* tw_lo;
+    const fr_t* tw_hi;
+    const fr_t* cs_lo;  // coset tables (or null)
+    const fr_t* cs_hi;
+    uint32_t logn, logR, logC, logNs;
+    int coset_in;   // multiply input element i by cs(i)
+    int scale_out;  // 0: none, 1: multiply outputs by `scale`, 2: multiply output i by cs(i)
+    fr_t scale;
+};
+
+__device__ __forceinline__ fr_t ld_fr(const fr_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    fr_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_fr(fr_t* p, const fr_t& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+__device__ __forceinline__ fr_t ld_sm(const uint4* lo, const uint4* hi, uint32_t i) {
+    uint4 a = lo[i], b = hi[i];
+    fr_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_sm(uint4* lo, uint4* hi, uint32_t i, const fr_t& v) {
+    lo[i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    hi[i] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+// element E of a two-level power table: lo[E & mask] * hi[E >> TW_LO_BITS]
+__device__ __forceinline__ fr_t table_pow(const fr_t* lo, const fr_t* hi, uint32_t E) {
+    fr_t a = ld_fr(lo + (E & ((1u << TW_LO_BITS) - 1)));
+    uint32_t h = E >> TW_LO_BITS;
+    if (h == 0) return a;  // warp-divergent only at table boundaries; saves a multiply for small E
+    return mul(a, ld_fr(hi + h));
+}
+
+__global__ void __launch_bounds__(256) ntt_pass_kernel(NttPassParams p) {
+    extern __shared__ uint4 smem[];
+    const uint32_t logR = p.logR, logC = p.logC, logNs = p.logNs;
+    const uint32_t R = 1u << logR, C = 1u << logC, RC = R << logC;
+    uint4* s_lo = smem;
+    uint4* s_hi = smem + RC;
+    uint4* t_lo = smem + 2 * RC;
+    uint4* t_hi = t_lo + (R >> 1);
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const size_t n = (size_t)1 << p.logn;
+    const fr_t* in = p.in + (size_t)blockIdx.y * n;
+    fr_t* out = p.out + (size_t)blockIdx.y * n;
+    const uint32_t j0 = blockIdx.x << logC;
+
+    // sub-FFT twiddles w_R^i, i < R/2
+    for (uint32_t i = tid; i < (R >> 1); i += nt) {
+        fr_t w = table_pow(p.tw_lo, p.tw_hi, i << (NTT_MAX_LOG - logR));
+        st_sm(t_lo, t_hi, i, w);
+    }
+    // load tile, apply coset shift and inter-pass twiddle, place rows bit-reversed
+    const uint32_t stride_in = (uint32_t)(n >> logR);
+    const uint32_t tw_shift = NTT_MAX_LOG - (logNs + logR);
+    const uint32_t ns_mask = (1u << logNs) - 1;
+    for (uint32_t idx = tid; idx < RC; idx += nt) {
+        uint32_t c = idx & (C - 1), r = idx >> logC;
+        uint32_t j = j0 + c;
+        uint32_t g = j + r * stride_in;
+        fr_t v = ld_fr(in + g);
+        if (p.coset_in) v = mul(v, table_pow(p.cs_lo, p.cs_hi, g));
+        if (logNs) {
+            uint32_t k = j & ns_mask;
+            v = mul(v, table_pow(p.tw_lo, p.tw_hi, (k * r) << tw_shift));
+        }
+        uint32_t rr = __brev(r) >> (32 - logR);
+        if (logR == 0) rr = 0;
+        st_sm(s_lo, s_hi, (rr << logC) + c, v);
+    }
+    __syncthreads();
+    // radix-2 DIT stages, natural-order output
+    const uint32_t nbf = RC >> 1;
+    for (uint32_t s = 1; s <= logR; s++) {
+        const uint32_t half = 1u << (s - 1);
+        for (uint32_t idx = tid; idx < nbf; idx += nt) {
+            uint32_t c = idx & (C - 1), b = idx >> logC;
+            uint32_t lowb = b & (half - 1);
+            uint32_t i = ((b >> (s - 1)) << s) | lowb;
+            uint32_t i0 = (i << logC) + c, i1 = ((i + half) << logC) + c;
+            fr_t w = ld_sm(t_lo, t_hi, lowb << (logR - s));
+            fr_t u = ld_sm(s_lo, s_hi, i0);
+            fr_t t = mul(ld_sm(s_lo, s_hi, i1), w);
+            st_sm(s_lo, s_hi, i0, add(u, t));
+            st_sm(s_lo, s_hi, i1, sub(u, t));
+        }
+        __syncthreads();
+    }
+    // store
+    for (uint32_t idx = tid; idx < RC; idx += nt) {
+        uint32_t c, r;
+        size_t o;
+        if (logNs == 0) {  // first pass: each column writes R consecutive outputs
+            r = idx & (R - 1);
+            c = idx >> logR;
+            o = ((size_t)(j0 + c) << logR) + r;
+        } else {
+            c = idx & (C - 1);
+            r = idx >> logC;
+            uint32_t j = j0 + c;
+            o = ((size_t)(j >> logNs) << (logNs + logR)) + (j & ns_mask) + ((size_t)r << logNs);
+        }
+        fr_t v = ld_sm(s_lo, s_hi, (r << logC) + c);
+        if (p.scale_out == 1) v = mul(v, p.scale);
+        else if (p.scale_out == 2) v = mul(v, table_pow(p.cs_lo, p.cs_hi, (uint32_t)o));
+        st_fr(out + o, v);
+    }
+}
+
+// out[i] = pre * base^(i << shift)
+__global__ void pow_table_kernel(fr_t* out, fr_t base, fr_t pre, uint32_t count, uint32_t shift) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    fr_t v = pow_u64(base, (uint64_t)i << shift);
+    st_fr(out + i, mul(v, pre));
+}
+
+__global__ void pointwise_mul_kernel(fr_t* a, const fr_t* b, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t step = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += step) st_fr(a + i, mul(ld_fr(a + i), ld_fr(b + i)));
+}
+
+__global__ void scale_kernel(fr_t* a, fr_t s, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t step = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += step) st_fr(a + i, mul(ld_fr(a + i), s));
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static fr_t fr_from_u64x4(const uint64_t v[4]) {
+    fr_t r;
+    for (int i = 0; i < 4; i++) {
+        r.l[2 * i] = (uint32_t)v[i];
+        r.l[2 * i + 1] = (uint32_t)(v[i] >> 32);
+    }
+    return r;
+}
+static fr_t fr_from_small(uint64_t x) {  // canonical small integer -> Montgomery (host templates)
+    fr_t r = fr_t::zero();
+    r.l[0] = (uint32_t)x;
+    r.l[1] = (uint32_t)(x >> 32);
+    return to_mont(r);
+}
+
+// scalar.rs:208-213 ROOT_OF_UNITY (Montgomery limbs), a primitive 2^32-th root of unity
+static const uint64_t ROOT_OF_UNITY_MONT[4] = {0xb9b58d8c5f0e466aull, 0x5b1b4c801819d7ecull,
+                                               0x0af53ae352a31e64ull, 0x5bf3adda19e9b27bull};
+
+static int launch_pow_table(bpk_ctx* ctx, fr_t* d_out, const fr_t& base, const fr_t& pre, uint32_t count,
+                            uint32_t shift) {
+    pow_table_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(d_out, base, pre, count, shift);
+    count_launch(ctx);
+    BPK_CUDA(cudaGetLastError());
+    return BPK_OK;
+}
+
+int ntt_init_tables(bpk_ctx* ctx) {
+    fr_t root = fr_from_u64x4(ROOT_OF_UNITY_MONT);
+    for (int i = 0; i < 32 - NTT_MAX_LOG; i++) root = sqr(root);  // primitive 2^NTT_MAX_LOG-th root
+    fr_t roots[2] = {root, inv(root)};
+    BPK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    for (int d = 0; d < 2; d++) {
+        BPK_CUDA(cudaMalloc(&ctx->tw_lo[d], sizeof(fr_t) << TW_LO_BITS));
+        BPK_CUDA(cudaMalloc(&ctx->tw_hi[d], sizeof(fr_t) << TW_HI_BITS));
+        BPK_CUDA(cudaMalloc(&ctx->coset_lo[d], sizeof(fr_t) << TW_LO_BITS));
+        BPK_CUDA(cudaMalloc(&ctx->coset_hi[d], sizeof(fr_t) << TW_HI_BITS));
+        BPK_TRY(launch_pow_table(ctx, ctx->tw_lo[d], roots[d], fr_t::one(), 1u << TW_LO_BITS, 0));
+        BPK_TRY(launch_pow_table(ctx, ctx->tw_hi[d], roots[d], fr_t::one(), 1u << TW_HI_BITS, TW_LO_BITS));
+    }
+    BPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BPK_OK;
+}
+
+static void plan_passes(uint32_t logn, uint32_t max_logR, std::vector<uint32_t>& out) {
+    out.clear();
+    if (logn == 0) return;
+    uint32_t passes = (logn + max_logR - 1) / max_logR;
+    uint32_t rem = logn;
+    for (uint32_t i = 0; i < passes; i++) {
+        uint32_t left = passes - i;
+        uint32_t a = (rem + left - 1) / left;
+        out.push_back(a);
+        rem -= a;
+    }
+}
+
+int ntt_run(bpk_ctx* ctx, const fr_t* d_in, fr_t* d_out, size_t n, size_t batch, bool inverse,
+            const fr_t* shift) {
+    if (n == 0 || (n & (n - 1)) != 0) return BPK_ERR_NOT_POW2;
+    uint32_t logn = 0;
+    while (((size_t)1 << logn) < n) logn++;
+    if (logn > (uint32_t)NTT_MAX_LOG) return BPK_ERR_TOO_LARGE;
+    if (batch == 0) return BPK_OK;
+    if (batch > 65535) return BPK_ERR_TOO_LARGE;
+    const int dir = inverse ? 1 : 0;
+    const size_t bytes = n * batch * sizeof(fr_t);
+
+    // n^-1 (inverse) and coset tables
+    fr_t scale = fr_t::one();
+    if (inverse) scale = inv(fr_from_small((uint64_t)n));
+    if (shift) {
+        // the inverse table folds n^-1 into its low half, so it is keyed by (shift, n)
+        bool need = !ctx->coset_valid[dir] || ctx->coset_shift[dir] != *shift || (inverse && ctx->coset_n != n);
+        if (need) {
+            StageTimer t(ctx, "ntt.coset_table");
+            fr_t g = inverse ? inv(*shift) : *shift;
+            BPK_TRY(launch_pow_table(ctx, ctx->coset_lo[dir], g, scale, 1u << TW_LO_BITS, 0));
+            BPK_TRY(launch_pow_table(ctx, ctx->coset_hi[dir], g, fr_t::one(), 1u << TW_HI_BITS, TW_LO_BITS));
+            ctx->coset_shift[dir] = *shift;
+            ctx->coset_valid[dir] = true;
+            if (inverse) ctx->coset_n = n;
+            t.end();
+        }
+    }
+
+    if (logn == 0) {  // n == 1: the transform is the identity (times n^-1 = 1; coset factor g^0 = 1)
+        if (d_in != d_out) BPK_CUDA(cudaMemcpyAsync(d_out, d_in, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        return BPK_OK;
+    }
+
+    const uint32_t tile_log = (uint32_t)ctx->opt_ntt_tile_log2;  // log2(R * C)
+    const uint32_t max_logR = tile_log > 10 ? 10 : tile_log;
+    std::vector<uint32_t> plan;
+    plan_passes(logn, max_logR, plan);
+    const size_t np = plan.size();
+
+    fr_t* tmp[2] = {nullptr, nullptr};
+    if (np >= 2) BPK_TRY(ws_reserve(ctx, 0, bytes, (void**)&tmp[0]));
+    if (np >= 3) BPK_TRY(ws_reserve(ctx, 1, bytes, (void**)&tmp[1]));
+
+    StageTimer t(ctx, "ntt.pass");
+    uint32_t logNs = 0;
+    const fr_t* src = d_in;
+    for (size_t pi = 0; pi < np; pi++) {
+        uint32_t logR = plan[pi];
+        uint32_t logC = tile_log - logR;
+        if (logC > logn - logR) logC = logn - logR;
+        if (logNs && logC > logNs) logC = logNs;
+        fr_t* dst = (pi + 1 == np) ? d_out : tmp[pi & 1];
+        NttPassParams p;
+        p.in = src;
+        p.out = dst;
+        p.tw_lo = ctx->tw_lo[dir];
+        p.tw_hi = ctx->tw_hi[dir];
+        p.cs_lo = ctx->coset_lo[dir];
+        p.cs_hi = ctx->coset_hi[dir];
+        p.logn = logn;
+        p.logR = logR;
+        p.logC = logC;
+        p.logNs = logNs;
+        p.coset_in = (shift && !inverse && pi == 0) ? 1 : 0;
+        p.scale_out = 0;
+        p.scale = scale;
+        if (pi + 1 == np && inverse) p.scale_out = shift ? 2 : 1;
+        size_t smem = ((size_t)2 << (logR + logC)) * sizeof(uint4) + ((size_t)1 << logR) * sizeof(uint4);
+        if (smem > 200 * 1024) return BPK_ERR_INVALID_ARG;
+        dim3 grid((unsigned)(n >> (logR + logC)), (unsigned)batch);
+        ntt_pass_kernel<<<grid, 256, smem, ctx->stream>>>(p);
+        count_launch(ctx);
+        BPK_CUDA(cudaGetLastError());
+        src = dst;
+        logNs += logR;
+    }
+    t.end();
+    return BPK_OK;
+}
+
+int pointwise_mul(bpk_ctx* ctx, fr_t* d_a, const fr_t* d_b, size_t n) {
+    StageTimer t(ctx, "fr.pointwise");
+    size_t blocks = (n + 255) / 256;
+    size_t cap = (size_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    pointwise_mul_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_a, d_b, n);
+    count_launch(ctx);
+    BPK_CUDA(cudaGetLastError());
+    t.end();
+    return BPK_OK;
+}
+
+}  // namespace bpk

@@ -1,0 +1,134 @@
+/* bpk.h -- C ABI of the B200-native MSM / NTT library for baby-plonk-rust.
+ *
+ * The reference (ChainUpZero/baby-plonk-rust) has no FFI; its hot path is reached through three
+ * plain Rust call surfaces.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference root).  A Rust maintainer binds these
+ * with `extern "C"` exactly as INTEGRATION.md shows.
+ *
+ * Data conventions (identical to what Rust holds in memory, so `as_ptr()` is passed unchanged):
+ *   Scalar (Fr)      4 x u64 little-endian limbs, Montgomery form, R = 2^256, value < q
+ *                    (lib/bls12_381/src/scalar.rs:22)
+ *   Fp               6 x u64 limbs, Montgomery, R = 2^384, value < p  (lib/bls12_381/src/fp.rs:15)
+ *   G1Projective     18 x u64: X | Y | Z homogeneous projective, Z == 0 <=> identity
+ *                    (lib/bls12_381/src/g1.rs:442-446, identity (0,1,0) g1.rs:605-611)
+ * Every G1 output is the affine-normalised representative (x, y, 1) or the identity (0, 1, 0), all
+ * in Montgomery form; G1Projective equality in the reference is projective equivalence
+ * (g1.rs:479-496), so Rust-side `==`, the transcript bytes and the verifier see no difference.
+ *
+ * Ownership: the caller owns every buffer; the library never keeps a host pointer after return.
+ * Threading: calls on one context are serialised by the caller (the reference is single-threaded).
+ * Errors: every function returns 0 on success or a negative bpk_status; nothing throws or aborts.
+ * The Rust shim turns a non-zero status into `panic!`, preserving the reference's error behaviour.
+ * There is no CPU fallback: without a CUDA device bpk_init fails with BPK_ERR_NO_DEVICE.
+ */
+#ifndef BPK_H
+#define BPK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bpk_ctx bpk_ctx;
+
+enum bpk_status {
+    BPK_OK = 0,
+    BPK_ERR_NO_DEVICE = -1,    /* no usable CUDA device / wrong architecture */
+    BPK_ERR_CUDA = -2,         /* a CUDA runtime call failed; see bpk_last_error */
+    BPK_ERR_INVALID_ARG = -3,  /* null pointer, bad handle, ... */
+    BPK_ERR_NOT_POW2 = -4,     /* NTT length is not a power of two (utils.rs:65,108 assert!) */
+    BPK_ERR_TOO_LARGE = -5,    /* size beyond the supported range */
+    BPK_ERR_WINDOW = -6,       /* bucket_msm (b, c) the reference itself panics on */
+    BPK_ERR_OOM = -7
+};
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* One context per GPU (one process per GPU in multi-GPU runs).  `device` is the CUDA ordinal. */
+int bpk_init(bpk_ctx** out, int device);
+void bpk_destroy(bpk_ctx* ctx);
+const char* bpk_strerror(int status);
+const char* bpk_last_error(bpk_ctx* ctx); /* text of the last CUDA error seen by this context */
+int bpk_abi_version(void);
+/* Use an existing CUDA stream (cudaStream_t) for all work; NULL = legacy default stream. */
+int bpk_set_stream(bpk_ctx* ctx, void* cuda_stream);
+int bpk_synchronize(bpk_ctx* ctx);
+
+/* ---- SRS (Setup.powers_of_x, src/setup.rs:7-10) --------------------------------------------- */
+/* Upload n projective points (18 u64 each) once per Setup; they are kept on the device in affine
+ * form.  Replaces passing `&self.powers_of_x` on every commit (setup.rs:36). */
+int bpk_srs_load(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n, uint64_t* handle_out);
+/* Setup::generate_srs powers_of_x (setup.rs:12-31): [tau^i] G for i < n, built on the device. */
+int bpk_srs_generate(bpk_ctx* ctx, const uint64_t tau_mont[4], size_t n, uint64_t* handle_out);
+/* Read points [first, first+count) back as normalised G1Projective limbs. */
+int bpk_srs_read(bpk_ctx* ctx, uint64_t handle, size_t first, size_t count, uint64_t* out_xyz);
+int bpk_srs_len(bpk_ctx* ctx, uint64_t handle, size_t* n_out);
+int bpk_srs_free(bpk_ctx* ctx, uint64_t handle);
+
+/* ---- MSM ------------------------------------------------------------------------------------ */
+/* BucketMSM::bucket_msm(points, scalars, b, c) (src/msm.rs:76-118) with points = the SRS behind
+ * `handle`.  Semantics of the reference, exactly: k = b / c windows; the result is
+ * sum_i (s_i >> (256 - k*c)) * P_i over the first min(n_points, n_scalars) pairs (zip truncation,
+ * msm.rs:29); k == 0 or k*c > 256 is a panic in the reference (msm.rs:105,133) and
+ * BPK_ERR_WINDOW here.  For every c dividing 256 -- the only in-tree call is (256, 4),
+ * setup.rs:36 -- this is the plain MSM.  The GPU chooses its own window size. */
+int bpk_bucket_msm(bpk_ctx* ctx, uint64_t handle, const uint64_t* scalars_mont, size_t n_scalars,
+                   size_t b, size_t c, uint64_t out_xyz[18]);
+/* Setup::commit (src/setup.rs:32-37) == bpk_bucket_msm(.., 256, 4). */
+int bpk_msm_g1(bpk_ctx* ctx, uint64_t handle, const uint64_t* scalars_mont, size_t n_scalars,
+               uint64_t out_xyz[18]);
+/* Same with the points passed on every call, as the reference signature does (no device cache). */
+int bpk_msm_g1_points(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n_points,
+                      const uint64_t* scalars_mont, size_t n_scalars, uint64_t out_xyz[18]);
+/* Device-resident variant: scalars already in HBM (device pointer, n x 4 u64 Montgomery), result
+ * written to a device buffer of 18 u64.  `first` selects the SRS slice [first, first + n) so that a
+ * rank of a multi-GPU job can own a shard of the points.  normalise == 0 returns an un-normalised
+ * projective representative (a valid G1Projective) -- the per-rank partial sum that is gathered
+ * over NCCL and added by bpk_g1_sum. */
+int bpk_msm_g1_dev(bpk_ctx* ctx, uint64_t handle, size_t first, const void* d_scalars_mont,
+                   size_t n, int normalise, void* d_out_xyz);
+/* Sum of n projective points (host pointers, 18 u64 each), normalised: the post-gather step. */
+int bpk_g1_sum(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n, uint64_t out_xyz[18]);
+
+/* ---- NTT ------------------------------------------------------------------------------------ */
+/* ntt_381 (src/utils.rs:63-81): out[i] = sum_j in[j] w^(ij), w = ROOT_OF_UNITY^(2^32 / n), natural
+ * order in and out; `batch` independent transforms stored back to back.  n must be a power of two
+ * (else BPK_ERR_NOT_POW2, the reference asserts).  in == out is allowed. */
+int bpk_ntt_fr(bpk_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, size_t batch);
+/* i_ntt_381 (src/utils.rs:106-129): inverse transform, scaled by n^-1. */
+int bpk_intt_fr(bpk_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, size_t batch);
+/* Coset variants (no reference counterpart; used by the quotient pipeline that replaces the
+ * evaluate-on-domain loop of impl Mul, src/polynomial.rs:241-273): forward evaluates the
+ * polynomial on shift * w^i; inverse interpolates from those evaluations. */
+int bpk_coset_ntt_fr(bpk_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, size_t batch,
+                     const uint64_t shift_mont[4]);
+int bpk_coset_intt_fr(bpk_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, size_t batch,
+                      const uint64_t shift_mont[4]);
+/* Device-resident NTT: d_in / d_out are device pointers (may be equal).
+ * flags: bit 0 = inverse, bit 1 = coset (d_shift_mont: HOST pointer to 4 u64, may be NULL). */
+int bpk_ntt_fr_dev(bpk_ctx* ctx, const void* d_in, void* d_out, size_t n, size_t batch, int flags,
+                   const uint64_t* shift_mont);
+/* impl Mul for Polynomial, Monomial x Monomial (src/polynomial.rs:189-273): out has la + lb - 1
+ * coefficients (trailing zeros kept, polynomial.rs:272). la, lb >= 1. */
+int bpk_poly_mul_fr(bpk_ctx* ctx, const uint64_t* a, size_t la, const uint64_t* b, size_t lb,
+                    uint64_t* out);
+
+/* ---- instrumentation (bench.py, tests) -------------------------------------------------------- */
+/* When enabled, every kernel stage is bracketed by CUDA events on the context's stream. */
+int bpk_profile_enable(bpk_ctx* ctx, int on);
+int bpk_profile_reset(bpk_ctx* ctx);
+/* Accumulated device time (ms) and number of kernel launches of stage `name`
+ * ("msm.recode", "msm.sort", "msm.accumulate", "msm.reduce", "msm.finalize", "ntt.pass", ...). */
+int bpk_profile_get(bpk_ctx* ctx, const char* name, double* ms_out, uint64_t* launches_out);
+/* Total kernel launches issued by this context since bpk_profile_reset. */
+uint64_t bpk_launch_count(bpk_ctx* ctx);
+/* Register-only IMAD.WIDE throughput probe: returns 32x32+64 multiply-adds per second. */
+int bpk_imad_peak(bpk_ctx* ctx, double* wide_imad_per_s_out, double* seconds_out);
+/* Tunables: "msm.window" (0 = auto), "msm.chunk", "ntt.tile_log2". */
+int bpk_set_option(bpk_ctx* ctx, const char* key, long value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPK_H */
