@@ -68,6 +68,8 @@ _SIGNATURES = {
     "bpk_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
     "bpk_srs_load": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64)]),
     "bpk_srs_generate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64)]),
+    "bpk_srs_generate_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                              ctypes.POINTER(ctypes.c_uint64)]),
     "bpk_srs_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p]),
     "bpk_srs_len": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_size_t)]),
     "bpk_srs_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64]),
@@ -79,6 +81,7 @@ _SIGNATURES = {
     "bpk_msm_g1_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_void_p,
                                       ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
     "bpk_g1_sum": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "bpk_g1_sum_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "bpk_ntt_fr": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t]),
     "bpk_intt_fr": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t]),
     "bpk_coset_ntt_fr": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
@@ -426,12 +429,14 @@ class Setup:
         self.n = n
 
     @classmethod
-    def generate_srs(cls, powers: int, tau: int, ctx: Optional[Context] = None) -> "Setup":
-        """setup.rs:12-31: [tau^i]G for i < powers (G2 part stays with the CPU verifier, out of scope)"""
+    def generate_srs(cls, powers: int, tau: int, ctx: Optional[Context] = None, first: int = 0) -> "Setup":
+        """setup.rs:12-31: [tau^i]G for first <= i < first + powers (first != 0: the shard one rank of a
+        multi-GPU job owns).  The G2 part stays with the CPU verifier (out of scope)."""
         ctx = ctx or get_context()
         t = scalars_from_ints([tau])
         h = ctypes.c_uint64()
-        ctx.check(ctx.lib.bpk_srs_generate(ctx.handle, t.ctypes.data, powers, ctypes.byref(h)), "bpk_srs_generate")
+        ctx.check(ctx.lib.bpk_srs_generate_range(ctx.handle, t.ctypes.data, first, powers, ctypes.byref(h)),
+                  "bpk_srs_generate_range")
         return cls(ctx, h.value, powers)
 
     @classmethod

@@ -268,11 +268,16 @@ extern "C" int bpk_srs_load(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n, 
 }
 
 extern "C" int bpk_srs_generate(bpk_ctx* ctx, const uint64_t tau_mont[4], size_t n, uint64_t* handle_out) {
+    return bpk_srs_generate_range(ctx, tau_mont, 0, n, handle_out);
+}
+
+extern "C" int bpk_srs_generate_range(bpk_ctx* ctx, const uint64_t tau_mont[4], size_t first, size_t n,
+                                      uint64_t* handle_out) {
     if (!ctx || !handle_out || !tau_mont) return BPK_ERR_INVALID_ARG;
     BPK_CUDA(cudaSetDevice(ctx->device));
     affine_t* pts = nullptr;
     BPK_CUDA(cudaMalloc(&pts, (n ? n : 1) * sizeof(affine_t)));
-    int s = srs_generate(ctx, fr_from_host(tau_mont), n, pts);
+    int s = srs_generate(ctx, fr_from_host(tau_mont), first, n, pts);
     if (s == BPK_OK) {
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) s = cuda_fail(ctx, e, "srs generate", __FILE__, __LINE__);
@@ -391,6 +396,12 @@ extern "C" int bpk_g1_sum(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n, ui
     BPK_CUDA(cudaMemcpyAsync(out_xyz, d_out, 18 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     BPK_CUDA(cudaStreamSynchronize(ctx->stream));
     return BPK_OK;
+}
+
+extern "C" int bpk_g1_sum_dev(bpk_ctx* ctx, const void* d_points_xyz, size_t n, void* d_out_xyz) {
+    if (!ctx || !d_out_xyz || (n && !d_points_xyz) || n > (1u << 20)) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    return g1_sum_run(ctx, (const uint64_t*)d_points_xyz, n, (uint64_t*)d_out_xyz);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -124,7 +124,7 @@ int g1_sum_run(bpk_ctx* ctx, const uint64_t* d_points_xyz, size_t n, uint64_t* d
 // ---- srs.cu ----
 int srs_from_projective(bpk_ctx* ctx, const uint64_t* d_xyz, size_t n, affine_t* d_out);
 int srs_to_projective(bpk_ctx* ctx, const affine_t* d_pts, size_t n, uint64_t* d_xyz);
-int srs_generate(bpk_ctx* ctx, const fr_t& tau, size_t n, affine_t* d_out);
+int srs_generate(bpk_ctx* ctx, const fr_t& tau, size_t first, size_t n, affine_t* d_out);
 
 // ---- misc ----
 int imad_peak_run(bpk_ctx* ctx, double* rate, double* seconds);

@@ -98,11 +98,11 @@ __global__ void xyzz_to_affine_kernel(const xyzz_t* in, size_t n, affine_t* out)
 }
 
 // out[i] = [tau^i] G
-__global__ void __launch_bounds__(128) srs_generate_kernel(const affine_t* __restrict__ table, fr_t tau, size_t n,
-                                                            affine_t* __restrict__ out) {
+__global__ void __launch_bounds__(128) srs_generate_kernel(const affine_t* __restrict__ table, fr_t tau, size_t first,
+                                                            size_t n, affine_t* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fr_t e = from_mont(pow_u64(tau, (uint64_t)i));  // canonical tau^i
+    fr_t e = from_mont(pow_u64(tau, (uint64_t)(first + i)));  // canonical tau^(first + i)
     xyzz_t acc = xyzz_t::inf();
 #pragma unroll 1
     for (uint32_t k = 0; k < 32; k++) {
@@ -142,7 +142,7 @@ int srs_to_projective(bpk_ctx* ctx, const affine_t* d_pts, size_t n, uint64_t* d
     return BPK_OK;
 }
 
-int srs_generate(bpk_ctx* ctx, const fr_t& tau, size_t n, affine_t* d_out) {
+int srs_generate(bpk_ctx* ctx, const fr_t& tau, size_t first, size_t n, affine_t* d_out) {
     if (ctx->gen_table == nullptr) {
         StageTimer t(ctx, "srs.gen_table");
         xyzz_t* tmp;
@@ -160,7 +160,7 @@ int srs_generate(bpk_ctx* ctx, const fr_t& tau, size_t n, affine_t* d_out) {
     }
     if (n == 0) return BPK_OK;
     StageTimer t(ctx, "srs.generate");
-    srs_generate_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->gen_table, tau, n, d_out);
+    srs_generate_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->gen_table, tau, first, n, d_out);
     count_launch(ctx);
     BPK_CUDA(cudaGetLastError());
     t.end();

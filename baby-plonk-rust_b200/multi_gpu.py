@@ -1,0 +1,89 @@
+"""Sharded MSM across the GPUs of one box: one process per GPU, torch.distributed for the plumbing.
+
+The MSM sum_i s_i P_i shards by index range: rank r of R owns pairs
+[r N / R, (r+1) N / R) -- its slice of the SRS stays resident on its GPU -- and produces ONE
+partial G1 point (18 u64, un-normalised projective).  The only exchange on the data path is an
+all-gather of R x 144 bytes (NCCL over NVLink / NVSwitch on GPUs, gloo in the CPU tests); every
+rank then adds the R partials and normalises.  The message is latency-bound (~1 kB), so there is
+nothing for a fused compute+collective kernel to overlap; NTTs do not shard ("replicas only":
+independent polynomials of a round are dealt to different GPUs).
+
+`compute_partial` and `sum_points` are injectable so the host-side logic (bounds, gather order,
+result replication) is testable on CPU with world_size 2 over gloo.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+
+def shard_bounds(n: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """index range [lo, hi) of rank `rank`; ranges tile [0, n) in rank order, sizes differ by <= 1"""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad rank / world_size")
+    lo = n * rank // world_size
+    hi = n * (rank + 1) // world_size
+    return lo, hi
+
+
+def all_gather_points(partial, group=None):
+    """gather one 18-limb point per rank -> tensor [world, 18] in rank order (int64 carrier dtype)"""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    partial = partial.reshape(18).contiguous()
+    out = torch.empty((world, 18), dtype=partial.dtype, device=partial.device)
+    dist.all_gather_into_tensor(out.view(-1), partial, group=group)
+    return out
+
+
+def sharded_msm(partial, sum_points: Callable, group=None):
+    """partial: this rank's partial sum as an int64[18] tensor (bit pattern of the u64 limbs), on the
+    device the process group communicates on.  Returns sum_points(gathered [world, 18])."""
+    gathered = all_gather_points(partial, group)
+    return sum_points(gathered)
+
+
+class ShardedCommitter:
+    """Per-rank state of a sharded KZG commitment: SRS slice on this GPU + reusable device buffers."""
+
+    def __init__(self, pkg, ctx, n_total: int, tau: int, rank: int, world_size: int, group=None):
+        import torch
+
+        self.pkg, self.ctx, self.group = pkg, ctx, group
+        self.rank, self.world = rank, world_size
+        self.lo, self.hi = shard_bounds(n_total, world_size, rank)
+        self.setup = pkg.Setup.generate_srs(self.hi - self.lo, tau, ctx, first=self.lo)
+        self.device = torch.device("cuda", ctx.device)
+        self.d_partial = torch.zeros(18, dtype=torch.int64, device=self.device)
+        self.d_out = torch.zeros(18, dtype=torch.int64, device=self.device)
+        self.d_gather = torch.zeros((world_size, 18), dtype=torch.int64, device=self.device)
+
+    def commit_device(self, d_scalars) -> "torch.Tensor":
+        """d_scalars: int64 tensor holding this rank's (hi - lo) x 4 u64 Montgomery limbs in HBM.
+        Returns the normalised commitment (int64[18] on the device), identical on every rank."""
+        import torch.distributed as dist
+
+        lib, h = self.ctx.lib, self.ctx.handle
+        n = self.hi - self.lo
+        if self.world == 1:
+            self.ctx.check(lib.bpk_msm_g1_dev(h, self.setup.handle, 0, d_scalars.data_ptr(), n, 1,
+                                              self.d_out.data_ptr()), "bpk_msm_g1_dev")
+            return self.d_out
+        self.ctx.check(lib.bpk_msm_g1_dev(h, self.setup.handle, 0, d_scalars.data_ptr(), n, 0,
+                                          self.d_partial.data_ptr()), "bpk_msm_g1_dev")
+        dist.all_gather_into_tensor(self.d_gather.view(-1), self.d_partial, group=self.group)
+        self.ctx.check(lib.bpk_g1_sum_dev(h, self.d_gather.data_ptr(), self.world, self.d_out.data_ptr()),
+                       "bpk_g1_sum_dev")
+        return self.d_out
+
+    def commit_host(self, scalars: np.ndarray, d_staging) -> np.ndarray:
+        """end-to-end: this rank's scalars in (pinned) host memory -> H2D -> sharded MSM -> D2H."""
+        import torch
+
+        src = torch.from_numpy(scalars.view(np.int64).reshape(-1))
+        d_staging[: src.numel()].copy_(src, non_blocking=True)
+        out = self.commit_device(d_staging)
+        return out.cpu().numpy().view(np.uint64)

@@ -61,6 +61,9 @@ int bpk_synchronize(bpk_ctx* ctx);
 int bpk_srs_load(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n, uint64_t* handle_out);
 /* Setup::generate_srs powers_of_x (setup.rs:12-31): [tau^i] G for i < n, built on the device. */
 int bpk_srs_generate(bpk_ctx* ctx, const uint64_t tau_mont[4], size_t n, uint64_t* handle_out);
+/* The slice [tau^i] G for first <= i < first + n: the shard of the SRS one rank of a multi-GPU job owns. */
+int bpk_srs_generate_range(bpk_ctx* ctx, const uint64_t tau_mont[4], size_t first, size_t n,
+                           uint64_t* handle_out);
 /* Read points [first, first+count) back as normalised G1Projective limbs. */
 int bpk_srs_read(bpk_ctx* ctx, uint64_t handle, size_t first, size_t count, uint64_t* out_xyz);
 int bpk_srs_len(bpk_ctx* ctx, uint64_t handle, size_t* n_out);
@@ -90,6 +93,8 @@ int bpk_msm_g1_dev(bpk_ctx* ctx, uint64_t handle, size_t first, const void* d_sc
                    size_t n, int normalise, void* d_out_xyz);
 /* Sum of n projective points (host pointers, 18 u64 each), normalised: the post-gather step. */
 int bpk_g1_sum(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n, uint64_t out_xyz[18]);
+/* Same with device pointers (the gathered partials stay in HBM). */
+int bpk_g1_sum_dev(bpk_ctx* ctx, const void* d_points_xyz, size_t n, void* d_out_xyz);
 
 /* ---- NTT ------------------------------------------------------------------------------------ */
 /* ntt_381 (src/utils.rs:63-81): out[i] = sum_j in[j] w^(ij), w = ROOT_OF_UNITY^(2^32 / n), natural
