@@ -34,7 +34,7 @@ from typing import Iterable, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbpk.so")
+LIB_PATH = os.environ.get("BPK_LIB") or os.path.join(_HERE, "libbpk.so")  # BPK_LIB: A/B kernel builds
 
 # ---------------------------------------------------------------------------------------------
 # field constants needed by the host layer (value conversion only; no data-path arithmetic)

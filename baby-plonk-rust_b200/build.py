@@ -63,5 +63,35 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(tag, defines):
+    """Experimental build with extra -D flags -> libbpk_<tag>.so (loaded with BPK_LIB=<path>).
+    Used for A/B measurements of kernel formulations on the GPU box; not the shipped library."""
+    vobj = os.path.join(HERE, "_obj_" + tag)
+    os.makedirs(vobj, exist_ok=True)
+    out = os.path.join(HERE, "libbpk_%s.so" % tag)
+
+    def comp(src):
+        obj = os.path.join(vobj, src.replace(".cu", ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        with open(os.path.join(vobj, src.replace(".cu", ".ptxas.log")), "w") as f:
+            f.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(r.stdout + r.stderr)
+        return obj
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(comp, SOURCES))
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -81,6 +81,23 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(uint64_t* out, uint32_t
 #pragma unroll
         for (int i = 0; i < 8; i++) s ^= acc[i];
         out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+    } else if (mode == 2) {
+        // fused accumulate: IMAD.WIDE.U32 Rd, Ra, Rb, Rd (what mul() issues), 14 independent columns
+        uint32_t lo[14], hi[14], m[14];
+#pragma unroll
+        for (int i = 0; i < 14; i++) {
+            lo[i] = a + i;
+            hi[i] = b + i;
+            m[i] = a * (i + 3);
+        }
+        for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 14; i++) detail::mad_wide(lo[i], hi[i], m[i], b);
+        }
+        uint64_t s = 0;
+#pragma unroll
+        for (int i = 0; i < 14; i++) s ^= ((uint64_t)hi[i] << 32) | lo[i];
+        out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
     } else {
         uint32_t x[12], y[12], m[12];
 #pragma unroll
@@ -119,7 +136,7 @@ int imad_peak_run(bpk_ctx* ctx, double* rate, double* seconds) {
     BPK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    double per_thread = mode == 0 ? 8.0 * iters : 12.0 * iters;  // mode 1: 2 chains x 6 wide IMADs
+    double per_thread = mode == 0 ? 8.0 * iters : (mode == 2 ? 14.0 * iters : 12.0 * iters);  // mode 1: 2 chains x 6
     *rate = per_thread * 256.0 * blocks / (ms * 1e-3);
     *seconds = ms * 1e-3;
     return BPK_OK;

@@ -150,6 +150,14 @@ struct FrParams {
                                    0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
         return m[i];
     }
+    // reduced-radix form used inside mul(): 9 limbs of 29 bits (261 bits), operand a pre-shifted by 5
+    static constexpr int RB = 29, NL = 9, PRESHIFT = 5;
+    static constexpr uint32_t M0R = 0x1fffffffu;  // -q^-1 mod 2^29
+    BPK_HD static constexpr uint32_t modr(int i) {
+        constexpr uint32_t m[9] = {0x00000001u, 0x1ffffff8u, 0x1f96ffbfu, 0x1b4805ffu, 0x1d80553bu,
+                                   0x0c0404d0u, 0x1520cce7u, 0x0a6533afu, 0x0073eda7u};
+        return m[i];
+    }
 };
 
 // fp.rs:70-77 (MODULUS), :80 (INV), :83-90 (R), :93-100 (R2)
@@ -174,6 +182,15 @@ struct FpParams {
                                     0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
         return m[i];
     }
+    // reduced-radix form used inside mul(): 14 limbs of 28 bits (392 bits), operand a pre-shifted by 8
+    static constexpr int RB = 28, NL = 14, PRESHIFT = 8;
+    static constexpr uint32_t M0R = 0x0ffcfffdu;  // -p^-1 mod 2^28
+    BPK_HD static constexpr uint32_t modr(int i) {
+        constexpr uint32_t m[14] = {0x0fffaaabu, 0x0fefffffu, 0x03ffffb9u, 0x0fffeb15u, 0x06241eabu,
+                                    0x0a0f6b0fu, 0x0f6730d2u, 0x0f38512bu, 0x04774b84u, 0x04bacd76u,
+                                    0x0ba7b643u, 0x0e69a4b1u, 0x01ea397fu, 0x0001a011u};
+        return m[i];
+    }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -181,6 +198,7 @@ struct FpParams {
 // ------------------------------------------------------------------------------------------
 template <class P>
 struct alignas(16) Fe {
+    typedef P params;
     static constexpr int N = P::N;
     uint32_t l[N];
 
@@ -219,14 +237,23 @@ struct alignas(16) Fe {
 
 namespace detail {
 
+// 32 x 32 -> 64 product with no addend: a plain IMAD.WIDE.U32 Rd, Ra, Rb, RZ (one heavy-pipe slot;
+// any 64-bit or carry-in addend makes it two, profiles/r1_imad_forms.md)
+BPK_HD void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    asm("{ .reg .b64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+#else
+    uint64_t t = (uint64_t)a * b;
+    lo = (uint32_t)t;
+    hi = (uint32_t)(t >> 32);
+#endif
+}
+
 // acc[j], acc[j+1] = a[j] * bi for even j
 template <int N>
 BPK_HD void mul_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
 #pragma unroll
-    for (int j = 0; j < N; j += 2) {
-        acc[j] = ptx::mul_lo(a[j], bi);
-        acc[j + 1] = ptx::mul_hi(a[j], bi);
-    }
+    for (int j = 0; j < N; j += 2) mul_wide(acc[j], acc[j + 1], a[j], bi);
 }
 
 // (acc[j], acc[j+1]) += a[j] * bi for even j, one carry chain; the carry-out stays in CC
@@ -266,9 +293,41 @@ BPK_HD void madc_n_rshift(uint32_t* odd, const uint32_t* a, uint32_t bi) {
     odd[N - 1] = ptx::madc_hi(a[N - 2], bi, 0);
 }
 
+// "split" forms of madc_n_rshift / cmad_mod: the products are formed without addend on the heavy
+// FMA pipe and folded in by an add-with-carry chain on the ALU pipe (IADD3.X), so that the two
+// pipes share the work of a row instead of the FMA pipe doing all of it at half rate.
+template <int N>
+BPK_HD void madc_n_rshift_split(uint32_t* odd, const uint32_t* a, uint32_t bi) {
+    uint32_t pl[N / 2], ph[N / 2];
+#pragma unroll
+    for (int j = 0; j < N; j += 2) mul_wide(pl[j / 2], ph[j / 2], a[j], bi);
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) {
+        odd[j] = ptx::addc_cc(pl[j / 2], odd[j + 2]);
+        odd[j + 1] = ptx::addc_cc(ph[j / 2], odd[j + 3]);
+    }
+    odd[N - 2] = ptx::addc_cc(pl[N / 2 - 1], 0);
+    odd[N - 1] = ptx::addc(ph[N / 2 - 1], 0);
+}
+template <class P, int OFF>
+BPK_HD void cmad_mod_split(uint32_t* acc, uint32_t mi) {
+    constexpr int N = P::N;
+    uint32_t pl[N / 2], ph[N / 2];
+#pragma unroll
+    for (int j = 0; j < N; j += 2) mul_wide(pl[j / 2], ph[j / 2], P::mod(j + OFF), mi);
+    acc[0] = ptx::add_cc(acc[0], pl[0]);
+    acc[1] = ptx::addc_cc(acc[1], ph[0]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+        acc[j] = ptx::addc_cc(acc[j], pl[j / 2]);
+        acc[j + 1] = ptx::addc_cc(acc[j + 1], ph[j / 2]);
+    }
+}
+
 // one row of the interleaved multiply + Montgomery reduction.
 // value = sum even[j] 2^(32j) + sum odd[j] 2^(32(j+1)); on exit even[0] == 0
-template <class P, bool FIRST>
+// SPLIT: bit 0 -> odd a*b chain on the ALU pipe, bit 1 -> odd m*p chain, bit 2 -> even m*p chain
+template <class P, bool FIRST, int SPLIT = 0>
 BPK_HD void mad_n_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t bi) {
     constexpr int N = P::N;
     if (FIRST) {
@@ -276,13 +335,22 @@ BPK_HD void mad_n_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_
         mul_n<N>(even, a, bi);
     } else {
         even[0] = ptx::add_cc(even[0], odd[1]);
-        madc_n_rshift<N>(odd, a + 1, bi);
+        if (SPLIT & 1)
+            madc_n_rshift_split<N>(odd, a + 1, bi);
+        else
+            madc_n_rshift<N>(odd, a + 1, bi);
         cmad_n<N>(even, a, bi);
         odd[N - 1] = ptx::addc(odd[N - 1], 0);
     }
     uint32_t mi = even[0] * P::M0;
-    cmad_mod<P, 1>(odd, mi);
-    cmad_mod<P, 0>(even, mi);
+    if (SPLIT & 2)
+        cmad_mod_split<P, 1>(odd, mi);
+    else
+        cmad_mod<P, 1>(odd, mi);
+    if (SPLIT & 4)
+        cmad_mod_split<P, 0>(even, mi);
+    else
+        cmad_mod<P, 0>(even, mi);
     odd[N - 1] = ptx::addc(odd[N - 1], 0);
 }
 
@@ -301,18 +369,21 @@ BPK_HD void final_sub(uint32_t* r) {
 
 }  // namespace detail
 
-// Montgomery product a*b/R mod p, fully reduced.  (scalar.rs:562-586, fp.rs:565-609)
-template <class P>
-BPK_HD Fe<P> mul(const Fe<P>& a, const Fe<P>& b) {
+// Montgomery product a*b/R mod p, fully reduced -- carry-chained 32-bit-limb version (v1).
+// Kept as the cross-check of mul(); every IMAD.WIDE.U32.X it issues occupies the heavy FMA pipe for
+// two slots on sm_100 (measured, profiles/r1_v1_msm_accumulate_ncu.md), which is why mul() below
+// does not use carry flags on the multiplier pipe.
+template <class P, int SPLIT = 0>
+BPK_HD Fe<P> mul_cc(const Fe<P>& a, const Fe<P>& b) {
     constexpr int N = P::N;
     uint32_t even[N], odd[N];
 #pragma unroll
     for (int i = 0; i < N; i += 2) {
         if (i == 0)
-            detail::mad_n_redc<P, true>(even, odd, a.l, b.l[0]);
+            detail::mad_n_redc<P, true, SPLIT>(even, odd, a.l, b.l[0]);
         else
-            detail::mad_n_redc<P, false>(even, odd, a.l, b.l[i]);
-        detail::mad_n_redc<P, false>(odd, even, a.l, b.l[i + 1]);
+            detail::mad_n_redc<P, false, SPLIT>(even, odd, a.l, b.l[i]);
+        detail::mad_n_redc<P, false, SPLIT>(odd, even, a.l, b.l[i + 1]);
     }
     // merge: r[j] = even[j] + odd[j+1]
     Fe<P> r;
@@ -322,6 +393,118 @@ BPK_HD Fe<P> mul(const Fe<P>& a, const Fe<P>& b) {
     r.l[N - 1] = ptx::addc(even[N - 1], 0);
     detail::final_sub<P>(r.l);
     return r;
+}
+
+namespace detail {
+// (hi:lo) += a * b, 32 x 32 -> 64 multiply-add on a 64-bit accumulator held in two registers.
+// The mad.lo.cc / madc.hi pair is what ptxas fuses into ONE plain IMAD.WIDE.U32 Rd, Ra, Rb, Rd; a
+// `mad.wide.u32` with a 64-bit addend is instead split by ptxas into IMAD.WIDE(.., RZ) + IADD3 + IADD3.X.
+BPK_HD void mad_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    asm("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+#else
+    uint64_t t = (((uint64_t)hi << 32) | lo) + (uint64_t)a * b;
+    lo = (uint32_t)t;
+    hi = (uint32_t)(t >> 32);
+#endif
+}
+// limb k (RB bits) of the integer (x << SH), x given as N 32-bit words
+template <class P, int SH>
+BPK_HD uint32_t rr_limb(const uint32_t* x, int k) {
+    constexpr int N = P::N, RB = P::RB;
+    constexpr uint32_t MASK = (1u << RB) - 1;
+    const int s = RB * k - SH;
+    if (s < 0) return (x[0] << (-s)) & MASK;
+    const int w = s >> 5, off = s & 31;
+    if (w >= N) return 0;
+    uint32_t lo = x[w];
+    uint32_t hi = (w + 1 < N) ? x[w + 1] : 0u;
+    uint32_t v = off ? ((lo >> off) | (hi << (32 - off))) : lo;
+    return v & MASK;
+}
+}  // namespace detail
+
+// Montgomery product a*b/R mod p (R = 2^(32 N)), fully reduced; scalar.rs:562-586, fp.rs:565-609.
+//
+// Reduced-radix formulation for the sm_100 multiplier pipe: the operands are re-sliced into NL limbs
+// of RB bits (Fp: 14 x 28, Fr: 9 x 29) and every partial product a_j b_i and m_i p_j is accumulated
+// into a 64-bit column with a plain IMAD.WIDE.U32 -- 2 NL products of < 2^(2 RB) never overflow 64
+// bits, so the multiplier pipe sees no carry flags at all (a carry-in IMAD.WIDE.U32.X costs two pipe
+// slots).  One row retires RB bits: m_i = t0 * (-p^-1) mod 2^RB, t += m_i p, t >>= RB.  NL rows divide by
+// 2^(RB NL); operand a enters pre-shifted by RB NL - 32 N bits, so the result is exactly a b / 2^(32 N):
+// the Montgomery domain is the reference's.  Column carries, re-slicing and the final conditional
+// subtraction run on the ALU pipe, which is otherwise idle.
+template <class P>
+BPK_HD Fe<P> mul_rr(const Fe<P>& a, const Fe<P>& b) {
+    constexpr int N = P::N, NL = P::NL, RB = P::RB;
+    constexpr uint32_t MASK = (1u << RB) - 1;
+    uint32_t A[NL];
+#pragma unroll
+    for (int k = 0; k < NL; k++) A[k] = detail::rr_limb<P, P::PRESHIFT>(a.l, k);
+    uint32_t tl[NL + 1], th[NL + 1];  // 64-bit columns as (lo, hi) register pairs
+#pragma unroll
+    for (int k = 0; k <= NL; k++) tl[k] = th[k] = 0;
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+        const uint32_t bi = detail::rr_limb<P, 0>(b.l, i);
+#pragma unroll
+        for (int j = 0; j < NL; j++) detail::mad_wide(tl[j], th[j], A[j], bi);
+        const uint32_t m = (tl[0] * P::M0R) & MASK;
+#pragma unroll
+        for (int j = 0; j < NL; j++) detail::mad_wide(tl[j], th[j], m, P::modr(j));
+        // column 0 is now a multiple of 2^RB: retire it, carry into column 1, slide the window
+        const uint32_t cl = (tl[0] >> RB) | (th[0] << (32 - RB));
+        const uint32_t ch = th[0] >> RB;
+        tl[0] = ptx::add_cc(tl[1], cl);
+        th[0] = ptx::addc(th[1], ch);
+#pragma unroll
+        for (int j = 1; j < NL; j++) {
+            tl[j] = tl[j + 1];
+            th[j] = th[j + 1];
+        }
+        tl[NL] = th[NL] = 0;
+    }
+    // carry-normalise the NL columns to RB-bit limbs
+    uint32_t L[NL + 1];
+    uint32_t cl = 0, ch = 0;
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+        uint32_t vl = ptx::add_cc(tl[j], cl);
+        uint32_t vh = ptx::addc(th[j], ch);
+        L[j] = vl & MASK;
+        cl = (vl >> RB) | (vh << (32 - RB));
+        ch = vh >> RB;
+    }
+    L[NL] = cl;  // 0 for reduced inputs (result < 2p < 2^(RB NL))
+    // re-slice to 32-bit words
+    Fe<P> r;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const int bit = 32 * j;
+        const int k = bit / RB, off = bit % RB;
+        uint32_t v = L[k] >> off;
+        if (k + 1 <= NL) v |= L[k + 1] << (RB - off);
+        if (2 * RB - off < 32 && k + 2 <= NL) v |= L[k + 2] << (2 * RB - off);
+        r.l[j] = v;
+    }
+    detail::final_sub<P>(r.l);
+    return r;
+}
+
+// The product the kernels use.  BPK_MUL_IMPL: 0 = carry chains only (v1), 1 = reduced radix,
+// 2.. = carry chains with SPLIT = BPK_MUL_IMPL - 2 (some chains moved to the ALU pipe).
+#ifndef BPK_MUL_IMPL
+#define BPK_MUL_IMPL 0
+#endif
+template <class P>
+BPK_HD Fe<P> mul(const Fe<P>& a, const Fe<P>& b) {
+#if BPK_MUL_IMPL == 1
+    return mul_rr<P>(a, b);
+#elif BPK_MUL_IMPL >= 2
+    return mul_cc<P, BPK_MUL_IMPL - 2>(a, b);
+#else
+    return mul_cc<P, 0>(a, b);
+#endif
 }
 
 template <class P>

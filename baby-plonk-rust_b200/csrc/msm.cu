@@ -123,7 +123,10 @@ __global__ void __launch_bounds__(256) msm_recode_kernel(const fr_t* __restrict_
 // ------------------------------------------------------------------------------------------
 // K3: chunked bucket accumulation
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __restrict__ keys,
+#ifndef BPK_ACC_MINBLOCKS
+#define BPK_ACC_MINBLOCKS 3  // 3 x 128 threads / SM needs <= 170 registers per thread
+#endif
+__global__ void __launch_bounds__(128, BPK_ACC_MINBLOCKS) msm_accumulate_kernel(const uint32_t* __restrict__ keys,
                                                               const uint32_t* __restrict__ vals, size_t M,
                                                               uint32_t chunk, size_t num_chunks,
                                                               const affine_t* __restrict__ points, uint32_t nb_total,

@@ -252,10 +252,11 @@ def main():
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     wide_rate, _ = ctx.imad_peak(0)
     chain_rate, _ = ctx.imad_peak(1)
+    fused_rate, _ = ctx.imad_peak(2)
     acc_ms = stages["msm.accumulate"]["ms_per_step"]
     alg = imad_alg_accumulate(n_local)
     achieved = alg / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else 0.0
-    peak = 2.0 * max(wide_rate, chain_rate) / 1e12
+    peak = 2.0 * max(wide_rate, chain_rate, fused_rate) / 1e12
     sm_max = clocks.get("sm_max_mhz") or 1965.0
     roofline = {
         "bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": peak, "unit": "TIMAD/s",
@@ -264,7 +265,7 @@ def main():
         "peak_source": "measured on this GPU by bpk_imad_peak (register-only IMAD.WIDE.U32 probe), counted as 2 lo/hi "
                        "IMADs per wide op like the algorithmic figure (SURVEY 8d); nominal 148 SM x 64 lanes x f_max = "
                        "%.2f TIMAD/s" % (148 * 64 * sm_max * 1e6 / 1e12),
-        "probe_wide_imad_per_s": wide_rate, "probe_chain_imad_per_s": chain_rate,
+        "probe_wide_imad_per_s": wide_rate, "probe_chain_imad_per_s": chain_rate, "probe_fused_acc_imad_per_s": fused_rate,
         "hbm_algorithmic_gbs": (n_local * 16 * (8 + 96)) / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None,
     }
 

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <iostream>
 #include <sstream>
 #include "../../baby-plonk-rust_b200/csrc/ff.cuh"
@@ -27,9 +28,14 @@ template <class F> static int run_field(const std::string& op, std::istringstrea
     std::string ha, hb;
     ss >> ha;
     F a = parse<F>(ha), b = F::zero();
-    if (op == "mul" || op == "add" || op == "sub") { ss >> hb; b = parse<F>(hb); }
+    if (op.substr(0, 3) == "mul" || op == "add" || op == "sub") { ss >> hb; b = parse<F>(hb); }
     F r;
     if (op == "mul") r = mul(a, b);
+    else if (op == "mulcc") r = mul_cc(a, b);
+    else if (op == "mulrr") r = mul_rr(a, b);
+    else if (op == "mulsplit1") r = mul_cc<typename std::remove_reference<decltype(a)>::type::params, 1>(a, b);
+    else if (op == "mulsplit3") r = mul_cc<typename std::remove_reference<decltype(a)>::type::params, 3>(a, b);
+    else if (op == "mulsplit7") r = mul_cc<typename std::remove_reference<decltype(a)>::type::params, 7>(a, b);
     else if (op == "sqr") r = sqr(a);
     else if (op == "add") r = add(a, b);
     else if (op == "sub") r = sub(a, b);

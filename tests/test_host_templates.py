@@ -48,6 +48,8 @@ def test_field_ops(exe):
         for a in vals:
             for b in rng.sample(vals, 6) + [a, mod - 1 - a if a != mod - 1 else 0]:
                 lines.append(f"{name} mul {hx(a)} {hx(b)}"); exp.append(a * b * Rinv % mod)
+                for variant in ("mulcc", "mulrr", "mulsplit1", "mulsplit3", "mulsplit7"):
+                    lines.append(f"{name} {variant} {hx(a)} {hx(b)}"); exp.append(a * b * Rinv % mod)
                 lines.append(f"{name} add {hx(a)} {hx(b)}"); exp.append((a + b) % mod)
                 lines.append(f"{name} sub {hx(a)} {hx(b)}"); exp.append((a - b) % mod)
             lines.append(f"{name} sqr {hx(a)}"); exp.append(a * a * Rinv % mod)
