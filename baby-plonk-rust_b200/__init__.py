@@ -70,6 +70,7 @@ _SIGNATURES = {
     "bpk_srs_generate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64)]),
     "bpk_srs_generate_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
                                               ctypes.POINTER(ctypes.c_uint64)]),
+    "bpk_srs_precompute": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint]),
     "bpk_srs_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p]),
     "bpk_srs_len": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_size_t)]),
     "bpk_srs_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64]),
@@ -446,6 +447,13 @@ class Setup:
         h = ctypes.c_uint64()
         ctx.check(ctx.lib.bpk_srs_load(ctx.handle, pts.ctypes.data, pts.shape[0], ctypes.byref(h)), "bpk_srs_load")
         return cls(ctx, h.value, pts.shape[0])
+
+    def precompute(self, window_bits: int = 0) -> "Setup":
+        """keep [2^(c w)] P_i for every window next to the SRS (W x its size in HBM): later commits use one
+        shared bucket set, fewer windows, no final doubling chain.  Results are bit-identical."""
+        self.ctx.check(self.ctx.lib.bpk_srs_precompute(self.ctx.handle, self.handle, int(window_bits)),
+                       "bpk_srs_precompute")
+        return self
 
     def powers_of_x(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
         count = self.n - first if count is None else count

@@ -238,6 +238,7 @@ extern "C" int bpk_set_option(bpk_ctx* ctx, const char* key, long value) {
     std::string k(key);
     if (k == "msm.window") ctx->opt_msm_window = value;
     else if (k == "msm.chunk") ctx->opt_msm_chunk = value;
+    else if (k == "msm.fanin") ctx->opt_msm_fanin = value;
     else if (k == "ntt.tile_log2") {
         if (value < 1 || value > 12) return BPK_ERR_INVALID_ARG;
         ctx->opt_ntt_tile_log2 = value;
@@ -336,6 +337,47 @@ extern "C" int bpk_srs_free(bpk_ctx* ctx, uint64_t handle) {
     return BPK_OK;
 }
 
+// Trade HBM for work: store [2^(c w)] P_i for every window w next to the SRS (W x the SRS size; a 2^24-point
+// SRS with c = 22 is 12 x 1.5 GiB of a B200's 180 GB).  All windows of a scalar then share one set of
+// 2^(c-1) buckets: fewer windows for the same bucket memory, and no Horner doubling chain at the end.
+extern "C" int bpk_srs_precompute(bpk_ctx* ctx, uint64_t handle, unsigned window_bits) {
+    if (!ctx) return BPK_ERR_INVALID_ARG;
+    auto it = ctx->srs.find(handle);
+    if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
+    SrsEntry& e = it->second;
+    if (e.pre_c != 0) return window_bits == 0 || window_bits == e.pre_c ? BPK_OK : BPK_ERR_INVALID_ARG;
+    if (e.n == 0) return BPK_OK;
+    unsigned c = window_bits;
+    if (c == 0) {  // adds W n, bucket tree ~4.2 * 2^(c-1) addition equivalents, ~0.25 ms of serial depth per 3 bits
+        double best = 1e300;
+        for (unsigned cc = 8; cc <= 23; cc++) {
+            double W = (256 + cc - 1) / cc;
+            double cost = W * (double)e.n + 4.2 * (double)(1u << (cc - 1)) + 7.0e5 * ((cc - 1) / 3.0);
+            if (cost < best) { best = cost; c = cc; }
+        }
+    }
+    if (c < 2 || c > 24) return BPK_ERR_INVALID_ARG;
+    const unsigned W = (256 + c - 1) / c;
+    if ((size_t)W * e.n >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    affine_t* table = nullptr;
+    BPK_CUDA(cudaMalloc(&table, (size_t)W * e.n * sizeof(affine_t)));
+    cudaError_t err = cudaMemcpyAsync(table, e.points, e.n * sizeof(affine_t), cudaMemcpyDeviceToDevice, ctx->stream);
+    int s = err == cudaSuccess ? BPK_OK : cuda_fail(ctx, err, "precompute copy", __FILE__, __LINE__);
+    for (unsigned w = 1; w < W && s == BPK_OK; w++)
+        s = srs_precompute_level(ctx, table + (size_t)(w - 1) * e.n, table + (size_t)w * e.n, e.n, c);
+    if (s == BPK_OK) {
+        err = cudaStreamSynchronize(ctx->stream);
+        if (err != cudaSuccess) s = cuda_fail(ctx, err, "precompute", __FILE__, __LINE__);
+    }
+    if (s != BPK_OK) { cudaFree(table); return s; }
+    cudaFree(e.points);
+    e.points = table;
+    e.pre_c = c;
+    e.pre_W = W;
+    return BPK_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // MSM
 // ------------------------------------------------------------------------------------------------
@@ -349,8 +391,19 @@ static int window_to_shift(size_t b, size_t c, unsigned* rshift) {
     return BPK_OK;
 }
 
-static int msm_host_scalars(bpk_ctx* ctx, const affine_t* d_points, size_t n_points, const uint64_t* scalars,
-                            size_t n_scalars, unsigned rshift, uint64_t out_xyz[18]) {
+static MsmPoints msm_points_of(const SrsEntry& e, size_t first) {
+    MsmPoints p;
+    p.base = e.points + first;
+    p.level_stride = e.pre_c ? e.n : 0;
+    p.pre_c = e.pre_c;
+    p.pre_W = e.pre_W;
+    return p;
+}
+
+static int msm_host_scalars(bpk_ctx* ctx, const SrsEntry& srs, const uint64_t* scalars, size_t n_scalars,
+                            unsigned rshift, uint64_t out_xyz[18]) {
+    const size_t n_points = srs.n;
+    const MsmPoints d_points = msm_points_of(srs, 0);
     size_t n = n_points < n_scalars ? n_points : n_scalars;  // zip truncation (msm.rs:29)
     fr_t* d_scalars;
     BPK_TRY(ws_reserve(ctx, 9, (n ? n : 1) * sizeof(fr_t), (void**)&d_scalars));
@@ -371,7 +424,7 @@ extern "C" int bpk_bucket_msm(bpk_ctx* ctx, uint64_t handle, const uint64_t* sca
     auto it = ctx->srs.find(handle);
     if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
     BPK_CUDA(cudaSetDevice(ctx->device));
-    return msm_host_scalars(ctx, it->second.points, it->second.n, scalars_mont, n_scalars, rshift, out_xyz);
+    return msm_host_scalars(ctx, it->second, scalars_mont, n_scalars, rshift, out_xyz);
 }
 
 extern "C" int bpk_msm_g1(bpk_ctx* ctx, uint64_t handle, const uint64_t* scalars_mont, size_t n_scalars,
@@ -397,7 +450,7 @@ extern "C" int bpk_msm_g1_dev(bpk_ctx* ctx, uint64_t handle, size_t first, const
     if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
     if (first > it->second.n || n > it->second.n - first) return BPK_ERR_INVALID_ARG;
     BPK_CUDA(cudaSetDevice(ctx->device));
-    return msm_run(ctx, it->second.points + first, (const fr_t*)d_scalars_mont, n, 0, normalise != 0,
+    return msm_run(ctx, msm_points_of(it->second, first), (const fr_t*)d_scalars_mont, n, 0, normalise != 0,
                    (uint64_t*)d_out_xyz);
 }
 

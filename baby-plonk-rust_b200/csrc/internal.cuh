@@ -23,8 +23,19 @@ struct DeviceBuffer {
 };
 
 struct SrsEntry {
-    affine_t* points = nullptr;  // n affine points, Montgomery, (0,0) = infinity
+    // n affine points, Montgomery, (0,0) = infinity.  After bpk_srs_precompute the buffer holds pre_W
+    // levels of n points each: level w = [2^(pre_c * w)] P_i (level 0 = the SRS itself), so that all windows
+    // of a scalar fall into ONE set of 2^(pre_c - 1) buckets and no window Horner pass is needed.
+    affine_t* points = nullptr;
     size_t n = 0;
+    uint32_t pre_c = 0;
+    uint32_t pre_W = 0;
+};
+
+struct MsmPoints {
+    const affine_t* base;  // first point of this call's slice (level 0)
+    size_t level_stride;   // distance between precomputed levels, in points (0 if not precomputed)
+    uint32_t pre_c, pre_W;
 };
 
 struct StageStat {
@@ -68,6 +79,7 @@ struct bpk_ctx {
     // options
     long opt_msm_window = 0;
     long opt_msm_chunk = 0;
+    long opt_msm_fanin = 8;
     long opt_ntt_tile_log2 = 11;
     long opt_imad_mode = 0;
 
@@ -117,7 +129,7 @@ int ntt_run(bpk_ctx* ctx, const fr_t* d_in, fr_t* d_out, size_t n, size_t batch,
 int pointwise_mul(bpk_ctx* ctx, fr_t* d_a, const fr_t* d_b, size_t n);
 
 // ---- msm.cu ----
-int msm_run(bpk_ctx* ctx, const affine_t* d_points, const fr_t* d_scalars, size_t n, unsigned rshift,
+int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n, unsigned rshift,
             bool normalise, uint64_t* d_out_xyz /* 18 u64 on device */);
 int g1_sum_run(bpk_ctx* ctx, const uint64_t* d_points_xyz, size_t n, uint64_t* d_out_xyz);
 
@@ -125,6 +137,8 @@ int g1_sum_run(bpk_ctx* ctx, const uint64_t* d_points_xyz, size_t n, uint64_t* d
 int srs_from_projective(bpk_ctx* ctx, const uint64_t* d_xyz, size_t n, affine_t* d_out);
 int srs_to_projective(bpk_ctx* ctx, const affine_t* d_pts, size_t n, uint64_t* d_xyz);
 int srs_generate(bpk_ctx* ctx, const fr_t& tau, size_t first, size_t n, affine_t* d_out);
+// level w of the precomputed table from level w-1: out[i] = [2^c] in[i]
+int srs_precompute_level(bpk_ctx* ctx, const affine_t* d_in, affine_t* d_out, size_t n, uint32_t c);
 
 // ---- misc ----
 int imad_peak_run(bpk_ctx* ctx, double* rate, double* seconds);

@@ -72,8 +72,11 @@ __device__ __forceinline__ fr_t ld_fr_g(const fr_t* p) {
 // ------------------------------------------------------------------------------------------
 // K1: signed-digit recoding
 // ------------------------------------------------------------------------------------------
+// key_stride: buckets per window (2^(c-1)) for per-window bucket sets, 0 when every window shares one
+// bucket set (precomputed SRS levels); val_stride: distance between precomputed levels in points, else 0.
 __global__ void __launch_bounds__(256) msm_recode_kernel(const fr_t* __restrict__ scalars, uint32_t n, uint32_t c,
-                                                          uint32_t W, uint32_t rshift, uint32_t* __restrict__ keys,
+                                                          uint32_t W, uint32_t rshift, uint32_t key_stride,
+                                                          uint32_t val_stride, uint32_t* __restrict__ keys,
                                                           uint32_t* __restrict__ vals) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -115,8 +118,8 @@ __global__ void __launch_bounds__(256) msm_recode_kernel(const fr_t* __restrict_
             carry = 0;
         }
         size_t o = (size_t)w * n + i;
-        keys[o] = d ? (w * half + d - 1) : INVALID_KEY;
-        vals[o] = i | (neg << 31);
+        keys[o] = d ? (w * key_stride + d - 1) : INVALID_KEY;
+        vals[o] = (w * val_stride + i) | (neg << 31);
     }
 }
 
@@ -329,8 +332,10 @@ static uint32_t pick_window(bpk_ctx* ctx, size_t n) {
     return best_c;
 }
 
-int msm_run(bpk_ctx* ctx, const affine_t* d_points, const fr_t* d_scalars, size_t n, unsigned rshift,
+int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n, unsigned rshift,
             bool normalise, uint64_t* d_out) {
+    const affine_t* d_points = pts.base;
+    const bool pre = pts.pre_c != 0;  // all windows share one bucket set (precomputed SRS levels)
     if (n >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
     if (n == 0) {  // empty sum: identity (0, R, 0)
         xyzz_t* zero;
@@ -341,12 +346,14 @@ int msm_run(bpk_ctx* ctx, const affine_t* d_points, const fr_t* d_scalars, size_
         BPK_CUDA(cudaGetLastError());
         return BPK_OK;
     }
-    const uint32_t c = pick_window(ctx, n);
-    const uint32_t W = (256 + c - 1) / c;
+    const uint32_t c = pre ? pts.pre_c : pick_window(ctx, n);
+    const uint32_t W = pre ? pts.pre_W : (256 + c - 1) / c;
     const uint32_t half = 1u << (c - 1);
-    const uint32_t nb_total = W * half;
+    const uint32_t WB = pre ? 1 : W;  // number of bucket sets
+    const uint32_t nb_total = WB * half;
     const size_t M = (size_t)W * n;
     if (M >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
+    if (pre && (size_t)W * pts.level_stride >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
 
     // workspace carve-up
     uint32_t *keys_in, *vals_in, *keys_out, *vals_out;
@@ -388,8 +395,8 @@ int msm_run(bpk_ctx* ctx, const affine_t* d_points, const fr_t* d_scalars, size_
 
     {
         StageTimer t(ctx, "msm.recode");
-        msm_recode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_scalars, (uint32_t)n, c, W, rshift,
-                                                                               keys_in, vals_in);
+        msm_recode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+            d_scalars, (uint32_t)n, c, W, rshift, pre ? 0u : half, pre ? (uint32_t)pts.level_stride : 0u, keys_in, vals_in);
         count_launch(ctx);
         BPK_CUDA(cudaGetLastError());
         t.end();
@@ -419,26 +426,30 @@ int msm_run(bpk_ctx* ctx, const affine_t* d_points, const fr_t* d_scalars, size_
         BPK_CUDA(cudaGetLastError());
         t.end();
     }
-    // reduction tree: fold 2^5 items per thread per level
+    // reduction tree: fold `fanin` items per thread per level (serial depth 3 x fanin additions per level)
+    const uint32_t W_h = W;  // (window count of the Horner pass is WB below)
+    (void)W_h;
+    uint32_t fanin = (uint32_t)ctx->opt_msm_fanin;
+    if (fanin < 2 || fanin > 32 || (fanin & (fanin - 1))) fanin = 8;
     const xyzz_t* A = buckets;
     const xyzz_t* V = nullptr;
     {
         StageTimer t(ctx, "msm.reduce");
         xyzz_t* lvl;
         // level outputs: items/32 (+ /1024 + ...) per window, A and V each; 2 * nb_total/16 is ample
-        size_t lvl_elems = (size_t)W * (half / 2 + 64);
+        size_t lvl_elems = (size_t)WB * (half + 64);
         BPK_TRY(ws_reserve(ctx, 6, 2 * lvl_elems * sizeof(xyzz_t), (void**)&lvl));
         uint32_t items = half;
         uint32_t dbls = 0;
         size_t off = 0;
         while (items > 1) {
-            uint32_t S = items >= 32 ? 32 : items;
+            uint32_t S = items >= fanin ? fanin : items;
             uint32_t groups = items / S;
             xyzz_t* A2 = lvl + off;
-            xyzz_t* V2 = lvl + off + (size_t)W * groups;
-            off += 2 * (size_t)W * groups;
-            uint32_t threads = W * groups;
-            msm_reduce_level_kernel<<<(threads + 127) / 128, 128, 0, ctx->stream>>>(A, V, A2, V2, items, S, W, dbls);
+            xyzz_t* V2 = lvl + off + (size_t)WB * groups;
+            off += 2 * (size_t)WB * groups;
+            uint32_t threads = WB * groups;
+            msm_reduce_level_kernel<<<(threads + 127) / 128, 128, 0, ctx->stream>>>(A, V, A2, V2, items, S, WB, dbls);
             count_launch(ctx);
             BPK_CUDA(cudaGetLastError());
             A = A2;
@@ -450,14 +461,14 @@ int msm_run(bpk_ctx* ctx, const affine_t* d_points, const fr_t* d_scalars, size_
         }
         if (V == nullptr) {  // c == 1: a single bucket per window, weight 1, no tree level ran
             xyzz_t* z = lvl + off;
-            BPK_CUDA(cudaMemsetAsync(z, 0, (size_t)W * sizeof(xyzz_t), ctx->stream));
+            BPK_CUDA(cudaMemsetAsync(z, 0, (size_t)WB * sizeof(xyzz_t), ctx->stream));
             V = z;
         }
         t.end();
     }
     {
         StageTimer t(ctx, "msm.finalize");
-        msm_finalize_kernel<<<1, 1, 0, ctx->stream>>>(A, V, W, c, normalise ? 1 : 0, d_out);
+        msm_finalize_kernel<<<1, 1, 0, ctx->stream>>>(A, V, WB, c, normalise ? 1 : 0, d_out);
         count_launch(ctx);
         BPK_CUDA(cudaGetLastError());
         t.end();

@@ -123,7 +123,67 @@ __global__ void __launch_bounds__(128) srs_generate_kernel(const affine_t* __res
     st_fp_s(&out[i].y, a.y);
 }
 
+// out[i] = [2^c] in[i]: c doublings in XYZZ, back to affine.  Each thread owns PRE_BATCH consecutive
+// points and shares one field inversion among them (Montgomery's trick: invert the product of the
+// ZZ*ZZZ denominators, peel the individual inverses off backwards).
+constexpr int PRE_BATCH = 2;  // 6 x PRE_BATCH field elements stay in registers
+__global__ void __launch_bounds__(128) srs_precompute_level_kernel(const affine_t* __restrict__ in,
+                                                                    affine_t* __restrict__ out, size_t n, uint32_t c) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i0 = t * PRE_BATCH;
+    if (i0 >= n) return;
+    fp_t X[PRE_BATCH], Y[PRE_BATCH], D[PRE_BATCH], Zz[PRE_BATCH], Zzz[PRE_BATCH], pre[PRE_BATCH];
+    bool inf[PRE_BATCH];
+    fp_t run = fp_t::one();
+#pragma unroll
+    for (int k = 0; k < PRE_BATCH; k++) {
+        inf[k] = true;
+        if (i0 + k < n) {
+            affine_t a;
+            a.x = ld_fp_s(&in[i0 + k].x);
+            a.y = ld_fp_s(&in[i0 + k].y);
+            xyzz_t p = xyzz_t::from_affine(a);
+#pragma unroll 1
+            for (uint32_t d = 0; d < c; d++) xyzz_dbl(p);
+            inf[k] = p.is_inf();
+            X[k] = p.X;
+            Y[k] = p.Y;
+            Zz[k] = p.ZZ;
+            Zzz[k] = p.ZZZ;
+        }
+        D[k] = inf[k] ? fp_t::one() : mul(Zz[k], Zzz[k]);
+        pre[k] = run;  // product of the denominators before k
+        run = mul(run, D[k]);
+    }
+    fp_t iv = inv(run);
+#pragma unroll
+    for (int k = PRE_BATCH - 1; k >= 0; k--) {
+        fp_t dk_inv = mul(iv, pre[k]);  // 1 / D[k]
+        iv = mul(iv, D[k]);
+        if (i0 + k < n) {
+            affine_t a = affine_t::inf();
+            if (!inf[k]) {  // x = X / ZZ = X * ZZZ / D, y = Y / ZZZ = Y * ZZ / D
+                a.x = mul(X[k], mul(dk_inv, Zzz[k]));
+                a.y = mul(Y[k], mul(dk_inv, Zz[k]));
+            }
+            st_fp_s(&out[i0 + k].x, a.x);
+            st_fp_s(&out[i0 + k].y, a.y);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
+int srs_precompute_level(bpk_ctx* ctx, const affine_t* d_in, affine_t* d_out, size_t n, uint32_t c) {
+    if (n == 0) return BPK_OK;
+    StageTimer t(ctx, "srs.precompute");
+    size_t threads = (n + PRE_BATCH - 1) / PRE_BATCH;
+    srs_precompute_level_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(d_in, d_out, n, c);
+    count_launch(ctx);
+    BPK_CUDA(cudaGetLastError());
+    t.end();
+    return BPK_OK;
+}
+
 int srs_from_projective(bpk_ctx* ctx, const uint64_t* d_xyz, size_t n, affine_t* d_out) {
     if (n == 0) return BPK_OK;
     StageTimer t(ctx, "srs.from_projective");

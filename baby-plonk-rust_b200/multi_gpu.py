@@ -49,13 +49,15 @@ def sharded_msm(partial, sum_points: Callable, group=None):
 class ShardedCommitter:
     """Per-rank state of a sharded KZG commitment: SRS slice on this GPU + reusable device buffers."""
 
-    def __init__(self, pkg, ctx, n_total: int, tau: int, rank: int, world_size: int, group=None):
+    def __init__(self, pkg, ctx, n_total: int, tau: int, rank: int, world_size: int, group=None, precompute=0):
         import torch
 
         self.pkg, self.ctx, self.group = pkg, ctx, group
         self.rank, self.world = rank, world_size
         self.lo, self.hi = shard_bounds(n_total, world_size, rank)
         self.setup = pkg.Setup.generate_srs(self.hi - self.lo, tau, ctx, first=self.lo)
+        if precompute is not None:  # window bits, 0 = auto
+            self.setup.precompute(precompute)
         self.device = torch.device("cuda", ctx.device)
         self.d_partial = torch.zeros(18, dtype=torch.int64, device=self.device)
         self.d_out = torch.zeros(18, dtype=torch.int64, device=self.device)

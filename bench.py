@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--window", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--no-precompute", action="store_true", help="do not keep [2^(cw)]P_i levels next to the SRS")
+    ap.add_argument("--pre-window", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -191,7 +193,8 @@ def main():
     if args.chunk:
         ctx.set_option("msm.chunk", args.chunk)
     n_total = 1 << args.logn
-    com = mg.ShardedCommitter(pkg, ctx, n_total, TAU, rank, world)
+    com = mg.ShardedCommitter(pkg, ctx, n_total, TAU, rank, world,
+                              precompute=None if args.no_precompute else args.pre_window)
     n_local = com.hi - com.lo
 
     # synthetic scalars: pinned host copy (for e2e) + device copy (for value)
@@ -250,22 +253,24 @@ def main():
     assert np.array_equal(r.reshape(-1), result_limbs.reshape(-1)), "e2e and device-resident results differ"
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------
-    wide_rate, _ = ctx.imad_peak(0)
-    chain_rate, _ = ctx.imad_peak(1)
-    fused_rate, _ = ctx.imad_peak(2)
+    chain_rate, _ = ctx.imad_peak(1)   # dense IMAD.WIDE.U32.X carry chains (what the multiplier issues)
+    fused_rate, _ = ctx.imad_peak(2)   # IMAD.WIDE.U32 with a 64-bit addend
     acc_ms = stages["msm.accumulate"]["ms_per_step"]
     alg = imad_alg_accumulate(n_local)
     achieved = alg / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else 0.0
-    peak = 2.0 * max(wide_rate, chain_rate, fused_rate) / 1e12
     sm_max = clocks.get("sm_max_mhz") or 1965.0
+    nominal = 148 * 64 * sm_max * 1e6 / 1e12
+    # a 32x32->64 IMAD.WIDE retires at 32 / clk / SM on sm_100 in every form (profiles/r1_imad_forms.md) and counts
+    # as 2 lo/hi IMADs in SURVEY 8d's algorithmic figure, so the measured peak in those units is 2 x the probe rate
+    peak = 2.0 * max(chain_rate, fused_rate) / 1e12
     roofline = {
         "bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": peak, "unit": "TIMAD/s",
         "frac": achieved / peak if peak else None, "traffic": None,
         "algorithmic_imad_per_launch": alg, "kernel_ms": acc_ms,
-        "peak_source": "measured on this GPU by bpk_imad_peak (register-only IMAD.WIDE.U32 probe), counted as 2 lo/hi "
-                       "IMADs per wide op like the algorithmic figure (SURVEY 8d); nominal 148 SM x 64 lanes x f_max = "
-                       "%.2f TIMAD/s" % (148 * 64 * sm_max * 1e6 / 1e12),
-        "probe_wide_imad_per_s": wide_rate, "probe_chain_imad_per_s": chain_rate, "probe_fused_acc_imad_per_s": fused_rate,
+        "peak_source": "measured on this GPU by bpk_imad_peak: register-only IMAD.WIDE.U32(.X) probe, 2 lo/hi IMADs per "
+                       "wide op as in SURVEY 8d; nominal 148 SM x 64 lanes x f_max = %.2f TIMAD/s" % nominal,
+        "frac_of_nominal": achieved / nominal,
+        "probe_chain_wide_imad_per_s": chain_rate, "probe_fused_acc_wide_imad_per_s": fused_rate,
         "hbm_algorithmic_gbs": (n_local * 16 * (8 + 96)) / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None,
     }
 
@@ -292,7 +297,8 @@ def main():
             "config": {"workload": "configs[1]: standalone G1 MSM, 2^%d uniform Fr scalars x synthetic SRS [tau^i]G (tau=101)"
                                    % args.logn + (", sharded over %d GPUs by index range + NCCL all-gather of partials (configs[4])" % world if world > 1 else ""),
                        "pairs": n_total, "pairs_per_gpu": n_local, "l2": "inputs larger than L2 (scalars %d MiB + SRS %d MiB per GPU)"
-                       % (n_local * 32 >> 20, n_local * 96 >> 20), "parallelism": "index-range shards x%d" % world},
+                       % (n_local * 32 >> 20, n_local * 96 >> 20), "parallelism": "index-range shards x%d" % world,
+                       "srs": "resident in HBM" + ("" if args.no_precompute else " with precomputed window levels (bpk_srs_precompute)")},
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(n_local * 32), "d2h_bytes_per_step": 144},
             "gpu_launches": int(launches),
             "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "power_w_max", "samples")},

@@ -64,6 +64,10 @@ int bpk_srs_generate(bpk_ctx* ctx, const uint64_t tau_mont[4], size_t n, uint64_
 /* The slice [tau^i] G for first <= i < first + n: the shard of the SRS one rank of a multi-GPU job owns. */
 int bpk_srs_generate_range(bpk_ctx* ctx, const uint64_t tau_mont[4], size_t first, size_t n,
                            uint64_t* handle_out);
+/* Optional: trade HBM for work.  Stores [2^(c w)] P_i for every c-bit window w next to the SRS (W = ceil(256/c)
+ * times the SRS size), so that every later MSM on this handle uses one shared bucket set, fewer windows and no
+ * final doubling chain.  window_bits == 0 picks c from the SRS length.  Results are unchanged (bit-exact). */
+int bpk_srs_precompute(bpk_ctx* ctx, uint64_t handle, unsigned window_bits);
 /* Read points [first, first+count) back as normalised G1Projective limbs. */
 int bpk_srs_read(bpk_ctx* ctx, uint64_t handle, size_t first, size_t count, uint64_t* out_xyz);
 int bpk_srs_len(bpk_ctx* ctx, uint64_t handle, size_t* n_out);

@@ -331,6 +331,64 @@ def test_msm_window_and_chunk_shapes(ctx, window, chunk):
     assert bpk.point_to_affine(got) == horner_expected(sc, 101)
 
 
+@pytest.mark.parametrize("c", [0, 2, 5, 8, 13, 16, 20])
+def test_msm_precomputed_srs_levels(ctx, c):
+    """bpk_srs_precompute stores [2^(c w)]P_i per window; every result must stay bit-identical"""
+    import torch
+    n = 2500
+    plain = bpk.Setup.generate_srs(n, 101, ctx)
+    pre = bpk.Setup.generate_srs(n, 101, ctx).precompute(c)
+    rng = random.Random(c)
+    for sc in (O.random_fr(900 + c, n), [rng.choice([0, 1, 3, O.Q - 1, 80]) for _ in range(n)], [O.Q - 1] * 7):
+        a = plain.commit_scalars(S(sc))
+        b = pre.commit_scalars(S(sc))
+        assert np.array_equal(a, b)
+        assert bpk.point_to_affine(b) == horner_expected(sc, 101)
+    # the SRS itself is unchanged by the precomputation
+    assert np.array_equal(plain.powers_of_x(0, 50), pre.powers_of_x(0, 50))
+    # the (b, c) quirk and zip truncation go through the same path
+    sc = O.random_fr(5, n + 3)
+    assert np.array_equal(plain.commit_scalars(S(sc), 256, 5), pre.commit_scalars(S(sc), 256, 5))
+    # device-resident shard with an offset into every level
+    sc = O.random_fr(6, n)
+    d_sc = torch.from_numpy(S(sc).view(np.int64)).cuda()
+    outs = []
+    for setup in (plain, pre):
+        d_out = torch.zeros(18, dtype=torch.int64, device="cuda")
+        ctx.check(ctx.lib.bpk_msm_g1_dev(ctx.handle, setup.handle, 700, d_sc.data_ptr() + 32 * 700, 1500, 1,
+                                         d_out.data_ptr()))
+        torch.cuda.synchronize()
+        outs.append(d_out.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    plain.free()
+    pre.free()
+
+
+def test_msm_precomputed_degenerate_points(ctx):
+    G = O.G1_GEN
+    pts = [G] * 20 + [None, O.g1_neg(G), G, None]
+    sc = O.random_fr(3, len(pts))
+    s = bpk.Setup.from_points(bpk.points_from_affine(pts), ctx).precompute(6)
+    assert bpk.point_to_affine(s.commit_scalars(S(sc))) == O.msm_naive(pts, sc)
+    s.free()
+
+
+@pytest.mark.parametrize("fanin", [2, 4, 8, 32])
+def test_msm_reduce_fanin(ctx, fanin):
+    n = 2000
+    setup = bpk.Setup.generate_srs(n, 101, ctx)
+    sc = O.random_fr(fanin, n)
+    ctx.set_option("msm.fanin", fanin)
+    try:
+        for w in (0, 7, 12):
+            ctx.set_option("msm.window", w)
+            assert bpk.point_to_affine(setup.commit_scalars(S(sc))) == horner_expected(sc, 101)
+    finally:
+        ctx.set_option("msm.fanin", 8)
+        ctx.set_option("msm.window", 0)
+        setup.free()
+
+
 @pytest.mark.parametrize("dist", ["witness", "all_equal", "tiny", "qminus1", "two_values"])
 def test_msm_skewed_distributions(ctx, dist):
     """heavy buckets: runs that span many chunks exercise the partial-merge path"""
