@@ -98,6 +98,7 @@ _SIGNATURES = {
     "bpk_profile_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double),
                                        ctypes.POINTER(ctypes.c_uint64)]),
     "bpk_launch_count": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "bpk_msm_last_plan": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint)]),
     "bpk_imad_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "bpk_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_long]),
 }
@@ -253,6 +254,11 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.bpk_launch_count(self.handle))
+
+    def msm_last_plan(self) -> dict:
+        arr = (ctypes.c_uint * 4)()
+        self.check(self.lib.bpk_msm_last_plan(self.handle, arr), "bpk_msm_last_plan")
+        return {"window_bits": arr[0], "windows": arr[1], "pairs_per_thread": arr[2], "buckets": arr[3]}
 
     def synchronize(self):
         self.check(self.lib.bpk_synchronize(self.handle), "bpk_synchronize")

@@ -577,6 +577,15 @@ extern "C" int bpk_profile_get(bpk_ctx* ctx, const char* name, double* ms_out, u
 }
 extern "C" uint64_t bpk_launch_count(bpk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int bpk_msm_last_plan(bpk_ctx* ctx, unsigned out[4]) {
+    if (!ctx || !out) return BPK_ERR_INVALID_ARG;
+    out[0] = ctx->last_c;
+    out[1] = ctx->last_W;
+    out[2] = ctx->last_chunk;
+    out[3] = ctx->last_buckets;
+    return BPK_OK;
+}
+
 extern "C" int bpk_imad_peak(bpk_ctx* ctx, double* rate, double* seconds) {
     if (!ctx || !rate || !seconds) return BPK_ERR_INVALID_ARG;
     BPK_CUDA(cudaSetDevice(ctx->device));

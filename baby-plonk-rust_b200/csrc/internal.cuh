@@ -83,6 +83,9 @@ struct bpk_ctx {
     long opt_ntt_tile_log2 = 11;
     long opt_imad_mode = 0;
 
+    // plan of the most recent MSM (window bits, windows, pairs per accumulate thread, buckets)
+    unsigned last_c = 0, last_W = 0, last_chunk = 0, last_buckets = 0;
+
     // instrumentation
     bool profiling = false;
     uint64_t launches = 0;

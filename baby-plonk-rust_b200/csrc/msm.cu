@@ -380,6 +380,10 @@ int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n,
         chunk = (uint32_t)(target < 16 ? 16 : (target > 256 ? 256 : target));
     }
     const size_t num_chunks = (M + chunk - 1) / chunk;
+    ctx->last_c = c;
+    ctx->last_W = W;
+    ctx->last_chunk = chunk;
+    ctx->last_buckets = nb_total;
 
     xyzz_t* buckets;
     BPK_TRY(ws_reserve(ctx, 4, (size_t)nb_total * sizeof(xyzz_t), (void**)&buckets));

@@ -132,6 +132,8 @@ int bpk_profile_reset(bpk_ctx* ctx);
 int bpk_profile_get(bpk_ctx* ctx, const char* name, double* ms_out, uint64_t* launches_out);
 /* Total kernel launches issued by this context since bpk_profile_reset. */
 uint64_t bpk_launch_count(bpk_ctx* ctx);
+/* Plan of the most recent MSM: {window bits c, windows W, pairs per accumulate thread, buckets}. */
+int bpk_msm_last_plan(bpk_ctx* ctx, unsigned out[4]);
 /* Register-only IMAD.WIDE throughput probe: returns 32x32+64 multiply-adds per second. */
 int bpk_imad_peak(bpk_ctx* ctx, double* wide_imad_per_s_out, double* seconds_out);
 /* Tunables: "msm.window" (0 = auto), "msm.chunk", "ntt.tile_log2". */
