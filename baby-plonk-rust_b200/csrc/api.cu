@@ -213,6 +213,8 @@ extern "C" void bpk_destroy(bpk_ctx* ctx) {
         cudaFree(ctx->tw_hi[d]);
         cudaFree(ctx->coset_lo[d]);
         cudaFree(ctx->coset_hi[d]);
+        for (auto& t : ctx->tw_direct[d])
+            if (t) cudaFree(t);
     }
     if (ctx->gen_table) cudaFree(ctx->gen_table);
     delete ctx;
@@ -242,6 +244,15 @@ extern "C" int bpk_set_option(bpk_ctx* ctx, const char* key, long value) {
     else if (k == "ntt.tile_log2") {
         if (value < 1 || value > 12) return BPK_ERR_INVALID_ARG;
         ctx->opt_ntt_tile_log2 = value;
+    } else if (k == "ntt.max_radix_log2") {
+        if (value < 1 || value > 12) return BPK_ERR_INVALID_ARG;
+        ctx->opt_ntt_max_radix_log2 = value;
+    } else if (k == "ntt.direct_max_log2") {
+        if (value < 0 || value > 28) return BPK_ERR_INVALID_ARG;
+        ctx->opt_ntt_direct_max_log2 = value;
+    } else if (k == "ntt.threads") {
+        if (value != 0 && (value < 32 || value > 1024 || (value & 31))) return BPK_ERR_INVALID_ARG;
+        ctx->opt_ntt_threads = value;
     } else if (k == "imad.mode") ctx->opt_imad_mode = value;
     else return BPK_ERR_INVALID_ARG;
     return BPK_OK;

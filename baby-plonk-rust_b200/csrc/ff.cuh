@@ -131,10 +131,61 @@ BPK_HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) {
 // ------------------------------------------------------------------------------------------
 // field parameters
 // ------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+// q's two low limbs are 0x00000001 and 0xffffffff.  As immediates ptxas strength-reduces the products with
+// them, which breaks the lo/hi -> IMAD.WIDE.U32.X fusion of BOTH m*q carry chains of every row; read from
+// constant memory the limbs are opaque operands (c[bank][offset]) and every pair fuses.
+static __device__ __constant__ uint32_t FR_MOD_CONST[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                                          0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+static __device__ uint32_t FR_M0_GLOBAL = 0xffffffffu;
+static __device__ uint32_t FR_LANE_ZERO[32] = {0};
+static __device__ uint32_t FR_MOD_GLOBAL[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                               0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+#endif
+
 // scalar.rs:83-88 (MODULUS), :164 (INV -> low 32 bits), :167-172 (R), :175-180 (R2)
 struct FrParams {
     static constexpr int N = 8;
     static constexpr uint32_t M0 = 0xffffffffu;  // -q^-1 mod 2^32
+#ifndef BPK_FR_SPECIAL
+#define BPK_FR_SPECIAL 1
+#endif
+    static constexpr bool SPECIAL_LOW64 = BPK_FR_SPECIAL != 0;  // q mod 2^64 == 2^64 - 2^32 + 1 and M0 == -1
+    BPK_HD static uint32_t m0_opaque() {
+#if defined(__CUDA_ARCH__)
+        uint32_t v;
+        asm("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(&FR_M0_GLOBAL));
+        return v;
+#else
+        return M0;
+#endif
+    }
+    BPK_HD static uint32_t modk(int i) {  // modulus limb as a multiplier operand
+#if defined(__CUDA_ARCH__) && BPK_FR_MODK == 1
+        uint32_t v;
+        asm("ld.const.u32 %0, [%1];" : "=r"(v) : "l"(&FR_MOD_CONST[i]));
+        return v;
+#elif defined(__CUDA_ARCH__) && BPK_FR_MODK == 3
+        // limbs fetched from global memory land in ordinary (per-thread) registers with values ptxas cannot
+        // see: no strength reduction of the 0x00000001 / 0xffffffff limbs, no uniform-register operands
+        // The index detours through a per-lane zero that is itself loaded from memory, so ptxas can neither see
+        // the limb value nor prove the address warp-uniform: the limb stays in a per-thread register.
+        uint32_t v, lane, z;
+        asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+        asm("ld.global.nc.u32 %0, [%1];" : "=r"(z) : "l"(&FR_LANE_ZERO[lane]));
+        asm("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(&FR_MOD_GLOBAL[i + z]));
+        return v;
+#elif defined(__CUDA_ARCH__) && BPK_FR_MODK == 2
+        // ptxas keeps warp-uniform values in uniform registers, and IMAD.WIDE.U32.X has no UR operand form;
+        // a lane-indexed move (every lane reads its own lane) makes the limb a per-thread register
+        uint32_t v = mod(i), lane;
+        asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+        asm("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+r"(v) : "r"(lane));
+        return v;
+#else
+        return mod(i);
+#endif
+    }
     BPK_HD static constexpr uint32_t mod(int i) {
         constexpr uint32_t m[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
                                    0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
@@ -164,6 +215,9 @@ struct FrParams {
 struct FpParams {
     static constexpr int N = 12;
     static constexpr uint32_t M0 = 0xfffcfffdu;  // -p^-1 mod 2^32
+    static constexpr bool SPECIAL_LOW64 = false;
+    BPK_HD static constexpr uint32_t m0_opaque() { return M0; }
+    BPK_HD static constexpr uint32_t modk(int i) { return mod(i); }  // immediates fuse fine for p
     BPK_HD static constexpr uint32_t mod(int i) {
         constexpr uint32_t m[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu,
                                     0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u,
@@ -272,12 +326,12 @@ BPK_HD void cmad_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
 template <class P, int OFF>
 BPK_HD void cmad_mod(uint32_t* acc, uint32_t mi) {
     constexpr int N = P::N;
-    acc[0] = ptx::mad_lo_cc(P::mod(OFF), mi, acc[0]);
-    acc[1] = ptx::madc_hi_cc(P::mod(OFF), mi, acc[1]);
+    acc[0] = ptx::mad_lo_cc(P::modk(OFF), mi, acc[0]);
+    acc[1] = ptx::madc_hi_cc(P::modk(OFF), mi, acc[1]);
 #pragma unroll
     for (int j = 2; j < N; j += 2) {
-        acc[j] = ptx::madc_lo_cc(P::mod(j + OFF), mi, acc[j]);
-        acc[j + 1] = ptx::madc_hi_cc(P::mod(j + OFF), mi, acc[j + 1]);
+        acc[j] = ptx::madc_lo_cc(P::modk(j + OFF), mi, acc[j]);
+        acc[j + 1] = ptx::madc_hi_cc(P::modk(j + OFF), mi, acc[j + 1]);
     }
 }
 
@@ -341,6 +395,36 @@ BPK_HD void mad_n_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_
             madc_n_rshift<N>(odd, a + 1, bi);
         cmad_n<N>(even, a, bi);
         odd[N - 1] = ptx::addc(odd[N - 1], 0);
+    }
+    if (P::SPECIAL_LOW64) {
+        // Fr: q = q_hi 2^64 + (2^64 - 2^32 + 1) and -q^-1 = -1 (mod 2^32), so m = -even[0] and
+        //   V + m q = (V - even[0]) + 2^32 Y + 2^64 m q_hi,   Y = m 2^32 - (m - c0),  c0 = [even[0] != 0]
+        // (even[0] + m = c0 2^32).  Only the six q_hi limbs need real products -- 14 instead of 16 wide
+        // IMADs per row -- and the two awkward limbs 0x00000001 / 0xffffffff, whose strength reduction by
+        // ptxas otherwise un-fuses both m*q carry chains, never appear as multiplier operands.
+        // m = even[0] * (-1).  The factor is fetched from memory on the device: when ptxas can see that m is a
+        // negation it rewrites the m * q_j products and stops fusing their lo/hi pairs into IMAD.WIDE.U32.X.
+        const uint32_t m = even[0] * P::m0_opaque();
+        const uint32_t c0 = even[0] != 0 ? 1u : 0u;
+        const uint32_t ylo = ptx::sub_cc(0u, m - c0);
+        const uint32_t yhi = ptx::subc(m, 0u);
+        odd[0] = ptx::add_cc(odd[0], ylo);     // position 1
+        odd[1] = ptx::addc_cc(odd[1], yhi);    // position 2
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {       // q3, q5, q7 at positions 3, 5, 7
+            odd[j] = ptx::madc_lo_cc(P::mod(j + 1), m, odd[j]);
+            odd[j + 1] = ptx::madc_hi_cc(P::mod(j + 1), m, odd[j + 1]);
+        }
+        even[2] = ptx::mad_lo_cc(P::mod(2), m, even[2]);  // q2, q4, q6 at positions 2, 4, 6
+        even[3] = ptx::madc_hi_cc(P::mod(2), m, even[3]);
+#pragma unroll
+        for (int j = 4; j < N; j += 2) {
+            even[j] = ptx::madc_lo_cc(P::mod(j), m, even[j]);
+            even[j + 1] = ptx::madc_hi_cc(P::mod(j), m, even[j + 1]);
+        }
+        odd[N - 1] = ptx::addc(odd[N - 1], 0);
+        even[0] = 0;
+        return;
     }
     uint32_t mi = even[0] * P::M0;
     if (SPLIT & 2)

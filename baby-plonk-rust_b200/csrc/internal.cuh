@@ -60,6 +60,8 @@ struct bpk_ctx {
     // NTT tables: powers of the primitive 2^NTT_MAX_LOG-th root (forward / inverse)
     bpk::fr_t* tw_lo[2] = {nullptr, nullptr};
     bpk::fr_t* tw_hi[2] = {nullptr, nullptr};
+    // per-size inter-pass twiddle tables w_{2^lg}^e, e < 2^lg (built on first use, forward / inverse)
+    bpk::fr_t* tw_direct[2][bpk::NTT_MAX_LOG + 1] = {};
     // coset tables for the last shift used (lo: g^i, hi: g^(i << TW_LO_BITS)), forward / inverse
     bpk::fr_t* coset_lo[2] = {nullptr, nullptr};
     bpk::fr_t* coset_hi[2] = {nullptr, nullptr};
@@ -80,7 +82,10 @@ struct bpk_ctx {
     long opt_msm_window = 0;
     long opt_msm_chunk = 0;
     long opt_msm_fanin = 8;
-    long opt_ntt_tile_log2 = 11;
+    long opt_ntt_tile_log2 = 10;  // R x C elements per CTA tile (32 KiB): best of the sweep in profiles/
+    long opt_ntt_max_radix_log2 = 10;
+    long opt_ntt_threads = 0;
+    long opt_ntt_direct_max_log2 = 25;  // largest direct twiddle table (2^25 x 32 B = 1 GiB)
     long opt_imad_mode = 0;
 
     // plan of the most recent MSM (window bits, windows, pairs per accumulate thread, buckets)

@@ -28,6 +28,7 @@ struct NttPassParams {
     const fr_t* tw_hi;
     const fr_t* cs_lo;  // coset tables (or null)
     const fr_t* cs_hi;
+    const fr_t* tw_direct;  // optional: w_{Ns R}^e for e < Ns R, one lookup instead of lookup-lookup-multiply
     uint32_t logn, logR, logC, logNs;
     int coset_in;   // multiply input element i by cs(i)
     int scale_out;  // 0: none, 1: multiply outputs by `scale`, 2: multiply output i by cs(i)
@@ -66,7 +67,7 @@ __device__ __forceinline__ fr_t table_pow(const fr_t* lo, const fr_t* hi, uint32
     return mul(a, ld_fr(hi + h));
 }
 
-__global__ void __launch_bounds__(256) ntt_pass_kernel(NttPassParams p) {
+__global__ void __launch_bounds__(1024) ntt_pass_kernel(NttPassParams p) {
     extern __shared__ uint4 smem[];
     const uint32_t logR = p.logR, logC = p.logC, logNs = p.logNs;
     const uint32_t R = 1u << logR, C = 1u << logC, RC = R << logC;
@@ -97,7 +98,10 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(NttPassParams p) {
         if (p.coset_in) v = mul(v, table_pow(p.cs_lo, p.cs_hi, g));
         if (logNs) {
             uint32_t k = j & ns_mask;
-            v = mul(v, table_pow(p.tw_lo, p.tw_hi, (k * r) << tw_shift));
+            if (p.tw_direct)
+                v = mul(v, ld_fr(p.tw_direct + k * r));
+            else
+                v = mul(v, table_pow(p.tw_lo, p.tw_hi, (k * r) << tw_shift));
         }
         uint32_t rr = __brev(r) >> (32 - logR);
         if (logR == 0) rr = 0;
@@ -113,9 +117,9 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(NttPassParams p) {
             uint32_t lowb = b & (half - 1);
             uint32_t i = ((b >> (s - 1)) << s) | lowb;
             uint32_t i0 = (i << logC) + c, i1 = ((i + half) << logC) + c;
-            fr_t w = ld_sm(t_lo, t_hi, lowb << (logR - s));
             fr_t u = ld_sm(s_lo, s_hi, i0);
-            fr_t t = mul(ld_sm(s_lo, s_hi, i1), w);
+            fr_t t = ld_sm(s_lo, s_hi, i1);
+            if (s > 1) t = mul(t, ld_sm(t_lo, t_hi, lowb << (logR - s)));  // stage 1 twiddles are all 1
             st_sm(s_lo, s_hi, i0, add(u, t));
             st_sm(s_lo, s_hi, i1, sub(u, t));
         }
@@ -148,6 +152,13 @@ __global__ void pow_table_kernel(fr_t* out, fr_t base, fr_t pre, uint32_t count,
     if (i >= count) return;
     fr_t v = pow_u64(base, (uint64_t)i << shift);
     st_fr(out + i, mul(v, pre));
+}
+
+// out[e] = root^(e << shift) from the two-level table: the per-pass inter-pass twiddle table
+__global__ void direct_table_kernel(fr_t* out, const fr_t* lo, const fr_t* hi, uint32_t count, uint32_t shift) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    st_fr(out + e, table_pow(lo, hi, e << shift));
 }
 
 __global__ void pointwise_mul_kernel(fr_t* a, const fr_t* b, size_t n) {
@@ -257,7 +268,9 @@ int ntt_run(bpk_ctx* ctx, const fr_t* d_in, fr_t* d_out, size_t n, size_t batch,
     }
 
     const uint32_t tile_log = (uint32_t)ctx->opt_ntt_tile_log2;  // log2(R * C)
-    const uint32_t max_logR = tile_log > 10 ? 10 : tile_log;
+    uint32_t max_logR = (uint32_t)ctx->opt_ntt_max_radix_log2;
+    if (max_logR > tile_log) max_logR = tile_log;
+    if (max_logR < 1) max_logR = 1;
     std::vector<uint32_t> plan;
     plan_passes(logn, max_logR, plan);
     const size_t np = plan.size();
@@ -282,6 +295,21 @@ int ntt_run(bpk_ctx* ctx, const fr_t* d_in, fr_t* d_out, size_t n, size_t batch,
         p.tw_hi = ctx->tw_hi[dir];
         p.cs_lo = ctx->coset_lo[dir];
         p.cs_hi = ctx->coset_hi[dir];
+        p.tw_direct = nullptr;
+        if (logNs && logNs + logR <= (uint32_t)ctx->opt_ntt_direct_max_log2) {
+            // w_{Ns R}^e, e < Ns R: HBM is idle in this kernel (6 % of peak) while the multiplier pipe is the
+            // limiter, so 32 B more traffic per element buys one multiplication less per element
+            const uint32_t lg = logNs + logR;
+            fr_t*& tab = ctx->tw_direct[dir][lg];
+            if (tab == nullptr) {
+                BPK_CUDA(cudaMalloc(&tab, sizeof(fr_t) << lg));
+                direct_table_kernel<<<(unsigned)(((size_t)1 << lg) + 255) / 256, 256, 0, ctx->stream>>>(
+                    tab, ctx->tw_lo[dir], ctx->tw_hi[dir], 1u << lg, NTT_MAX_LOG - lg);
+                count_launch(ctx);
+                BPK_CUDA(cudaGetLastError());
+            }
+            p.tw_direct = tab;
+        }
         p.logn = logn;
         p.logR = logR;
         p.logC = logC;
@@ -293,7 +321,9 @@ int ntt_run(bpk_ctx* ctx, const fr_t* d_in, fr_t* d_out, size_t n, size_t batch,
         size_t smem = ((size_t)2 << (logR + logC)) * sizeof(uint4) + ((size_t)1 << logR) * sizeof(uint4);
         if (smem > 200 * 1024) return BPK_ERR_INVALID_ARG;
         dim3 grid((unsigned)(n >> (logR + logC)), (unsigned)batch);
-        ntt_pass_kernel<<<grid, 256, smem, ctx->stream>>>(p);
+        unsigned threads = (unsigned)ctx->opt_ntt_threads;
+        if (threads == 0) threads = (logR + logC >= 12) ? 1024 : 256;
+        ntt_pass_kernel<<<grid, threads, smem, ctx->stream>>>(p);
         count_launch(ctx);
         BPK_CUDA(cudaGetLastError());
         src = dst;

@@ -91,7 +91,23 @@ def test_ntt_tile_shapes(ctx, tile):
             assert I(bpk.i_ntt_381(S(x), ctx)) == O.ntt_fast(x, inverse=True), (tile, logn)
             assert I(bpk.coset_ntt(S(x), 7, ctx)) == O.ntt_fast(x, coset_shift=7), (tile, logn)
     finally:
-        ctx.set_option("ntt.tile_log2", 11)
+        ctx.set_option("ntt.tile_log2", 10)
+
+
+def test_ntt_direct_and_two_level_twiddles_agree(ctx):
+    """inter-pass twiddles come either from a per-size direct table or from the two-level table"""
+    for logn in (11, 14, 17):
+        x = S(O.random_fr(700 + logn, 1 << logn))
+        ctx.set_option("ntt.direct_max_log2", 0)
+        try:
+            a = bpk.ntt_381(x, ctx)
+            ai = bpk.i_ntt_381(x, ctx)
+        finally:
+            ctx.set_option("ntt.direct_max_log2", 25)
+        assert np.array_equal(a, bpk.ntt_381(x, ctx))
+        assert np.array_equal(ai, bpk.i_ntt_381(x, ctx))
+        if logn <= 14:
+            assert I(a) == O.ntt_fast(I(x))
 
 
 @pytest.mark.parametrize("logn", [0, 1, 5, 10, 12])
