@@ -199,22 +199,85 @@ __global__ void __launch_bounds__(128, BPK_ACC_MINBLOCKS) msm_accumulate_kernel(
     pkeys[2 * t + 1] = pk1;
 }
 
-// K3b: a run that crosses chunk borders starts as slot 1 of some chunk and continues as slot 0 of the
-// following chunks; the thread that owns the head adds the run up and writes the bucket.
+// K3b: a run that crosses chunk borders starts as slot 1 of some chunk t0 (the head) and continues as slot 0
+// of the chunks t0+1 .. t1 whose first pair has the same key.  The thread that owns the head finds t1 by a
+// binary search over the first keys of the chunks (sorted), adds short runs itself and queues long runs
+// (heavy buckets: skewed scalars, narrow top windows) for a block-wide tree reduction, so that no scalar
+// distribution can serialise the merge.
+constexpr uint32_t MERGE_SERIAL_MAX = 24;
+struct LongRun {
+    uint32_t key, t0, t1, pad;
+};
+
 __global__ void __launch_bounds__(128) msm_merge_partials_kernel(const uint32_t* __restrict__ pkeys,
                                                                   const xyzz_t* __restrict__ pvals,
-                                                                  size_t num_chunks, xyzz_t* __restrict__ buckets) {
+                                                                  size_t num_chunks, xyzz_t* __restrict__ buckets,
+                                                                  const uint32_t* __restrict__ keys, uint32_t chunk,
+                                                                  LongRun* __restrict__ long_runs,
+                                                                  uint32_t* __restrict__ long_count) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= num_chunks) return;
     uint32_t k = pkeys[2 * t + 1];
     if (k == INVALID_KEY) return;
+    // chunk t+1 starts with key k (the head is right-open); find the last chunk that does
+    size_t lo = t + 1, hi = num_chunks;
+    while (lo + 1 < hi) {
+        size_t mid = lo + (hi - lo) / 2;
+        if (keys[mid * chunk] <= k)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    const size_t t1 = lo;
+    if (t1 - t > MERGE_SERIAL_MAX) {
+        uint32_t slot = atomicAdd(long_count, 1u);
+        LongRun r;
+        r.key = k;
+        r.t0 = (uint32_t)t;
+        r.t1 = (uint32_t)t1;
+        r.pad = 0;
+        long_runs[slot] = r;
+        return;
+    }
     xyzz_t acc = ld_xyzz(pvals + 2 * t + 1);
-    for (size_t u = t + 1; u < num_chunks; u++) {
-        if (pkeys[2 * u] != k) break;
+    for (size_t u = t + 1; u <= t1; u++) {
         xyzz_t q = ld_xyzz(pvals + 2 * u);
         xyzz_add(acc, q);
     }
     st_xyzz(buckets + k, acc);
+}
+
+// one block per long run: strided partial sums, then a shared-memory tree
+constexpr int MERGE_BLOCK = 256;
+__global__ void __launch_bounds__(MERGE_BLOCK) msm_merge_long_runs_kernel(const LongRun* __restrict__ long_runs,
+                                                                           const uint32_t* __restrict__ long_count,
+                                                                           const xyzz_t* __restrict__ pvals,
+                                                                           xyzz_t* __restrict__ buckets) {
+    __shared__ xyzz_t sm[MERGE_BLOCK];
+    const uint32_t count = *long_count;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = blockIdx.x; i < count; i += gridDim.x) {
+        const LongRun r = long_runs[i];
+        xyzz_t acc = xyzz_t::inf();
+        if (tid == 0) acc = ld_xyzz(pvals + 2 * (size_t)r.t0 + 1);  // the head partial
+        for (size_t u = (size_t)r.t0 + 1 + tid; u <= r.t1; u += MERGE_BLOCK) {
+            xyzz_t q = ld_xyzz(pvals + 2 * u);
+            xyzz_add(acc, q);
+        }
+        sm[tid] = acc;
+        __syncthreads();
+        for (uint32_t s = MERGE_BLOCK / 2; s >= 1; s >>= 1) {
+            if (tid < s) {
+                xyzz_t a = sm[tid];
+                xyzz_t b = sm[tid + s];
+                xyzz_add(a, b);
+                sm[tid] = a;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) st_xyzz(buckets + r.key, sm[0]);
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -424,9 +487,20 @@ int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n,
     }
     {
         StageTimer t(ctx, "msm.merge");
-        msm_merge_partials_kernel<<<(unsigned)((num_chunks + 127) / 128), 128, 0, ctx->stream>>>(pkeys, pvals,
-                                                                                              num_chunks, buckets);
-        count_launch(ctx);
+        LongRun* long_runs;
+        uint32_t* long_count;
+        {
+            void* base;
+            BPK_TRY(ws_reserve(ctx, 11, (num_chunks / MERGE_SERIAL_MAX + 2) * sizeof(LongRun) + 16, &base));
+            long_count = (uint32_t*)base;
+            long_runs = (LongRun*)((char*)base + 16);
+        }
+        BPK_CUDA(cudaMemsetAsync(long_count, 0, sizeof(uint32_t), ctx->stream));
+        msm_merge_partials_kernel<<<(unsigned)((num_chunks + 127) / 128), 128, 0, ctx->stream>>>(
+            pkeys, pvals, num_chunks, buckets, keys_out, chunk, long_runs, long_count);
+        msm_merge_long_runs_kernel<<<(unsigned)ctx->sm_count * 2, MERGE_BLOCK, 0, ctx->stream>>>(long_runs, long_count,
+                                                                                              pvals, buckets);
+        count_launch(ctx, 2);
         BPK_CUDA(cudaGetLastError());
         t.end();
     }

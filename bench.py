@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--no-precompute", action="store_true", help="do not keep [2^(cw)]P_i levels next to the SRS")
     ap.add_argument("--pre-window", type=int, default=0)
+    ap.add_argument("--fanin", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -209,6 +210,8 @@ def main():
         ctx.set_option("msm.window", args.window)
     if args.chunk:
         ctx.set_option("msm.chunk", args.chunk)
+    if args.fanin:
+        ctx.set_option("msm.fanin", args.fanin)
     n_total = 1 << args.logn
     com = mg.ShardedCommitter(pkg, ctx, n_total, TAU, rank, world,
                               precompute=None if args.no_precompute else args.pre_window)

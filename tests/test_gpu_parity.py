@@ -427,6 +427,45 @@ def test_msm_skewed_distributions(ctx, dist):
     assert bpk.point_to_affine(got) == horner_expected(sc, 101)
 
 
+@pytest.mark.parametrize("pre", [None, 0, 21])
+def test_msm_heavy_buckets_take_the_block_merge_path(ctx, pre):
+    """runs of one bucket over thousands of accumulate chunks (all-equal scalars, 4 pairs per thread; a
+    precomputed window size whose top window has only a few buckets) are merged by a block-wide tree"""
+    n = 1 << 15
+    setup = bpk.Setup.generate_srs(n, 101, ctx)
+    if pre is not None:
+        setup.precompute(pre)
+    rng = random.Random(3)
+    cases = [[0x1234567890ABCDEF1234567890ABCDEF] * n,
+             [rng.choice([5, O.Q - 5]) for _ in range(n)],
+             O.random_fr(31, n)]
+    ctx.set_option("msm.chunk", 4)
+    try:
+        for sc in cases:
+            assert bpk.point_to_affine(setup.commit_scalars(S(sc))) == horner_expected(sc, 101)
+    finally:
+        ctx.set_option("msm.chunk", 0)
+        setup.free()
+
+
+def test_msm_all_equal_scalars_at_scale_is_not_serialised(ctx):
+    """2^20 identical scalars: one bucket per window holds every point; must finish in milliseconds"""
+    import time
+    n = 1 << 20
+    setup = bpk.Setup.generate_srs(n, 101, ctx)
+    sc_one = 0xDEADBEEFCAFEBABE1234567
+    arr = np.repeat(S([sc_one]), n, axis=0)
+    setup.commit_scalars(arr)
+    t0 = time.perf_counter()
+    got = setup.commit_scalars(arr)
+    dt = time.perf_counter() - t0
+    setup.free()
+    # sum_i tau^i = (tau^n - 1) / (tau - 1)
+    geo = (pow(101, n, O.Q) - 1) * pow(100, -1, O.Q) % O.Q
+    assert bpk.point_to_affine(got) == O.g1_mul(O.G1_GEN, sc_one * geo % O.Q)
+    assert dt < 0.5, dt
+
+
 @pytest.mark.parametrize("logn", [16, 20])
 def test_msm_full_size_closed_form(ctx, logn):
     n = (1 << logn) + 6  # the prover commits n + 6 coefficients (prover.rs:483-485)
