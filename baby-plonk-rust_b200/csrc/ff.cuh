@@ -649,9 +649,9 @@ BPK_HD Fe<P> to_mont(const Fe<P>& a) {
     return mul(a, Fe<P>::r2());
 }
 
-// a^(p-2): field inversion by Fermat (fp.rs:346-358); 0 -> 0
+// a^(p-2): field inversion by Fermat (fp.rs:346-358); 0 -> 0.  Kept as the cross-check of inv().
 template <class P>
-BPK_HD Fe<P> inv(const Fe<P>& a) {
+BPK_HD Fe<P> inv_fermat(const Fe<P>& a) {
     constexpr int N = P::N;
     Fe<P> r = Fe<P>::one();
     // exponent p - 2, limb by limb with borrow (Fr's low limb is 1)
@@ -673,6 +673,80 @@ BPK_HD Fe<P> inv(const Fe<P>& a) {
         }
     }
     return r;
+}
+
+// Field inversion, 0 -> 0 (same value as fp.rs:346-358 / scalar.rs:416-511, which exponentiate).
+// Binary extended Euclid on the raw limbs: ~2 * bits iterations of shifts and add/sub chains, no
+// multiplications -- about 6x shorter than the 570 dependent Montgomery multiplications of Fermat's
+// method when a single thread has to normalise an MSM result (msm_finalize_kernel).
+template <class P>
+BPK_HD Fe<P> inv(const Fe<P>& a) {
+    constexpr int N = P::N;
+    if (a.is_zero()) return a;
+    uint32_t u[N], v[N];
+    Fe<P> x1 = Fe<P>::zero(), x2 = Fe<P>::zero();
+    x1.l[0] = 1;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        u[i] = a.l[i];
+        v[i] = P::mod(i);
+    }
+    // x <- x / 2 mod p
+    auto halve = [](Fe<P>& x) {
+        uint32_t c = 0;
+        if (x.l[0] & 1u) {
+            x.l[0] = ptx::add_cc(x.l[0], P::mod(0));
+#pragma unroll
+            for (int i = 1; i < N; i++) x.l[i] = ptx::addc_cc(x.l[i], P::mod(i));
+            c = ptx::addc(0u, 0u);
+        }
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) x.l[i] = (x.l[i] >> 1) | (x.l[i + 1] << 31);
+        x.l[N - 1] = (x.l[N - 1] >> 1) | (c << 31);
+    };
+    auto shr1 = [](uint32_t* w) {
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) w[i] = (w[i] >> 1) | (w[i + 1] << 31);
+        w[N - 1] >>= 1;
+    };
+    auto is_one = [](const uint32_t* w) {
+        uint32_t acc = w[0] ^ 1u;
+#pragma unroll
+        for (int i = 1; i < N; i++) acc |= w[i];
+        return acc == 0;
+    };
+#pragma unroll 1
+    while (!is_one(u) && !is_one(v)) {
+#pragma unroll 1
+        while ((u[0] & 1u) == 0) {
+            shr1(u);
+            halve(x1);
+        }
+#pragma unroll 1
+        while ((v[0] & 1u) == 0) {
+            shr1(v);
+            halve(x2);
+        }
+        uint32_t t[N];
+        t[0] = ptx::sub_cc(u[0], v[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) t[i] = ptx::subc_cc(u[i], v[i]);
+        uint32_t borrow = ptx::subc(0u, 0u);
+        if (borrow == 0) {  // u >= v
+#pragma unroll
+            for (int i = 0; i < N; i++) u[i] = t[i];
+            x1 = sub(x1, x2);
+        } else {
+            v[0] = ptx::sub_cc(v[0], u[0]);
+#pragma unroll
+            for (int i = 1; i < N - 1; i++) v[i] = ptx::subc_cc(v[i], u[i]);
+            v[N - 1] = ptx::subc(v[N - 1], u[N - 1]);
+            x2 = sub(x2, x1);
+        }
+    }
+    Fe<P> t = is_one(u) ? x1 : x2;  // (a as a plain integer)^-1 = (value R)^-1
+    // value^-1 R = t R^2: two Montgomery multiplications by R^2
+    return mul(mul(t, Fe<P>::r2()), Fe<P>::r2());
 }
 
 // a^e for a 64-bit exponent (Scalar::pow with [e,0,0,0], scalar.rs:381-392)

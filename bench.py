@@ -365,9 +365,22 @@ def extras(ctx, pkg, com, d_scalars, torch, args):
         n = 1 << logn
         if n > com.hi - com.lo:
             continue
-        mean, best = timed(lambda: ctx.check(lib.bpk_msm_g1_dev(h, com.setup.handle, 0, d_scalars.data_ptr(), n, 1,
+        # its own SRS of exactly n points (window levels sized for n), like a Setup of that size
+        setup = pkg.Setup.generate_srs(n, TAU, ctx)
+        if not args.no_precompute:
+            setup.precompute(0)
+        mean, best = timed(lambda: ctx.check(lib.bpk_msm_g1_dev(h, setup.handle, 0, d_scalars.data_ptr(), n, 1,
                                                                 d_out.data_ptr())))
-        out["msm_ms_2^%d" % logn] = {"mean": mean, "min": best}
+        stages = {}
+        ctx.profile_reset()
+        ctx.profile_enable(True)
+        ctx.check(lib.bpk_msm_g1_dev(h, setup.handle, 0, d_scalars.data_ptr(), n, 1, d_out.data_ptr()))
+        torch.cuda.synchronize()
+        for nm in ("msm.recode", "msm.sort", "msm.accumulate", "msm.merge", "msm.reduce", "msm.finalize"):
+            stages[nm] = round(ctx.profile_get(nm)[0], 4)
+        ctx.profile_enable(False)
+        out["msm_ms_2^%d" % logn] = {"mean": mean, "min": best, "plan": ctx.msm_last_plan(), "stages_ms": stages}
+        setup.free()
     for logn, batch in ((22, 1), (20, 3), (24, 1)):
         n = 1 << logn
         x = torch.from_numpy(gen_scalars(n * batch, 2022).view(np.int64).reshape(-1)).cuda()

@@ -41,6 +41,7 @@ template <class F> static int run_field(const std::string& op, std::istringstrea
     else if (op == "sub") r = sub(a, b);
     else if (op == "neg") r = neg(a);
     else if (op == "inv") r = inv(a);
+    else if (op == "invf") r = inv_fermat(a);
     else if (op == "from_mont") r = from_mont(a);
     else if (op == "to_mont") r = to_mont(a);
     else return 1;

@@ -56,9 +56,12 @@ def test_field_ops(exe):
             lines.append(f"{name} neg {hx(a)}"); exp.append((-a) % mod)
             lines.append(f"{name} from_mont {hx(a)}"); exp.append(a * Rinv % mod)
             lines.append(f"{name} to_mont {hx(a)}"); exp.append(a * R % mod)
-        for a in vals[:12]:
+        for a in vals[:30]:
             # Montgomery inverse: inv(aR) = a^-1 R  ->  on raw value v: v^-1 R^2
             lines.append(f"{name} inv {hx(a)}")
+            exp.append(pow(a, -1, mod) * R * R % mod if a else 0)
+        for a in vals[:10]:
+            lines.append(f"{name} invf {hx(a)}")
             exp.append(pow(a, -1, mod) * R * R % mod if a else 0)
     got = run(exe, lines)
     assert len(got) == len(exp)
