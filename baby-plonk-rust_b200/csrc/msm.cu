@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(128, BPK_ACC_MINBLOCKS) msm_accumulate_kernel(
 // binary search over the first keys of the chunks (sorted), adds short runs itself and queues long runs
 // (heavy buckets: skewed scalars, narrow top windows) for a block-wide tree reduction, so that no scalar
 // distribution can serialise the merge.
-constexpr uint32_t MERGE_SERIAL_MAX = 24;
+constexpr uint32_t MERGE_SERIAL_MAX = 8;    // runs up to this many partials: added by the head's thread
+constexpr uint32_t MERGE_WARP_MAX = 256;    // up to this many: one warp per run; longer: one block per run
 struct LongRun {
     uint32_t key, t0, t1, pad;
 };
@@ -214,7 +215,9 @@ __global__ void __launch_bounds__(128) msm_merge_partials_kernel(const uint32_t*
                                                                   size_t num_chunks, xyzz_t* __restrict__ buckets,
                                                                   const uint32_t* __restrict__ keys, uint32_t chunk,
                                                                   LongRun* __restrict__ long_runs,
-                                                                  uint32_t* __restrict__ long_count) {
+                                                                  uint32_t* __restrict__ long_count,
+                                                                  LongRun* __restrict__ warp_runs,
+                                                                  uint32_t* __restrict__ warp_count) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= num_chunks) return;
     uint32_t k = pkeys[2 * t + 1];
@@ -230,13 +233,15 @@ __global__ void __launch_bounds__(128) msm_merge_partials_kernel(const uint32_t*
     }
     const size_t t1 = lo;
     if (t1 - t > MERGE_SERIAL_MAX) {
-        uint32_t slot = atomicAdd(long_count, 1u);
         LongRun r;
         r.key = k;
         r.t0 = (uint32_t)t;
         r.t1 = (uint32_t)t1;
         r.pad = 0;
-        long_runs[slot] = r;
+        if (t1 - t > MERGE_WARP_MAX)
+            long_runs[atomicAdd(long_count, 1u)] = r;
+        else
+            warp_runs[atomicAdd(warp_count, 1u)] = r;
         return;
     }
     xyzz_t acc = ld_xyzz(pvals + 2 * t + 1);
@@ -245,6 +250,45 @@ __global__ void __launch_bounds__(128) msm_merge_partials_kernel(const uint32_t*
         xyzz_add(acc, q);
     }
     st_xyzz(buckets + k, acc);
+}
+
+__device__ __forceinline__ fp_t shfl_down_fp(const fp_t& v, int delta) {
+    fp_t r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = __shfl_down_sync(0xffffffffu, v.l[i], delta);
+    return r;
+}
+
+// one warp per medium run: lane-strided partial sums, then a shuffle tree
+__global__ void __launch_bounds__(128) msm_merge_warp_runs_kernel(const LongRun* __restrict__ runs,
+                                                                   const uint32_t* __restrict__ run_count,
+                                                                   const xyzz_t* __restrict__ pvals,
+                                                                   xyzz_t* __restrict__ buckets) {
+    const uint32_t count = *run_count;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = warp; i < count; i += nwarps) {
+        const LongRun r = runs[i];
+        xyzz_t acc = xyzz_t::inf();
+        if (lane == 0) acc = ld_xyzz(pvals + 2 * (size_t)r.t0 + 1);  // the head partial
+        for (size_t u = (size_t)r.t0 + 1 + lane; u <= r.t1; u += 32) {
+            xyzz_t q = ld_xyzz(pvals + 2 * u);
+            xyzz_add(acc, q);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int delta = 16; delta >= 1; delta >>= 1) {
+            xyzz_t o;
+            o.X = shfl_down_fp(acc.X, delta);
+            o.Y = shfl_down_fp(acc.Y, delta);
+            o.ZZ = shfl_down_fp(acc.ZZ, delta);
+            o.ZZZ = shfl_down_fp(acc.ZZZ, delta);
+            xyzz_add(acc, o);
+            __syncwarp();
+        }
+        if (lane == 0) st_xyzz(buckets + r.key, acc);
+    }
 }
 
 // one block per long run: strided partial sums, then a shared-memory tree
@@ -487,20 +531,25 @@ int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n,
     }
     {
         StageTimer t(ctx, "msm.merge");
-        LongRun* long_runs;
-        uint32_t* long_count;
+        LongRun *long_runs, *warp_runs;
+        uint32_t *long_count, *warp_count;
         {
             void* base;
-            BPK_TRY(ws_reserve(ctx, 11, (num_chunks / MERGE_SERIAL_MAX + 2) * sizeof(LongRun) + 16, &base));
+            const size_t cap = num_chunks / MERGE_SERIAL_MAX + 2;  // a queued run covers > MERGE_SERIAL_MAX chunks
+            BPK_TRY(ws_reserve(ctx, 11, 2 * cap * sizeof(LongRun) + 16, &base));
             long_count = (uint32_t*)base;
+            warp_count = long_count + 1;
             long_runs = (LongRun*)((char*)base + 16);
+            warp_runs = long_runs + cap;
         }
-        BPK_CUDA(cudaMemsetAsync(long_count, 0, sizeof(uint32_t), ctx->stream));
+        BPK_CUDA(cudaMemsetAsync(long_count, 0, 2 * sizeof(uint32_t), ctx->stream));
         msm_merge_partials_kernel<<<(unsigned)((num_chunks + 127) / 128), 128, 0, ctx->stream>>>(
-            pkeys, pvals, num_chunks, buckets, keys_out, chunk, long_runs, long_count);
+            pkeys, pvals, num_chunks, buckets, keys_out, chunk, long_runs, long_count, warp_runs, warp_count);
+        msm_merge_warp_runs_kernel<<<(unsigned)ctx->sm_count * 4, 128, 0, ctx->stream>>>(warp_runs, warp_count, pvals,
+                                                                                         buckets);
         msm_merge_long_runs_kernel<<<(unsigned)ctx->sm_count * 2, MERGE_BLOCK, 0, ctx->stream>>>(long_runs, long_count,
                                                                                               pvals, buckets);
-        count_launch(ctx, 2);
+        count_launch(ctx, 3);
         BPK_CUDA(cudaGetLastError());
         t.end();
     }
