@@ -132,15 +132,8 @@ BPK_HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) {
 // field parameters
 // ------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)
-// q's two low limbs are 0x00000001 and 0xffffffff.  As immediates ptxas strength-reduces the products with
-// them, which breaks the lo/hi -> IMAD.WIDE.U32.X fusion of BOTH m*q carry chains of every row; read from
-// constant memory the limbs are opaque operands (c[bank][offset]) and every pair fuses.
-static __device__ __constant__ uint32_t FR_MOD_CONST[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
-                                                          0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+// -q^-1 mod 2^32 = 0xffffffff, fetched from memory by the kernels (see FrParams::m0_opaque)
 static __device__ uint32_t FR_M0_GLOBAL = 0xffffffffu;
-static __device__ uint32_t FR_LANE_ZERO[32] = {0};
-static __device__ uint32_t FR_MOD_GLOBAL[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
-                                               0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
 #endif
 
 // scalar.rs:83-88 (MODULUS), :164 (INV -> low 32 bits), :167-172 (R), :175-180 (R2)
@@ -160,32 +153,7 @@ struct FrParams {
         return M0;
 #endif
     }
-    BPK_HD static uint32_t modk(int i) {  // modulus limb as a multiplier operand
-#if defined(__CUDA_ARCH__) && BPK_FR_MODK == 1
-        uint32_t v;
-        asm("ld.const.u32 %0, [%1];" : "=r"(v) : "l"(&FR_MOD_CONST[i]));
-        return v;
-#elif defined(__CUDA_ARCH__) && BPK_FR_MODK == 3
-        // limbs fetched from global memory land in ordinary (per-thread) registers with values ptxas cannot
-        // see: no strength reduction of the 0x00000001 / 0xffffffff limbs, no uniform-register operands
-        // The index detours through a per-lane zero that is itself loaded from memory, so ptxas can neither see
-        // the limb value nor prove the address warp-uniform: the limb stays in a per-thread register.
-        uint32_t v, lane, z;
-        asm("mov.u32 %0, %%laneid;" : "=r"(lane));
-        asm("ld.global.nc.u32 %0, [%1];" : "=r"(z) : "l"(&FR_LANE_ZERO[lane]));
-        asm("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(&FR_MOD_GLOBAL[i + z]));
-        return v;
-#elif defined(__CUDA_ARCH__) && BPK_FR_MODK == 2
-        // ptxas keeps warp-uniform values in uniform registers, and IMAD.WIDE.U32.X has no UR operand form;
-        // a lane-indexed move (every lane reads its own lane) makes the limb a per-thread register
-        uint32_t v = mod(i), lane;
-        asm("mov.u32 %0, %%laneid;" : "=r"(lane));
-        asm("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+r"(v) : "r"(lane));
-        return v;
-#else
-        return mod(i);
-#endif
-    }
+    BPK_HD static constexpr uint32_t modk(int i) { return mod(i); }  // (unused: SPECIAL_LOW64 path)
     BPK_HD static constexpr uint32_t mod(int i) {
         constexpr uint32_t m[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
                                    0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
@@ -580,8 +548,32 @@ BPK_HD Fe<P> mul_rr(const Fe<P>& a, const Fe<P>& b) {
 #ifndef BPK_MUL_IMPL
 #define BPK_MUL_IMPL 0
 #endif
+#if defined(__CUDACC__) && defined(BPK_FP_MUL_CALL)
+// Out-of-line Fp product: a kernel whose hot loop inlines ten ~450-instruction multiplications (the MSM
+// accumulate loop is ~75 KB of SASS) overflows the instruction caches; calling one shared body keeps the
+// loop resident at the price of a register-passing call per product.
+template <class P, int SPLIT>
+BPK_HD Fe<P> mul_cc(const Fe<P>& a, const Fe<P>& b);
+static __device__ __noinline__ Fe<FpParams> fp_mul_call(Fe<FpParams> a, Fe<FpParams> b) {
+    return mul_cc<FpParams, 0>(a, b);
+}
+template <class P>
+struct MulCall {
+    static __device__ __forceinline__ Fe<P> run(const Fe<P>& a, const Fe<P>& b) { return mul_cc<P, 0>(a, b); }
+};
+template <>
+struct MulCall<FpParams> {
+    static __device__ __forceinline__ Fe<FpParams> run(const Fe<FpParams>& a, const Fe<FpParams>& b) {
+        return fp_mul_call(a, b);
+    }
+};
+#endif
+
 template <class P>
 BPK_HD Fe<P> mul(const Fe<P>& a, const Fe<P>& b) {
+#if defined(__CUDA_ARCH__) && defined(BPK_FP_MUL_CALL)
+    return MulCall<P>::run(a, b);
+#endif
 #if BPK_MUL_IMPL == 1
     return mul_rr<P>(a, b);
 #elif BPK_MUL_IMPL >= 2

@@ -19,6 +19,10 @@
 // sorted pair + 96 B point gather -- two orders of magnitude below the arithmetic time.
 #include <cub/device/device_radix_sort.cuh>
 
+// One shared out-of-line body for the Fp product: the accumulate loop otherwise inlines ten ~450-instruction
+// multiplications (~75 KB of SASS) and stalls on instruction fetch (14 % "no_instructions" samples in
+// profiles/r1_final_msm_accumulate_ncu.md); measured 79.9 -> 77.3 ms at 2^24.
+#define BPK_FP_MUL_CALL 1
 #include "internal.cuh"
 
 namespace bpk {
