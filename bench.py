@@ -286,7 +286,8 @@ def main():
     peak = 2.0 * max(chain_rate, fused_rate) / 1e12
     roofline = {
         "bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": peak, "unit": "TIMAD/s",
-        "frac": achieved / peak if peak else None, "traffic": None,
+        "frac": achieved / peak if peak else None,
+        "traffic": ncu_traffic(args, world),
         "algorithmic_imad_per_launch": alg, "kernel_ms": acc_ms,
         "peak_source": "measured on this GPU by bpk_imad_peak: register-only IMAD.WIDE.U32(.X) probe, 2 lo/hi IMADs per "
                        "wide op as in SURVEY 8d; nominal 148 SM x 64 lanes x f_max = %.2f TIMAD/s" % nominal,
@@ -393,6 +394,17 @@ def extras(ctx, pkg, com, d_scalars, torch, args):
                     "imad_alg": (n / 2) * logn * 264 * batch}
         del x, y
     return out
+
+
+def ncu_traffic(args, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full
+    capture (profiles/ncu_traffic.json); only valid for the configuration that capture was taken on"""
+    if world != 1 or args.logn != 24 or args.no_precompute or args.pre_window or args.window or args.chunk:
+        return None
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["dram_bytes_per_launch"])
+    except Exception:
+        return None
 
 
 def measured_hbm_gbs():
