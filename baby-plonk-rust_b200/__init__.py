@@ -93,6 +93,20 @@ _SIGNATURES = {
                                       ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
     "bpk_poly_mul_fr": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                        ctypes.c_size_t, ctypes.c_void_p]),
+    "bpk_poly_mul_fr_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                           ctypes.c_size_t, ctypes.c_void_p]),
+    "bpk_fr_vec_op": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_size_t]),
+    "bpk_fr_scale_powers": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_size_t]),
+    "bpk_fr_poly_eval": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                        ctypes.c_void_p]),
+    "bpk_fr_poly_div_linear": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                              ctypes.c_void_p]),
+    "bpk_fr_poly_div_vanishing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                                 ctypes.c_void_p]),
+    "bpk_plonk_grand_product": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 6 + [ctypes.c_size_t] +
+                                [ctypes.c_void_p] * 5),
     "bpk_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "bpk_profile_reset": (ctypes.c_int, [ctypes.c_void_p]),
     "bpk_profile_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double),

@@ -556,6 +556,82 @@ extern "C" int bpk_poly_mul_fr(bpk_ctx* ctx, const uint64_t* a, size_t la, const
     return BPK_OK;
 }
 
+extern "C" int bpk_poly_mul_fr_dev(bpk_ctx* ctx, const void* d_a, size_t la, const void* d_b, size_t lb, void* d_out) {
+    if (!ctx || !d_a || !d_b || !d_out || la == 0 || lb == 0) return BPK_ERR_INVALID_ARG;
+    size_t target = la + lb - 1;
+    size_t D = 1;
+    while (D < target) D <<= 1;
+    if (D > ((size_t)1 << NTT_MAX_LOG)) return BPK_ERR_TOO_LARGE;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    fr_t* d_buf;
+    BPK_TRY(ws_reserve(ctx, 9, 2 * D * sizeof(fr_t), (void**)&d_buf));
+    BPK_CUDA(cudaMemsetAsync(d_buf, 0, 2 * D * sizeof(fr_t), ctx->stream));
+    BPK_CUDA(cudaMemcpyAsync(d_buf, d_a, la * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    BPK_CUDA(cudaMemcpyAsync(d_buf + D, d_b, lb * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    BPK_TRY(ntt_run(ctx, d_buf, d_buf, D, 2, false, nullptr));
+    BPK_TRY(pointwise_mul(ctx, d_buf, d_buf + D, D));
+    BPK_TRY(ntt_run(ctx, d_buf, d_buf, D, 1, true, nullptr));
+    BPK_CUDA(cudaMemcpyAsync(d_out, d_buf, target * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    return BPK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident Fr vector / polynomial primitives (prover rounds)
+// ------------------------------------------------------------------------------------------------
+extern "C" int bpk_fr_vec_op(bpk_ctx* ctx, int op, const void* d_a, const void* d_b, const uint64_t* scalar_mont,
+                             void* d_out, size_t n) {
+    if (!ctx || op < 0 || op > 6 || (n && (!d_a || !d_out))) return BPK_ERR_INVALID_ARG;
+    const bool needs_b = op == 0 || op == 1 || op == 2 || op == 4 || op == 6;
+    const bool needs_s = op >= 3;
+    if (n && ((needs_b && !d_b) || (needs_s && !scalar_mont))) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    fr_t s = needs_s ? fr_from_host(scalar_mont) : fr_t::zero();
+    return fr_vec_op(ctx, op, (const fr_t*)d_a, (const fr_t*)d_b, s, (fr_t*)d_out, n);
+}
+
+extern "C" int bpk_fr_scale_powers(bpk_ctx* ctx, const void* d_a, const uint64_t g_mont[4], const uint64_t c0_mont[4],
+                                   void* d_out, size_t n) {
+    if (!ctx || !g_mont || !c0_mont || (n && (!d_a || !d_out))) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    return fr_scale_powers(ctx, (const fr_t*)d_a, fr_from_host(g_mont), fr_from_host(c0_mont), (fr_t*)d_out, n);
+}
+
+extern "C" int bpk_fr_poly_eval(bpk_ctx* ctx, const void* d_coeffs, size_t n, const uint64_t x_mont[4],
+                                uint64_t out_mont[4]) {
+    if (!ctx || !x_mont || !out_mont || (n && !d_coeffs)) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    fr_t* d_out;
+    BPK_TRY(ws_reserve(ctx, 10, sizeof(fr_t) * 8, (void**)&d_out));
+    BPK_TRY(fr_poly_eval(ctx, (const fr_t*)d_coeffs, n, fr_from_host(x_mont), d_out));
+    BPK_CUDA(cudaMemcpyAsync(out_mont, d_out, sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    BPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BPK_OK;
+}
+
+extern "C" int bpk_fr_poly_div_linear(bpk_ctx* ctx, const void* d_coeffs, size_t n, const uint64_t root_mont[4],
+                                      void* d_quotient) {
+    if (!ctx || !root_mont || (n >= 2 && (!d_coeffs || !d_quotient))) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    return fr_poly_div_linear(ctx, (const fr_t*)d_coeffs, n, fr_from_host(root_mont), (fr_t*)d_quotient);
+}
+
+extern "C" int bpk_fr_poly_div_vanishing(bpk_ctx* ctx, const void* d_coeffs, size_t len, size_t n, void* d_quotient) {
+    if (!ctx || n == 0 || (len > n && (!d_coeffs || !d_quotient))) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    return fr_poly_div_vanishing(ctx, (const fr_t*)d_coeffs, len, n, (fr_t*)d_quotient);
+}
+
+extern "C" int bpk_plonk_grand_product(bpk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, const void* d_s1,
+                                       const void* d_s2, const void* d_s3, size_t n, const uint64_t beta[4],
+                                       const uint64_t gamma[4], const uint64_t k1[4], const uint64_t k2[4], void* d_z) {
+    if (!ctx || !d_a || !d_b || !d_c || !d_s1 || !d_s2 || !d_s3 || !beta || !gamma || !k1 || !k2 || !d_z)
+        return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    return plonk_grand_product(ctx, (const fr_t*)d_a, (const fr_t*)d_b, (const fr_t*)d_c, (const fr_t*)d_s1,
+                               (const fr_t*)d_s2, (const fr_t*)d_s3, n, fr_from_host(beta), fr_from_host(gamma),
+                               fr_from_host(k1), fr_from_host(k2), (fr_t*)d_z);
+}
+
 // ------------------------------------------------------------------------------------------------
 // instrumentation
 // ------------------------------------------------------------------------------------------------

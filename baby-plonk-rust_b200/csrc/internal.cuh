@@ -135,6 +135,18 @@ int ntt_init_tables(bpk_ctx* ctx);
 int ntt_run(bpk_ctx* ctx, const fr_t* d_in, fr_t* d_out, size_t n, size_t batch, bool inverse,
             const fr_t* shift /* host, Montgomery, or null */);
 int pointwise_mul(bpk_ctx* ctx, fr_t* d_a, const fr_t* d_b, size_t n);
+// out[i] = pre * base^(i << shift), i < count
+int launch_pow_table(bpk_ctx* ctx, fr_t* d_out, const fr_t& base, const fr_t& pre, uint32_t count, uint32_t shift);
+
+// ---- polyops.cu ----
+int fr_vec_op(bpk_ctx* ctx, int op, const fr_t* a, const fr_t* b, const fr_t& s, fr_t* out, size_t n);
+int fr_scale_powers(bpk_ctx* ctx, const fr_t* a, const fr_t& g, const fr_t& c0, fr_t* out, size_t n);
+int fr_poly_eval(bpk_ctx* ctx, const fr_t* c, size_t n, const fr_t& x, fr_t* d_out);
+int fr_poly_div_linear(bpk_ctx* ctx, const fr_t* c, size_t n, const fr_t& root, fr_t* q);
+int fr_poly_div_vanishing(bpk_ctx* ctx, const fr_t* c, size_t len, size_t n, fr_t* q);
+int plonk_grand_product(bpk_ctx* ctx, const fr_t* A, const fr_t* B, const fr_t* C, const fr_t* s1, const fr_t* s2,
+                        const fr_t* s3, size_t n, const fr_t& beta, const fr_t& gamma, const fr_t& k1, const fr_t& k2,
+                        fr_t* Z);
 
 // ---- msm.cu ----
 int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n, unsigned rshift,

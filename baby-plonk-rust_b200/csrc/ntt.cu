@@ -195,7 +195,7 @@ static fr_t fr_from_small(uint64_t x) {  // canonical small integer -> Montgomer
 static const uint64_t ROOT_OF_UNITY_MONT[4] = {0xb9b58d8c5f0e466aull, 0x5b1b4c801819d7ecull,
                                                0x0af53ae352a31e64ull, 0x5bf3adda19e9b27bull};
 
-static int launch_pow_table(bpk_ctx* ctx, fr_t* d_out, const fr_t& base, const fr_t& pre, uint32_t count,
+int launch_pow_table(bpk_ctx* ctx, fr_t* d_out, const fr_t& base, const fr_t& pre, uint32_t count,
                             uint32_t shift) {
     pow_table_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(d_out, base, pre, count, shift);
     count_launch(ctx);

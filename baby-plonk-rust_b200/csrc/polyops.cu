@@ -1,0 +1,271 @@
+// Device-resident Fr vector / polynomial primitives: the O(n) work of the prover rounds that sits between
+// the NTTs and the commitments.  Reference counterparts (all serial Rust on
+// Vec<Scalar>): Polynomial Add / Sub / Mul<Scalar> (src/polynomial.rs:57-187), coeffs_evaluate (:34-45),
+// Div by X^n - 1 and by X - zeta (:314-380), the grand-product loop of round 2 (src/prover.rs:286-317),
+// monomial_z_to_z_omega (src/prover.rs:661-674).  Every value is a canonical Montgomery residue, so the
+// results are bit-identical to the reference's whatever the evaluation order.
+#include <cub/device/device_scan.cuh>
+
+#include "internal.cuh"
+
+namespace bpk {
+
+__device__ __forceinline__ fr_t pld(const fr_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    fr_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void pst(fr_t* p, const fr_t& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+// base^E from a two-level table (lo: base^i, i < 2^13; hi: base^(i << 13))
+__device__ __forceinline__ fr_t ptable(const fr_t* lo, const fr_t* hi, uint32_t E) {
+    fr_t a = pld(lo + (E & ((1u << TW_LO_BITS) - 1)));
+    uint32_t h = E >> TW_LO_BITS;
+    if (h == 0) return a;
+    return mul(a, pld(hi + h));
+}
+
+// ---- elementwise ---------------------------------------------------------------------------------
+// op: 0 a+b, 1 a-b, 2 a*b, 3 a*s, 4 a + s*b, 5 a+s (every element), 6 a - s*b
+__global__ void fr_vec_op_kernel(int op, const fr_t* __restrict__ a, const fr_t* __restrict__ b, fr_t s,
+                                 fr_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t step = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += step) {
+        fr_t x = pld(a + i), r;
+        switch (op) {
+            case 0: r = add(x, pld(b + i)); break;
+            case 1: r = sub(x, pld(b + i)); break;
+            case 2: r = mul(x, pld(b + i)); break;
+            case 3: r = mul(x, s); break;
+            case 4: r = add(x, mul(s, pld(b + i))); break;
+            case 5: r = add(x, s); break;
+            default: r = sub(x, mul(s, pld(b + i))); break;
+        }
+        pst(out + i, r);
+    }
+}
+
+// out[i] = a[i] * c0 * g^i   (lo table already carries c0); reverse != 0 writes out[n-1-i] instead
+__global__ void fr_scale_powers_kernel(const fr_t* __restrict__ a, const fr_t* __restrict__ lo,
+                                       const fr_t* __restrict__ hi, fr_t* __restrict__ out, size_t n, int reverse) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t step = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += step) {
+        fr_t r = mul(pld(a + i), ptable(lo, hi, (uint32_t)i));
+        pst(out + (reverse ? n - 1 - i : i), r);
+    }
+}
+
+// q[i] = I[n-2-i] * zinv^(i+1)  (lo table carries the extra zinv)
+__global__ void fr_div_linear_finish_kernel(const fr_t* __restrict__ I, const fr_t* __restrict__ lo,
+                                            const fr_t* __restrict__ hi, fr_t* __restrict__ q, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t step = (size_t)gridDim.x * blockDim.x;
+    for (; i + 1 < n; i += step) pst(q + i, mul(pld(I + (n - 2 - i)), ptable(lo, hi, (uint32_t)i)));
+}
+
+// q[i] = sum_{k >= 1} c[i + k n]    (c / (X^n - 1), remainder dropped)
+__global__ void fr_div_vanishing_kernel(const fr_t* __restrict__ c, size_t len, size_t n, fr_t* __restrict__ q) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t step = (size_t)gridDim.x * blockDim.x;
+    for (; i + n < len; i += step) {
+        fr_t acc = pld(c + i + n);
+        for (size_t j = i + 2 * n; j < len; j += n) acc = add(acc, pld(c + j));
+        pst(q + i, acc);
+    }
+}
+
+// ---- reductions ------------------------------------------------------------------------------------
+// block partial sums of c[i] * x^i
+__global__ void __launch_bounds__(256) fr_eval_partial_kernel(const fr_t* __restrict__ c, const fr_t* __restrict__ lo,
+                                                               const fr_t* __restrict__ hi, size_t n,
+                                                               fr_t* __restrict__ partial) {
+    __shared__ fr_t sm[256];
+    fr_t acc = fr_t::zero();
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t step = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += step) acc = add(acc, mul(pld(c + i), ptable(lo, hi, (uint32_t)i)));
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s >= 1; s >>= 1) {
+        if ((int)threadIdx.x < s) sm[threadIdx.x] = add(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) pst(partial + blockIdx.x, sm[0]);
+}
+__global__ void __launch_bounds__(256) fr_sum_kernel(const fr_t* __restrict__ in, size_t n, fr_t* __restrict__ out) {
+    __shared__ fr_t sm[256];
+    fr_t acc = fr_t::zero();
+    for (size_t i = threadIdx.x; i < n; i += 256) acc = add(acc, pld(in + i));
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s >= 1; s >>= 1) {
+        if ((int)threadIdx.x < s) sm[threadIdx.x] = add(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) pst(out, sm[0]);
+}
+
+// ---- round 2: grand product -------------------------------------------------------------------------
+// r[i] = (A+b w^i+g)(B+b k1 w^i+g)(C+b k2 w^i+g) / ((A+b s1+g)(B+b s2+g)(C+b s3+g))     prover.rs:286-317
+__global__ void __launch_bounds__(128) plonk_ratio_kernel(const fr_t* __restrict__ A, const fr_t* __restrict__ B,
+                                                           const fr_t* __restrict__ C, const fr_t* __restrict__ s1,
+                                                           const fr_t* __restrict__ s2, const fr_t* __restrict__ s3,
+                                                           const fr_t* __restrict__ tw_lo, const fr_t* __restrict__ tw_hi,
+                                                           uint32_t logn, fr_t beta, fr_t gamma, fr_t k1, fr_t k2,
+                                                           fr_t* __restrict__ r, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) {  // pad so that the exclusive scan yields Z[n]
+        pst(r + n, fr_t::one());
+        return;
+    }
+    fr_t w = ptable(tw_lo, tw_hi, (uint32_t)i << (NTT_MAX_LOG - logn));
+    fr_t bw = mul(beta, w);
+    fr_t a = pld(A + i), b = pld(B + i), c = pld(C + i);
+    fr_t num = mul(mul(add(add(a, bw), gamma), add(add(b, mul(bw, k1)), gamma)), add(add(c, mul(bw, k2)), gamma));
+    fr_t den = mul(mul(add(add(a, mul(beta, pld(s1 + i))), gamma), add(add(b, mul(beta, pld(s2 + i))), gamma)),
+                   add(add(c, mul(beta, pld(s3 + i))), gamma));
+    pst(r + i, mul(num, inv(den)));
+}
+
+struct FrAddOp {
+    __device__ __forceinline__ fr_t operator()(const fr_t& a, const fr_t& b) const { return add(a, b); }
+};
+struct FrMulOp {
+    __device__ __forceinline__ fr_t operator()(const fr_t& a, const fr_t& b) const { return mul(a, b); }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static unsigned grid_for(bpk_ctx* ctx, size_t n, unsigned block) {
+    size_t blocks = (n + block - 1) / block;
+    size_t cap = (size_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks ? blocks : 1);
+}
+
+// two-level power table of g with g^0 replaced by c0 in the low half: lo[i] = c0 g^i, hi[i] = g^(i << 13)
+static int power_tables(bpk_ctx* ctx, const fr_t& g, const fr_t& c0, size_t n, fr_t** lo, fr_t** hi) {
+    size_t hi_count = (n >> TW_LO_BITS) + 1;
+    fr_t* base;
+    BPK_TRY(ws_reserve(ctx, 12, (((size_t)1 << TW_LO_BITS) + hi_count) * sizeof(fr_t), (void**)&base));
+    *lo = base;
+    *hi = base + ((size_t)1 << TW_LO_BITS);
+    BPK_TRY(launch_pow_table(ctx, *lo, g, c0, 1u << TW_LO_BITS, 0));
+    BPK_TRY(launch_pow_table(ctx, *hi, g, fr_t::one(), (uint32_t)hi_count, TW_LO_BITS));
+    return BPK_OK;
+}
+
+int fr_vec_op(bpk_ctx* ctx, int op, const fr_t* a, const fr_t* b, const fr_t& s, fr_t* out, size_t n) {
+    if (n == 0) return BPK_OK;
+    StageTimer t(ctx, "fr.vec_op");
+    fr_vec_op_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(op, a, b, s, out, n);
+    count_launch(ctx);
+    BPK_CUDA(cudaGetLastError());
+    t.end();
+    return BPK_OK;
+}
+
+int fr_scale_powers(bpk_ctx* ctx, const fr_t* a, const fr_t& g, const fr_t& c0, fr_t* out, size_t n) {
+    if (n == 0) return BPK_OK;
+    if (n > ((size_t)1 << NTT_MAX_LOG)) return BPK_ERR_TOO_LARGE;
+    StageTimer t(ctx, "fr.scale_powers");
+    fr_t *lo, *hi;
+    BPK_TRY(power_tables(ctx, g, c0, n, &lo, &hi));
+    fr_scale_powers_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(a, lo, hi, out, n, 0);
+    count_launch(ctx);
+    BPK_CUDA(cudaGetLastError());
+    t.end();
+    return BPK_OK;
+}
+
+int fr_poly_eval(bpk_ctx* ctx, const fr_t* c, size_t n, const fr_t& x, fr_t* d_out) {
+    if (n > ((size_t)1 << NTT_MAX_LOG)) return BPK_ERR_TOO_LARGE;
+    StageTimer t(ctx, "fr.eval");
+    fr_t *lo, *hi;
+    BPK_TRY(power_tables(ctx, x, fr_t::one(), n ? n : 1, &lo, &hi));
+    unsigned blocks = grid_for(ctx, n ? n : 1, 256);
+    fr_t* partial;
+    BPK_TRY(ws_reserve(ctx, 13, (size_t)blocks * sizeof(fr_t), (void**)&partial));
+    fr_eval_partial_kernel<<<blocks, 256, 0, ctx->stream>>>(c, lo, hi, n, partial);
+    fr_sum_kernel<<<1, 256, 0, ctx->stream>>>(partial, blocks, d_out);
+    count_launch(ctx, 2);
+    BPK_CUDA(cudaGetLastError());
+    t.end();
+    return BPK_OK;
+}
+
+// q = c / (X - root), remainder dropped; c has n coefficients, q gets n - 1
+int fr_poly_div_linear(bpk_ctx* ctx, const fr_t* c, size_t n, const fr_t& root, fr_t* q) {
+    if (n < 2) return BPK_OK;
+    if (n > ((size_t)1 << NTT_MAX_LOG)) return BPK_ERR_TOO_LARGE;
+    if (root.is_zero()) {  // c / X: shift down
+        BPK_CUDA(cudaMemcpyAsync(q, c + 1, (n - 1) * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        return BPK_OK;
+    }
+    StageTimer t(ctx, "fr.div_linear");
+    fr_t *lo, *hi, *tmp;
+    BPK_TRY(ws_reserve(ctx, 13, 2 * n * sizeof(fr_t), (void**)&tmp));
+    fr_t* rev = tmp;        // rev[n-1-j] = c_j root^j
+    fr_t* scan = tmp + n;   // inclusive prefix sums of rev
+    BPK_TRY(power_tables(ctx, root, fr_t::one(), n, &lo, &hi));
+    fr_scale_powers_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(c, lo, hi, rev, n, 1);
+    size_t bytes = 0;
+    cub::DeviceScan::InclusiveScan(nullptr, bytes, rev, scan, FrAddOp(), (int)n, ctx->stream);
+    void* cub_tmp;
+    BPK_TRY(ws_reserve(ctx, 14, bytes, &cub_tmp));
+    BPK_CUDA(cub::DeviceScan::InclusiveScan(cub_tmp, bytes, rev, scan, FrAddOp(), (int)n, ctx->stream));
+    // q_i = (sum_{j>i} c_j root^j) root^-(i+1)
+    fr_t rinv = inv(root);
+    BPK_TRY(power_tables(ctx, rinv, rinv, n, &lo, &hi));
+    fr_div_linear_finish_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(scan, lo, hi, q, n);
+    count_launch(ctx, 4);
+    BPK_CUDA(cudaGetLastError());
+    t.end();
+    return BPK_OK;
+}
+
+int fr_poly_div_vanishing(bpk_ctx* ctx, const fr_t* c, size_t len, size_t n, fr_t* q) {
+    if (len <= n) return BPK_OK;
+    StageTimer t(ctx, "fr.div_vanishing");
+    fr_div_vanishing_kernel<<<grid_for(ctx, len - n, 256), 256, 0, ctx->stream>>>(c, len, n, q);
+    count_launch(ctx);
+    BPK_CUDA(cudaGetLastError());
+    t.end();
+    return BPK_OK;
+}
+
+int plonk_grand_product(bpk_ctx* ctx, const fr_t* A, const fr_t* B, const fr_t* C, const fr_t* s1, const fr_t* s2,
+                        const fr_t* s3, size_t n, const fr_t& beta, const fr_t& gamma, const fr_t& k1, const fr_t& k2,
+                        fr_t* Z) {
+    if (n == 0 || (n & (n - 1))) return BPK_ERR_NOT_POW2;
+    uint32_t logn = 0;
+    while (((size_t)1 << logn) < n) logn++;
+    if (logn > (uint32_t)NTT_MAX_LOG) return BPK_ERR_TOO_LARGE;
+    StageTimer t(ctx, "plonk.grand_product");
+    fr_t* r;
+    BPK_TRY(ws_reserve(ctx, 13, (n + 1) * sizeof(fr_t), (void**)&r));
+    plonk_ratio_kernel<<<(unsigned)((n + 1 + 127) / 128), 128, 0, ctx->stream>>>(A, B, C, s1, s2, s3, ctx->tw_lo[0],
+                                                                                ctx->tw_hi[0], logn, beta, gamma, k1, k2,
+                                                                                r, n);
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveScan(nullptr, bytes, r, Z, FrMulOp(), fr_t::one(), (int)(n + 1), ctx->stream);
+    void* cub_tmp;
+    BPK_TRY(ws_reserve(ctx, 14, bytes, &cub_tmp));
+    BPK_CUDA(cub::DeviceScan::ExclusiveScan(cub_tmp, bytes, r, Z, FrMulOp(), fr_t::one(), (int)(n + 1), ctx->stream));
+    count_launch(ctx, 3);
+    BPK_CUDA(cudaGetLastError());
+    t.end();
+    return BPK_OK;
+}
+
+}  // namespace bpk

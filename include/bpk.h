@@ -123,6 +123,33 @@ int bpk_ntt_fr_dev(bpk_ctx* ctx, const void* d_in, void* d_out, size_t n, size_t
 int bpk_poly_mul_fr(bpk_ctx* ctx, const uint64_t* a, size_t la, const uint64_t* b, size_t lb,
                     uint64_t* out);
 
+/* Same with device pointers (la, lb >= 1; d_out holds la + lb - 1 coefficients; may not alias the inputs). */
+int bpk_poly_mul_fr_dev(bpk_ctx* ctx, const void* d_a, size_t la, const void* d_b, size_t lb, void* d_out);
+
+/* ---- device-resident Fr vector / polynomial primitives (the callers' O(n) work) ----
+ * All pointers named d_* are device pointers to n x 4 u64 Montgomery limbs; scalars are host pointers to
+ * 4 u64.  These keep the prover's polynomials in HBM between the NTTs and the commitments. */
+/* op: 0 a+b, 1 a-b, 2 a*b (pointwise), 3 a*s, 4 a + s*b, 5 a+s on every element, 6 a - s*b.
+ * Polynomial Add / Sub / Mul<Scalar> of src/polynomial.rs:57-187 on equal-length operands. d_out may alias. */
+int bpk_fr_vec_op(bpk_ctx* ctx, int op, const void* d_a, const void* d_b, const uint64_t* scalar_mont,
+                  void* d_out, size_t n);
+/* out[i] = a[i] * c0 * g^i: z(X) -> z(wX) (src/prover.rs:661-674), coset shifts. */
+int bpk_fr_scale_powers(bpk_ctx* ctx, const void* d_a, const uint64_t g_mont[4], const uint64_t c0_mont[4],
+                        void* d_out, size_t n);
+/* Polynomial::coeffs_evaluate (src/polynomial.rs:34-45): sum_i c_i x^i. */
+int bpk_fr_poly_eval(bpk_ctx* ctx, const void* d_coeffs, size_t n, const uint64_t x_mont[4], uint64_t out_mont[4]);
+/* impl Div by the linear polynomial X - root (src/polynomial.rs:314-380 as used at src/prover.rs:623-638):
+ * n coefficients in, n - 1 quotient coefficients out, remainder dropped. */
+int bpk_fr_poly_div_linear(bpk_ctx* ctx, const void* d_coeffs, size_t n, const uint64_t root_mont[4],
+                           void* d_quotient);
+/* impl Div by Z_H = X^n - 1 (src/prover.rs:450): len coefficients in, len - n quotient coefficients out. */
+int bpk_fr_poly_div_vanishing(bpk_ctx* ctx, const void* d_coeffs, size_t len, size_t n, void* d_quotient);
+/* Round 2 grand product (src/prover.rs:286-317): d_z receives n + 1 values Z_0 = 1 .. Z_n (Z_n == 1 for a
+ * satisfied permutation; the reference asserts it).  Inputs are the wire and sigma columns on H. */
+int bpk_plonk_grand_product(bpk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, const void* d_s1,
+                            const void* d_s2, const void* d_s3, size_t n, const uint64_t beta[4],
+                            const uint64_t gamma[4], const uint64_t k1[4], const uint64_t k2[4], void* d_z);
+
 /* ---- instrumentation (bench.py, tests) -------------------------------------------------------- */
 /* When enabled, every kernel stage is bracketed by CUDA events on the context's stream. */
 int bpk_profile_enable(bpk_ctx* ctx, int on);
