@@ -632,6 +632,19 @@ extern "C" int bpk_plonk_grand_product(bpk_ctx* ctx, const void* d_a, const void
                                fr_from_host(k1), fr_from_host(k2), (fr_t*)d_z);
 }
 
+extern "C" int bpk_plonk_quotient_evals(bpk_ctx* ctx, const void* d_evals, size_t domain, size_t n,
+                                        const uint64_t beta[4], const uint64_t gamma[4], const uint64_t alpha[4],
+                                        const uint64_t k1[4], const uint64_t k2[4], const uint64_t* zh_inv_mont,
+                                        void* d_out) {
+    if (!ctx || !d_evals || !beta || !gamma || !alpha || !k1 || !k2 || !zh_inv_mont || !d_out) return BPK_ERR_INVALID_ARG;
+    if (n == 0 || domain < n || domain / n > 64) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    fr_t zh[64];
+    for (size_t i = 0; i < domain / n; ++i) zh[i] = fr_from_host(zh_inv_mont + 4 * i);
+    return plonk_quotient_evals(ctx, (const fr_t*)d_evals, domain, n, fr_from_host(beta), fr_from_host(gamma),
+                                fr_from_host(alpha), fr_from_host(k1), fr_from_host(k2), zh, (fr_t*)d_out);
+}
+
 // ------------------------------------------------------------------------------------------------
 // instrumentation
 // ------------------------------------------------------------------------------------------------

@@ -136,6 +136,46 @@ __global__ void __launch_bounds__(128) plonk_ratio_kernel(const fr_t* __restrict
     pst(r + i, mul(num, inv(den)));
 }
 
+// ---- round 3: quotient evaluations on the coset g*<w_D> ------------------------------------------------
+// One fused pass over the D-point coset evaluations of the 15 prover polynomials (rows of `ev`, D apart):
+//   0 a  1 b  2 c  3 z  4 ql  5 qr  6 qm  7 qo  8 qc  9 PI  10 s1  11 s2  12 s3  13 L1  14 X
+// t(x) = [ gate + alpha * perm + alpha^2 * (z - 1) L1 ] / Z_H(x)                      prover.rs:370-452
+//   gate = a ql + b qr + a b qm + c qo + PI + qc
+//   perm = (a + beta x + gamma)(b + beta k1 x + gamma)(c + beta k2 x + gamma) z
+//        - (a + beta s1 + gamma)(b + beta s2 + gamma)(c + beta s3 + gamma) z(w x)
+// z(w x) is z's own row rotated by D / n positions; 1 / Z_H takes D / n distinct values on the coset.
+// The reference forms the same numerator by 16 full polynomial products (3 transforms each) and divides by
+// long division; the polynomial is the same, so its coefficients are.
+struct QuotientParams {
+    fr_t beta, gamma, alpha, alpha2, k1, k2;
+};
+__global__ void __launch_bounds__(256) plonk_quotient_kernel(const fr_t* __restrict__ ev, size_t D, uint32_t ratio,
+                                                              const fr_t* __restrict__ zh_inv, QuotientParams P,
+                                                              fr_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t step = (size_t)gridDim.x * blockDim.x;
+    for (; i < D; i += step) {
+        auto row = [&](int r) { return pld(ev + (size_t)r * D + i); };
+        fr_t a = row(0), b = row(1), c = row(2), z = row(3);
+        fr_t gate = mul(a, row(4));
+        gate = add(gate, mul(b, row(5)));
+        gate = add(gate, mul(mul(a, b), row(6)));
+        gate = add(gate, mul(c, row(7)));
+        gate = add(gate, add(row(8), row(9)));
+        fr_t bx = mul(P.beta, row(14));
+        fr_t ag = add(a, P.gamma), bg = add(b, P.gamma), cg = add(c, P.gamma);
+        fr_t lhs = mul(mul(add(ag, bx), add(bg, mul(bx, P.k1))), mul(add(cg, mul(bx, P.k2)), z));
+        size_t j = i + ratio;
+        if (j >= D) j -= D;
+        fr_t zw = pld(ev + 3 * D + j);
+        fr_t rhs = mul(mul(add(ag, mul(P.beta, row(10))), add(bg, mul(P.beta, row(11)))),
+                       mul(add(cg, mul(P.beta, row(12))), zw));
+        fr_t first = mul(sub(z, fr_t::one()), row(13));
+        fr_t num = add(gate, add(mul(P.alpha, sub(lhs, rhs)), mul(P.alpha2, first)));
+        pst(out + i, mul(num, pld(zh_inv + (i & (ratio - 1)))));
+    }
+}
+
 struct FrAddOp {
     __device__ __forceinline__ fr_t operator()(const fr_t& a, const fr_t& b) const { return add(a, b); }
 };
@@ -264,6 +304,23 @@ int plonk_grand_product(bpk_ctx* ctx, const fr_t* A, const fr_t* B, const fr_t* 
     BPK_CUDA(cub::DeviceScan::ExclusiveScan(cub_tmp, bytes, r, Z, FrMulOp(), fr_t::one(), (int)(n + 1), ctx->stream));
     count_launch(ctx, 3);
     BPK_CUDA(cudaGetLastError());
+    t.end();
+    return BPK_OK;
+}
+
+int plonk_quotient_evals(bpk_ctx* ctx, const fr_t* ev, size_t D, size_t n, const fr_t& beta, const fr_t& gamma,
+                         const fr_t& alpha, const fr_t& k1, const fr_t& k2, const fr_t* zh_inv_host, fr_t* out) {
+    if (D == 0 || (D & (D - 1)) || n == 0 || (n & (n - 1)) || D < n || D / n > 64) return BPK_ERR_INVALID_ARG;
+    uint32_t ratio = (uint32_t)(D / n);
+    StageTimer t(ctx, "plonk.quotient");
+    fr_t* d_zh;
+    BPK_TRY(ws_reserve(ctx, 12, 64 * sizeof(fr_t), (void**)&d_zh));
+    BPK_CUDA(cudaMemcpyAsync(d_zh, zh_inv_host, ratio * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    QuotientParams P{beta, gamma, alpha, mul(alpha, alpha), k1, k2};
+    plonk_quotient_kernel<<<grid_for(ctx, D, 256), 256, 0, ctx->stream>>>(ev, D, ratio, d_zh, P, out);
+    count_launch(ctx);
+    BPK_CUDA(cudaGetLastError());
+    // the pageable H2D copy above is staged by the runtime before it returns, so zh_inv_host may be reused
     t.end();
     return BPK_OK;
 }

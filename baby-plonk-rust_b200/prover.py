@@ -1,0 +1,353 @@
+"""Device-resident PLONK prover: the caller of the MSM / NTT hot path, kept in HBM end to end.
+
+Mirrors ``Prover::prove`` of the reference (src/prover.rs:106-176, rounds 1-5 at :177-647) with every
+polynomial living on the GPU between the transforms and the commitments:
+
+    reference step (serial Rust on Vec<Scalar>)            here (include/bpk.h)
+    -----------------------------------------------------  ------------------------------------------
+    i_ntt_381 of witness / selector / sigma columns        bpk_ntt_fr_dev (batched, inverse)
+    Setup::commit x 9                                      bpk_msm_g1_dev on the resident SRS
+    round 2 accumulator loop (prover.rs:286-317)           bpk_plonk_grand_product (ratio + product scan)
+    round 3: 16 Polynomial::mul + Div by Z_H               coset transforms on a 4n domain +
+      (prover.rs:370-452)                                    bpk_plonk_quotient_evals (one fused pass)
+    coeffs_evaluate at zeta (prover.rs:502-541)            bpk_fr_poly_eval
+    linearisation r(X), opening numerators                 bpk_fr_vec_op (a + s*b passes)
+    Div by X - zeta, X - zeta*omega (prover.rs:623-638)    bpk_fr_poly_div_linear (scaled prefix scan)
+
+The proof is the same group / field elements the reference computes: t(X) is formed from evaluations on
+a coset instead of by long division, which yields the same polynomial whenever the division is exact
+(it is for a satisfying witness; the reference drops the remainder otherwise and its own
+``assert r(zeta) == 0`` -- kept here -- fires).  One documented difference: the reference's Div loses
+interior zero quotient coefficients (polynomial.rs:314-380); with blinded polynomials that event has
+probability ~ n / 2^255 and is not reproduced.
+
+Only a few hundred bytes per round cross PCIe (commitments, evaluations, challenges).  Nothing here
+imports ``oracle/``; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import hashlib
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import (BpkPanic, Context, Setup, FR_MODULUS, _FR_RINV, is_power_of_two, point_to_compressed, root_of_unity,
+               scalars_from_ints)
+from .transcript import PlonkTranscript
+
+Q = FR_MODULUS
+COSET_SHIFT = 7           # multiplicative generator of Fr (scalar.rs GENERATOR): outside every 2-power subgroup
+K1, K2 = 2, 3             # coset representatives of the permutation argument (prover.rs:286-317)
+
+
+def _mont(v: int) -> np.ndarray:
+    return scalars_from_ints([v])[0]
+
+
+class _Scalars:
+    """Montgomery limb arrays for a C call; holds the arrays so the pointers stay valid during the call"""
+
+    def __init__(self, *values: int):
+        self.arrays = [_mont(v) for v in values]
+
+    def ptrs(self):
+        return [a.ctypes.data for a in self.arrays]
+
+
+def _from_mont(limbs) -> int:
+    m = 0
+    for k in range(4):
+        m |= int(limbs[k]) << (64 * k)
+    return m * _FR_RINV % Q
+
+
+@dataclass
+class Proof:
+    """src/verifier.rs:23-40 field order; points as 48-byte compressed G1, scalars canonical ints"""
+    a_1: bytes
+    b_1: bytes
+    c_1: bytes
+    z_1: bytes
+    t_lo_1: bytes
+    t_mid_1: bytes
+    t_hi_1: bytes
+    w_zeta_1: bytes
+    w_zeta_omega_1: bytes
+    a_bar: int
+    b_bar: int
+    c_bar: int
+    s1_bar: int
+    s2_bar: int
+    z_omega_bar: int
+
+    POINTS = ("a_1", "b_1", "c_1", "z_1", "t_lo_1", "t_mid_1", "t_hi_1", "w_zeta_1", "w_zeta_omega_1")
+    SCALARS = ("a_bar", "b_bar", "c_bar", "s1_bar", "s2_bar", "z_omega_bar")
+
+    def to_bytes(self) -> bytes:
+        out = b"".join(getattr(self, k) for k in self.POINTS)
+        out += b"".join(int(getattr(self, k)).to_bytes(32, "little") for k in self.SCALARS)
+        assert len(out) == 624
+        return out
+
+    def sha256(self) -> str:
+        return hashlib.sha256(self.to_bytes()).hexdigest()
+
+
+class DeviceProver:
+    """Prover { group_order, setup, pk } (src/prover.rs:90-104) on one GPU.
+
+    ``selectors`` = (QL, QR, QM, QO, QC) and ``sigmas`` = (S1, S2, S3) are the pre-processed Lagrange
+    columns of src/program.rs:51-147 as uint64[n, 4] Montgomery limbs (what the reference's
+    CommonPreprocessedInput holds).  They are uploaded once; their coefficient forms are recomputed in
+    every ``prove`` exactly as the reference does unless ``cache_preprocessed`` is set.
+    """
+
+    ROWS = ("a", "b", "c", "z", "ql", "qr", "qm", "qo", "qc", "pi", "s1", "s2", "s3")
+
+    def __init__(self, setup: Setup, group_order: int, selectors: Sequence[np.ndarray], sigmas: Sequence[np.ndarray],
+                 cache_preprocessed: bool = False):
+        import torch  # device memory only
+
+        if not is_power_of_two(group_order):
+            raise BpkPanic("assertion failed: is_power_of_two(group_order)")
+        self.torch = torch
+        self.setup = setup
+        self.ctx: Context = setup.ctx
+        self.lib = self.ctx.lib
+        self.n = n = int(group_order)
+        if setup.n < n + 6:
+            raise BpkPanic(f"SRS too short: {setup.n} powers for polynomials of {n + 6} coefficients")
+        self.dev = torch.device("cuda", self.ctx.device)
+        self.domain = 1
+        while self.domain < 3 * n + 6:
+            self.domain <<= 1
+        self.ratio = self.domain // n
+        self.stride = n + 8                       # room for the blinded degrees (n + 6 at most)
+        self.omega = root_of_unity(n)
+        cols = [np.ascontiguousarray(c, dtype=np.uint64).reshape(n, 4) for c in list(selectors) + list(sigmas)]
+        self.pk_lagrange = self._upload(np.stack(cols))          # [8, n, 4]: ql qr qm qo qc s1 s2 s3
+        self.cache_preprocessed = cache_preprocessed
+        self._pk_coeffs = None
+        w = root_of_unity(self.domain)
+        gn = pow(COSET_SHIFT, n, Q)
+        wn = pow(w, n, Q)
+        self._zh_inv = scalars_from_ints([pow((gn * pow(wn, i, Q) - 1) % Q, -1, Q) for i in range(self.ratio)])
+        self._shift = _mont(COSET_SHIFT)
+        self._one = _mont(1)
+
+    # ---- plumbing -------------------------------------------------------------------------------
+    def _upload(self, arr: np.ndarray):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.uint64).view(np.int64))
+        return t.to(self.dev, non_blocking=False)
+
+    def _zeros(self, *shape):
+        return self.torch.zeros(*shape, 4, dtype=self.torch.int64, device=self.dev)
+
+    def _empty(self, *shape):
+        return self.torch.empty(*shape, 4, dtype=self.torch.int64, device=self.dev)
+
+    def _ck(self, st: int, what: str):
+        self.ctx.check(st, what)
+
+    def _vec(self, op: int, a, b, s, out, n: int):
+        sp = None if s is None else s.ctypes.data   # s is a live array owned by the caller's frame
+        self._ck(self.lib.bpk_fr_vec_op(self.ctx.handle, op, a.data_ptr(), 0 if b is None else b.data_ptr(), sp,
+                                        out.data_ptr(), n), "bpk_fr_vec_op")
+
+    def _axpy(self, acc, s: int, p, length: int):
+        """acc[:length] += s * p[:length]"""
+        s %= Q
+        if s == 0:
+            return
+        sm = _mont(s)
+        self._vec(4, acc, p, sm, acc, length)
+
+    def _add_const(self, acc, index: int, s: int):
+        sm = _mont(s % Q)
+        self._vec(5, acc[index:index + 1], None, sm, acc[index:index + 1], 1)
+
+    def _intt(self, src, dst, n: int, batch: int = 1):
+        self._ck(self.lib.bpk_ntt_fr_dev(self.ctx.handle, src.data_ptr(), dst.data_ptr(), n, batch, 1, None),
+                 "bpk_ntt_fr_dev")
+
+    def _eval(self, coeffs, length: int, x: int) -> int:
+        out = np.empty(4, dtype=np.uint64)
+        xm = _mont(x)
+        self._ck(self.lib.bpk_fr_poly_eval(self.ctx.handle, coeffs.data_ptr(), length, xm.ctypes.data,
+                                           out.ctypes.data), "bpk_fr_poly_eval")
+        return _from_mont(out)
+
+    def _commit(self, coeffs, length: int) -> bytes:
+        """Setup::commit (src/setup.rs:32-37) on device-resident coefficients -> compressed G1"""
+        self._ck(self.lib.bpk_msm_g1_dev(self.ctx.handle, self.setup.handle, 0, coeffs.data_ptr(), length, 1,
+                                         self._pt.data_ptr()), "bpk_msm_g1_dev")
+        xyz = self._pt.cpu().numpy().view(np.uint64)
+        return point_to_compressed(xyz)
+
+    def _div_linear(self, coeffs, length: int, root: int, out):
+        rm = _mont(root)
+        self._ck(self.lib.bpk_fr_poly_div_linear(self.ctx.handle, coeffs.data_ptr(), length, rm.ctypes.data,
+                                                 out.data_ptr()), "bpk_fr_poly_div_linear")
+
+    def _preprocessed_coeffs(self):
+        """i_ntt of the eight pre-processed columns (prover.rs round 3 does this on every prove)"""
+        if self._pk_coeffs is not None:
+            return self._pk_coeffs
+        out = self._empty(8, self.n)
+        self._intt(self.pk_lagrange, out, self.n, 8)
+        if self.cache_preprocessed:
+            self._pk_coeffs = out
+        return out
+
+    # ---- Prover::prove --------------------------------------------------------------------------
+    def prove(self, wires: Sequence[np.ndarray], public_inputs: Sequence[int], blinding: Sequence[int],
+              trace: Optional[dict] = None) -> Proof:
+        """``wires`` = the (A, B, C) witness columns on H (uint64[n, 4] Montgomery, prover.rs:177-214 fills
+        them from the witness map); ``public_inputs`` the public values in declaration order;
+        ``blinding`` the 11 scalars b_1..b_11 the reference draws from thread_rng (prover.rs:108-110)."""
+        torch = self.torch
+        n, D, L = self.n, self.domain, self.stride
+        b = [int(x) % Q for x in blinding]
+        if len(b) != 11:
+            raise BpkPanic("11 blinding scalars expected")
+        tr = PlonkTranscript()
+        self._pt = torch.empty(18, dtype=torch.int64, device=self.dev)
+        # blinding values in the order they are patched in: (b2 + b1 X) Z_H etc.
+        blind = self._upload(scalars_from_ints([b[1], b[0], b[3], b[2], b[5], b[4], b[8], b[7], b[6], b[9], b[10]]))
+
+        coef = self._zeros(len(self.ROWS), L)     # coefficient forms, one row per polynomial
+        row = {name: coef[i] for i, name in enumerate(self.ROWS)}
+
+        # ---- round 1 (prover.rs:177-277)
+        W = self._upload(np.stack([np.ascontiguousarray(w, dtype=np.uint64).reshape(n, 4) for w in wires]))
+        tmp = self._empty(3, n)
+        self._intt(W, tmp, n, 3)
+        commits = []
+        for k, name in enumerate(("a", "b", "c")):
+            r = row[name]
+            r[:n].copy_(tmp[k])
+            bl = blind[2 * k:2 * k + 2]
+            self._vec(1, r[0:2], bl, None, r[0:2], 2)          # -(b_lo + b_hi X)
+            r[n:n + 2].copy_(bl)                               # +(b_lo + b_hi X) X^n
+            commits.append(self._commit(r, n + 2))
+        a_1, b_1, c_1 = commits
+        tr.append_point(b"a_1", a_1)
+        tr.append_point(b"b_1", b_1)
+        tr.append_point(b"c_1", c_1)
+        beta = tr.get_and_append_challenge(b"beta")
+        gamma = tr.get_and_append_challenge(b"gamma")
+
+        # ---- round 2 (prover.rs:279-368)
+        Z = self._empty(n + 1)
+        s_l = self.pk_lagrange
+        sc = _Scalars(beta, gamma, K1, K2)
+        self._ck(self.lib.bpk_plonk_grand_product(
+            self.ctx.handle, W[0].data_ptr(), W[1].data_ptr(), W[2].data_ptr(), s_l[5].data_ptr(), s_l[6].data_ptr(),
+            s_l[7].data_ptr(), n, *sc.ptrs(), Z.data_ptr()), "bpk_plonk_grand_product")
+        if _from_mont(Z[n].cpu().numpy().view(np.uint64)) != 1:
+            raise BpkPanic("assertion `left == right` failed: z_values.pop() == Scalar::one()")  # prover.rs:317
+        z = row["z"]
+        self._intt(Z, z, n)
+        bl = blind[6:9]
+        self._vec(1, z[0:3], bl, None, z[0:3], 3)
+        z[n:n + 3].copy_(bl)
+        z_1 = self._commit(z, n + 3)
+        tr.append_point(b"z_1", z_1)
+        alpha = tr.get_and_append_challenge(b"z_1")  # sic: src/transcript.rs:24 labels alpha "z_1"
+
+        # ---- round 3 (prover.rs:370-500)
+        pk = self._preprocessed_coeffs()
+        coef[4:9, :n].copy_(pk[0:5])
+        coef[10:13, :n].copy_(pk[5:8])
+        pi_l = self._zeros(n)
+        if len(public_inputs):
+            pi_l[:len(public_inputs)].copy_(self._upload(scalars_from_ints([(-int(v)) % Q for v in public_inputs])))
+        self._intt(pi_l, row["pi"], n)
+
+        ev = self._zeros(15, D)
+        ev[0:13, :L].copy_(coef)
+        ev[13, :n] = torch.from_numpy(_mont(pow(n, -1, Q)).view(np.int64)).to(self.dev)   # L1 = (1/n) sum X^i
+        ev[14, 1] = torch.from_numpy(self._one.view(np.int64)).to(self.dev)              # the polynomial X
+        self._ck(self.lib.bpk_ntt_fr_dev(self.ctx.handle, ev.data_ptr(), ev.data_ptr(), D, 15, 2,   # 2 = coset
+                                         self._shift.ctypes.data), "bpk_ntt_fr_dev")
+        t = self._empty(D)
+        sc = _Scalars(beta, gamma, alpha, K1, K2)
+        self._ck(self.lib.bpk_plonk_quotient_evals(
+            self.ctx.handle, ev.data_ptr(), D, n, *sc.ptrs(), self._zh_inv.ctypes.data, t.data_ptr()),
+            "bpk_plonk_quotient_evals")
+        del ev
+        self._ck(self.lib.bpk_ntt_fr_dev(self.ctx.handle, t.data_ptr(), t.data_ptr(), D, 1, 3,      # inverse | coset
+                                         self._shift.ctypes.data), "bpk_ntt_fr_dev")
+        # split_t_to_3pieces (prover.rs:454-500): t_lo + b10 X^n | t_mid - b10 + b11 X^n | t_hi - b11
+        parts = self._zeros(3, L)
+        t_lo, t_mid, t_hi = parts[0], parts[1], parts[2]
+        t_lo[:n].copy_(t[0:n])
+        t_lo[n].copy_(blind[9])
+        t_mid[:n].copy_(t[n:2 * n])
+        self._vec(1, t_mid[0:1], blind[9:10], None, t_mid[0:1], 1)
+        t_mid[n].copy_(blind[10])
+        t_hi[:n + 6].copy_(t[2 * n:3 * n + 6])
+        self._vec(1, t_hi[0:1], blind[10:11], None, t_hi[0:1], 1)
+        del t
+        t_lo_1 = self._commit(t_lo, n + 1)
+        t_mid_1 = self._commit(t_mid, n + 1)
+        t_hi_1 = self._commit(t_hi, n + 6)
+        tr.append_point(b"t_lo_1", t_lo_1)
+        tr.append_point(b"t_mid_1", t_mid_1)
+        tr.append_point(b"t_hi_1", t_hi_1)
+        zeta = tr.get_and_append_challenge(b"zeta")
+
+        # ---- round 4 (prover.rs:502-541)
+        a_bar = self._eval(row["a"], n + 2, zeta)
+        b_bar = self._eval(row["b"], n + 2, zeta)
+        c_bar = self._eval(row["c"], n + 2, zeta)
+        s1_bar = self._eval(row["s1"], n, zeta)
+        s2_bar = self._eval(row["s2"], n, zeta)
+        z_omega_bar = self._eval(z, n + 3, zeta * self.omega % Q)       # z(omega X) at zeta
+        for lab, v in ((b"a_eval", a_bar), (b"b_eval", b_bar), (b"c_eval", c_bar), (b"s1_eval", s1_bar),
+                       (b"s2_eval", s2_bar), (b"z_shifted_eval", z_omega_bar)):
+            tr.append_scalar(lab, v)
+        nu = tr.get_and_append_challenge(b"nu")
+
+        # ---- round 5 (prover.rs:543-647): linearisation polynomial r(X), then the two opening quotients
+        zeta_n = pow(zeta, n, Q)
+        zh_zeta = (zeta_n - 1) % Q
+        l1_zeta = zh_zeta * pow(n * (zeta - 1) % Q, -1, Q) % Q            # = (1/n) sum zeta^i
+        pi_zeta = self._eval(row["pi"], n, zeta)
+        f = (a_bar + zeta * beta + gamma) * (b_bar + zeta * beta * K1 + gamma) % Q * (c_bar + zeta * beta * K2 + gamma) % Q
+        g = (a_bar + s1_bar * beta + gamma) * (b_bar + s2_bar * beta + gamma) % Q * z_omega_bar % Q
+        a2 = alpha * alpha % Q
+        r = self._zeros(L)
+        self._axpy(r, a_bar * b_bar, row["qm"], n)
+        self._axpy(r, a_bar, row["ql"], n)
+        self._axpy(r, b_bar, row["qr"], n)
+        self._axpy(r, c_bar, row["qo"], n)
+        self._axpy(r, 1, row["qc"], n)
+        self._axpy(r, alpha * f + a2 * l1_zeta, z, n + 3)
+        self._axpy(r, -alpha * g * beta, row["s3"], n)
+        self._axpy(r, -zh_zeta, t_lo, n + 1)
+        self._axpy(r, -zh_zeta * zeta_n, t_mid, n + 1)
+        self._axpy(r, -zh_zeta * zeta_n * zeta_n, t_hi, n + 6)
+        self._add_const(r, 0, pi_zeta - alpha * g * (c_bar + gamma) - a2 * l1_zeta)
+        if self._eval(r, n + 6, zeta) != 0:
+            raise BpkPanic("assertion `left == right` failed: r.coeffs_evaluate(zeta) == Scalar::zero()")
+        nus = [pow(nu, k, Q) for k in range(6)]
+        for k, name in enumerate(("a", "b", "c", "s1", "s2"), start=1):
+            self._axpy(r, nus[k], row[name], n + 2 if k <= 3 else n)
+        self._add_const(r, 0, -(nus[1] * a_bar + nus[2] * b_bar + nus[3] * c_bar + nus[4] * s1_bar + nus[5] * s2_bar))
+        w_zeta = self._empty(L)
+        self._div_linear(r, n + 6, zeta, w_zeta)
+        self._add_const(z, 0, -z_omega_bar)
+        w_zeta_omega = self._empty(L)
+        self._div_linear(z, n + 3, zeta * self.omega % Q, w_zeta_omega)
+        w_zeta_1 = self._commit(w_zeta, n + 5)
+        w_zeta_omega_1 = self._commit(w_zeta_omega, n + 2)
+        tr.append_point(b"w_zeta_1", w_zeta_1)
+        tr.append_point(b"w_zeta_omega_1", w_zeta_omega_1)
+        mu = tr.get_and_append_challenge(b"mu")
+        if trace is not None:
+            trace.update(beta=beta, gamma=gamma, alpha=alpha, zeta=zeta, nu=nu, mu=mu)
+        return Proof(a_1=a_1, b_1=b_1, c_1=c_1, z_1=z_1, t_lo_1=t_lo_1, t_mid_1=t_mid_1, t_hi_1=t_hi_1,
+                     w_zeta_1=w_zeta_1, w_zeta_omega_1=w_zeta_omega_1, a_bar=a_bar, b_bar=b_bar, c_bar=c_bar,
+                     s1_bar=s1_bar, s2_bar=s2_bar, z_omega_bar=z_omega_bar)

@@ -256,6 +256,19 @@ def g1_to_compressed(pt) -> bytes:
     return bytes(b)
 
 
+def g1_from_compressed(b: bytes):
+    """G1Affine::from_compressed_unchecked.  g1.rs:336-398: y = sqrt(x^3 + 4) with the sign bit"""
+    assert len(b) == 48 and b[0] & 0x80
+    if b[0] & 0x40:
+        return None
+    x = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:], "big")
+    y = pow((x * x * x + 4) % P, (P + 1) // 4, P)   # p = 3 mod 4
+    assert y * y % P == (x * x * x + 4) % P, "not on the curve"
+    if fp_lexicographically_largest(y) != bool(b[0] & 0x20):
+        y = P - y
+    return (x, y)
+
+
 def g1_to_uncompressed(pt) -> bytes:
     """G1Affine::to_uncompressed.  g1.rs:246-260"""
     if pt is None:

@@ -1,0 +1,241 @@
+"""Device-resident prover: the Fr polynomial primitives of include/bpk.h against the
+oracle's restatement of src/polynomial.rs, and whole proofs from baby-plonk-rust_b200/prover.py against
+oracle/plonk.py::prove (the restatement of src/prover.rs) byte for byte."""
+import importlib
+
+import numpy as np
+import pytest
+
+from oracle import bls12_381 as O
+from oracle import plonk as P
+from tests._bpk import bpk
+
+pytestmark = pytest.mark.gpu
+Q = O.Q
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = bpk.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+    return t
+
+
+def up(torch, ints):
+    return torch.from_numpy(bpk.scalars_from_ints(ints).view(np.int64)).cuda()
+
+
+def down(t):
+    return bpk.scalars_to_ints(t.cpu().numpy().view(np.uint64))
+
+
+_keep = []
+
+
+def m(v):
+    """Montgomery limbs of one scalar; kept alive so that `.ctypes.data` stays valid across the C call"""
+    arr = bpk.scalars_from_ints([v])[0].copy()
+    _keep.append(arr)
+    del _keep[:-64]
+    return arr
+
+
+# ---------------------------------------------------------------------------------------------------
+# primitives
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 5, 1000, 70001])
+def test_vec_ops(ctx, torch, n):
+    a, b = O.random_fr(1, n), O.random_fr(2, n)
+    s = O.random_fr(3, 1)[0]
+    da, db = up(torch, a), up(torch, b)
+    out = torch.empty_like(da)
+    want = {0: [(x + y) % Q for x, y in zip(a, b)], 1: [(x - y) % Q for x, y in zip(a, b)],
+            2: [x * y % Q for x, y in zip(a, b)], 3: [x * s % Q for x in a],
+            4: [(x + s * y) % Q for x, y in zip(a, b)], 5: [(x + s) % Q for x in a],
+            6: [(x - s * y) % Q for x, y in zip(a, b)]}
+    for op, w in want.items():
+        st = ctx.lib.bpk_fr_vec_op(ctx.handle, op, da.data_ptr(), db.data_ptr(), m(s).ctypes.data, out.data_ptr(), n)
+        ctx.check(st, "vec_op")
+        assert down(out) == w, op
+
+
+def test_vec_op_argument_errors(ctx, torch):
+    da = up(torch, [1, 2])
+    assert ctx.lib.bpk_fr_vec_op(ctx.handle, 7, da.data_ptr(), da.data_ptr(), None, da.data_ptr(), 2) == -3
+    assert ctx.lib.bpk_fr_vec_op(ctx.handle, 0, da.data_ptr(), None, None, da.data_ptr(), 2) == -3
+    assert ctx.lib.bpk_fr_vec_op(ctx.handle, 3, da.data_ptr(), None, None, da.data_ptr(), 2) == -3
+
+
+@pytest.mark.parametrize("n", [1, 3, 8192, 8193, 50000])
+def test_scale_powers_and_eval(ctx, torch, n):
+    a = O.random_fr(4, n)
+    g, c0, x = O.random_fr(5, 3)
+    da = up(torch, a)
+    out = torch.empty_like(da)
+    ctx.check(ctx.lib.bpk_fr_scale_powers(ctx.handle, da.data_ptr(), m(g).ctypes.data, m(c0).ctypes.data,
+                                          out.data_ptr(), n), "scale_powers")
+    want, p = [], c0
+    for v in a:
+        want.append(v * p % Q)
+        p = p * g % Q
+    assert down(out) == want
+    res = np.empty(4, dtype=np.uint64)
+    ctx.check(ctx.lib.bpk_fr_poly_eval(ctx.handle, da.data_ptr(), n, m(x).ctypes.data, res.ctypes.data), "eval")
+    assert bpk.scalars_to_ints(res)[0] == P.p_eval(a, x)
+
+
+@pytest.mark.parametrize("n", [2, 3, 9, 4099, 66000])
+def test_div_linear_matches_reference_long_division(ctx, torch, n):
+    """impl Div (polynomial.rs:314-380) by X - root; non-exact division: the remainder is dropped"""
+    c = O.random_fr(6, n)
+    root = O.random_fr(7, 1)[0]
+    dc = up(torch, c)
+    q = torch.empty_like(dc)
+    ctx.check(ctx.lib.bpk_fr_poly_div_linear(ctx.handle, dc.data_ptr(), n, m(root).ctypes.data, q.data_ptr()), "div")
+    assert down(q[:n - 1]) == P.p_div(c, [(-root) % Q, 1])
+
+
+@pytest.mark.parametrize("n,extra", [(8, 14), (64, 70), (1024, 2054)])
+def test_div_vanishing(ctx, torch, n, extra):
+    """Div by Z_H = X^n - 1 (prover.rs:450), exact and non-exact"""
+    qq = O.random_fr(8, extra)
+    zh = [Q - 1] + [0] * (n - 1) + [1]
+    prod = (O.Polynomial(qq) * O.Polynomial(zh)).values
+    for c in (prod, O.random_fr(9, n + extra)):
+        dc = up(torch, c)
+        q = torch.empty_like(dc)
+        ctx.check(ctx.lib.bpk_fr_poly_div_vanishing(ctx.handle, dc.data_ptr(), len(c), n, q.data_ptr()), "divzh")
+        assert down(q[:len(c) - n]) == P.p_div(c, zh)
+        if c is prod:
+            assert down(q[:extra]) == qq
+
+
+@pytest.mark.parametrize("la,lb", [(1, 1), (2, 9), (10, 10), (300, 513), (5000, 3)])
+def test_poly_mul_dev(ctx, torch, la, lb):
+    a, b = O.random_fr(10, la), O.random_fr(11, lb)
+    da, db = up(torch, a), up(torch, b)
+    out = torch.empty(la + lb - 1, 4, dtype=torch.int64, device="cuda")
+    ctx.check(ctx.lib.bpk_poly_mul_fr_dev(ctx.handle, da.data_ptr(), la, db.data_ptr(), lb, out.data_ptr()), "mul")
+    assert down(out) == (O.Polynomial(a) * O.Polynomial(b)).values
+
+
+@pytest.mark.parametrize("n", [8, 64, 2048])
+def test_grand_product(ctx, torch, n):
+    """prover.rs:286-317 on a real permutation (Z_n == 1) and on random columns (Z_n != 1)"""
+    prog, wit, _ = P.synthetic_circuit(n, n - 2, seed=n)
+    s1, s2, s3 = prog.sigmas()
+    A = [wit[g.wires[0]] % Q if g.wires[0] is not None else 0 for g in prog.gates] + [0] * (n - len(prog.gates))
+    B = [wit[g.wires[1]] % Q if g.wires[1] is not None else 0 for g in prog.gates] + [0] * (n - len(prog.gates))
+    C = [wit[g.wires[2]] % Q if g.wires[2] is not None else 0 for g in prog.gates] + [0] * (n - len(prog.gates))
+    beta, gamma = O.random_fr(12, 2)
+    roots = O.roots_of_unity(n)
+    for cols in ((A, B, C), (O.random_fr(13, n), B, C)):
+        a, b, c = cols
+        Z = [1]
+        for i in range(n):
+            num = (a[i] + beta * roots[i] + gamma) * (b[i] + beta * 2 * roots[i] + gamma) % Q * (c[i] + beta * 3 * roots[i] + gamma) % Q
+            den = (a[i] + beta * s1[i] + gamma) * (b[i] + beta * s2[i] + gamma) % Q * (c[i] + beta * s3[i] + gamma) % Q
+            Z.append(Z[-1] * num % Q * pow(den, -1, Q) % Q)
+        d = [up(torch, v) for v in (a, b, c, s1, s2, s3)]
+        dz = torch.empty(n + 1, 4, dtype=torch.int64, device="cuda")
+        ctx.check(ctx.lib.bpk_plonk_grand_product(ctx.handle, *[t.data_ptr() for t in d], n, m(beta).ctypes.data,
+                                                  m(gamma).ctypes.data, m(2).ctypes.data, m(3).ctypes.data,
+                                                  dz.data_ptr()), "grand_product")
+        assert down(dz) == Z
+    assert Z[-1] != 1
+
+
+# ---------------------------------------------------------------------------------------------------
+# whole proofs
+# ---------------------------------------------------------------------------------------------------
+def columns(prog, wit):
+    n = prog.n
+    pad = n - len(prog.gates)
+    wires = []
+    for k in range(3):
+        col = [wit[g.wires[k]] % Q if g.wires[k] is not None else 0 for g in prog.gates] + [0] * pad
+        wires.append(bpk.scalars_from_ints(col))
+    sel = [bpk.scalars_from_ints(c) for c in prog.selectors()]
+    sig = [bpk.scalars_from_ints(c) for c in prog.sigmas()]
+    return wires, sel, sig
+
+
+def device_prover(ctx, prog, wit, powers, tau=101, precompute=False, cache=False):
+    prover_mod = importlib.import_module("baby-plonk-rust_b200.prover")
+    setup = bpk.Setup.generate_srs(powers, tau, ctx)
+    if precompute:
+        setup.precompute(0)
+    wires, sel, sig = columns(prog, wit)
+    return prover_mod.DeviceProver(setup, prog.n, sel, sig, cache_preprocessed=cache), wires, setup
+
+
+def as_oracle_proof(proof):
+    kw = {k: O.g1_from_compressed(getattr(proof, k)) for k in proof.POINTS}
+    kw.update({k: getattr(proof, k) for k in proof.SCALARS})
+    return P.Proof(**kw)
+
+
+def test_reference_test_program_on_device(ctx):
+    """tests/verify_proof_test.rs:13-50 with blinding 1..11: same 624 bytes as the CPU restatement and the
+    SHA-256 recorded in SURVEY.md 8c"""
+    prog, wit, pub = P.reference_test_circuit()
+    prover, wires, setup = device_prover(ctx, prog, wit, 14)
+    trace = {}
+    proof = prover.prove(wires, pub, list(range(1, 12)), trace=trace)
+    cpu_trace = {}
+    cpu = P.prove(prog, wit, list(range(1, 12)), P.OracleBackend(O.generate_srs_points(14, 101)), trace=cpu_trace)
+    assert trace == cpu_trace
+    assert proof.to_bytes() == cpu.to_bytes()
+    assert proof.sha256() == "479cc377c535fd831b5fcaf30af5c2756c535a3ddbc20589ab6759843e974967"
+
+
+@pytest.mark.parametrize("n,used,seed,cache", [(16, 10, 7, False), (64, 64, 8, True), (256, 200, 9, False)])
+def test_device_proofs_are_byte_identical(ctx, n, used, seed, cache):
+    prog, wit, pub = P.synthetic_circuit(n, used, seed=seed)
+    prover, wires, setup = device_prover(ctx, prog, wit, n + 6, precompute=(n >= 64), cache=cache)
+    srs = [bpk.point_to_affine(p) for p in setup.powers_of_x()]
+    blinding = O.random_fr(42, 11)
+    proof = prover.prove(wires, pub, blinding)
+    cpu = P.prove(prog, wit, blinding, P.OracleBackend(srs, reference_msm=False))
+    assert proof.to_bytes() == cpu.to_bytes()
+    if cache:   # second proof from cached pre-processed coefficients, different blinding
+        blinding = O.random_fr(43, 11)
+        assert prover.prove(wires, pub, blinding).to_bytes() == \
+            P.prove(prog, wit, blinding, P.OracleBackend(srs, reference_msm=False)).to_bytes()
+
+
+def test_zero_blinding_and_panics(ctx):
+    """b = 0 lowers every degree (the reference strips trailing zeros); a broken witness trips the
+    reference's own assertions"""
+    prog, wit, pub = P.synthetic_circuit(32, 20, seed=5)
+    prover, wires, setup = device_prover(ctx, prog, wit, 38)
+    srs = [bpk.point_to_affine(p) for p in setup.powers_of_x()]
+    proof = prover.prove(wires, pub, [0] * 11)
+    assert proof.to_bytes() == P.prove(prog, wit, [0] * 11, P.OracleBackend(srs, reference_msm=False)).to_bytes()
+    bad = [w.copy() for w in wires]
+    bad[2][3] = bpk.scalars_from_ints([12345])[0]         # breaks the copy constraint of that cell
+    with pytest.raises(bpk.BpkPanic, match="z_values"):
+        prover.prove(bad, pub, list(range(1, 12)))
+    with pytest.raises(bpk.BpkPanic, match="SRS too short"):
+        device_prover(ctx, prog, wit, 37)
+
+
+def test_device_prove_at_scale_self_verifies(ctx):
+    """n = 2^14: checked by the verifier equation in trapdoor form (oracle/plonk.py::verify)"""
+    n = 1 << 14
+    prog, wit, pub = P.synthetic_circuit(n, n - 5, seed=3)
+    prover, wires, setup = device_prover(ctx, prog, wit, n + 6, precompute=True)
+    proof = as_oracle_proof(prover.prove(wires, pub, O.random_fr(43, 11)))
+
+    def commit(coeffs):
+        return bpk.point_to_affine(setup.commit(bpk.Polynomial.from_ints(coeffs)))
+
+    assert P.verify(prog, proof, pub, 101, commit)
+    proof.z_omega_bar = (proof.z_omega_bar + 1) % Q
+    assert not P.verify(prog, proof, pub, 101, commit)
