@@ -107,8 +107,8 @@ _SIGNATURES = {
                                                  ctypes.c_void_p]),
     "bpk_plonk_grand_product": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 6 + [ctypes.c_size_t] +
                                 [ctypes.c_void_p] * 5),
-    "bpk_plonk_quotient_evals": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t] +
-                                 [ctypes.c_void_p] * 7),
+    "bpk_plonk_quotient_evals": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                ctypes.c_size_t] + [ctypes.c_void_p] * 7),
     "bpk_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "bpk_profile_reset": (ctypes.c_int, [ctypes.c_void_p]),
     "bpk_profile_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double),

@@ -241,6 +241,7 @@ extern "C" int bpk_set_option(bpk_ctx* ctx, const char* key, long value) {
     if (k == "msm.window") ctx->opt_msm_window = value;
     else if (k == "msm.chunk") ctx->opt_msm_chunk = value;
     else if (k == "msm.fanin") ctx->opt_msm_fanin = value;
+    else if (k == "msm.reduce") ctx->opt_msm_reduce = value;
     else if (k == "ntt.tile_log2") {
         if (value < 1 || value > 12) return BPK_ERR_INVALID_ARG;
         ctx->opt_ntt_tile_log2 = value;
@@ -632,16 +633,17 @@ extern "C" int bpk_plonk_grand_product(bpk_ctx* ctx, const void* d_a, const void
                                fr_from_host(k1), fr_from_host(k2), (fr_t*)d_z);
 }
 
-extern "C" int bpk_plonk_quotient_evals(bpk_ctx* ctx, const void* d_evals, size_t domain, size_t n,
+extern "C" int bpk_plonk_quotient_evals(bpk_ctx* ctx, const void* d_witness_evals, const void* d_circuit_evals,
+                                        size_t domain, size_t n,
                                         const uint64_t beta[4], const uint64_t gamma[4], const uint64_t alpha[4],
                                         const uint64_t k1[4], const uint64_t k2[4], const uint64_t* zh_inv_mont,
                                         void* d_out) {
-    if (!ctx || !d_evals || !beta || !gamma || !alpha || !k1 || !k2 || !zh_inv_mont || !d_out) return BPK_ERR_INVALID_ARG;
+    if (!ctx || !d_witness_evals || !d_circuit_evals || !beta || !gamma || !alpha || !k1 || !k2 || !zh_inv_mont || !d_out) return BPK_ERR_INVALID_ARG;
     if (n == 0 || domain < n || domain / n > 64) return BPK_ERR_INVALID_ARG;
     BPK_CUDA(cudaSetDevice(ctx->device));
     fr_t zh[64];
     for (size_t i = 0; i < domain / n; ++i) zh[i] = fr_from_host(zh_inv_mont + 4 * i);
-    return plonk_quotient_evals(ctx, (const fr_t*)d_evals, domain, n, fr_from_host(beta), fr_from_host(gamma),
+    return plonk_quotient_evals(ctx, (const fr_t*)d_witness_evals, (const fr_t*)d_circuit_evals, domain, n, fr_from_host(beta), fr_from_host(gamma),
                                 fr_from_host(alpha), fr_from_host(k1), fr_from_host(k2), zh, (fr_t*)d_out);
 }
 

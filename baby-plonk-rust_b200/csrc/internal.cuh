@@ -82,6 +82,7 @@ struct bpk_ctx {
     long opt_msm_window = 0;
     long opt_msm_chunk = 0;
     long opt_msm_fanin = 8;
+    long opt_msm_reduce = 0;  // 0: bit-plane reduction, 1: fan-in running-sum tree (kept for A/B runs)
     long opt_ntt_tile_log2 = 10;  // R x C elements per CTA tile (32 KiB): best of the sweep in profiles/
     long opt_ntt_max_radix_log2 = 10;
     long opt_ntt_threads = 0;
@@ -147,8 +148,8 @@ int fr_poly_div_vanishing(bpk_ctx* ctx, const fr_t* c, size_t len, size_t n, fr_
 int plonk_grand_product(bpk_ctx* ctx, const fr_t* A, const fr_t* B, const fr_t* C, const fr_t* s1, const fr_t* s2,
                         const fr_t* s3, size_t n, const fr_t& beta, const fr_t& gamma, const fr_t& k1, const fr_t& k2,
                         fr_t* Z);
-int plonk_quotient_evals(bpk_ctx* ctx, const fr_t* ev, size_t D, size_t n, const fr_t& beta, const fr_t& gamma,
-                         const fr_t& alpha, const fr_t& k1, const fr_t& k2, const fr_t* zh_inv_host, fr_t* out);
+int plonk_quotient_evals(bpk_ctx* ctx, const fr_t* wv, const fr_t* cv, size_t D, size_t n, const fr_t& beta,
+                         const fr_t& gamma, const fr_t& alpha, const fr_t& k1, const fr_t& k2, const fr_t* zh_inv_host, fr_t* out);
 
 // ---- msm.cu ----
 int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n, unsigned rshift,

@@ -115,30 +115,49 @@ __global__ void __launch_bounds__(256) fr_sum_kernel(const fr_t* __restrict__ in
 
 // ---- round 2: grand product -------------------------------------------------------------------------
 // r[i] = (A+b w^i+g)(B+b k1 w^i+g)(C+b k2 w^i+g) / ((A+b s1+g)(B+b s2+g)(C+b s3+g))     prover.rs:286-317
+// Each thread takes RATIO_BATCH consecutive rows and shares one field inversion between them (Montgomery's
+// trick: invert the product of the denominators, peel the factors off again).
+constexpr int RATIO_BATCH = 4;
 __global__ void __launch_bounds__(128) plonk_ratio_kernel(const fr_t* __restrict__ A, const fr_t* __restrict__ B,
                                                            const fr_t* __restrict__ C, const fr_t* __restrict__ s1,
                                                            const fr_t* __restrict__ s2, const fr_t* __restrict__ s3,
                                                            const fr_t* __restrict__ tw_lo, const fr_t* __restrict__ tw_hi,
                                                            uint32_t logn, fr_t beta, fr_t gamma, fr_t k1, fr_t k2,
                                                            fr_t* __restrict__ r, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n) return;
-    if (i == n) {  // pad so that the exclusive scan yields Z[n]
-        pst(r + n, fr_t::one());
-        return;
+    size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * RATIO_BATCH;
+    if (i0 == 0) pst(r + n, fr_t::one());  // pad so that the exclusive scan yields Z[n]
+    if (i0 >= n) return;
+    fr_t num[RATIO_BATCH], pre[RATIO_BATCH], den[RATIO_BATCH];
+    fr_t run = fr_t::one();
+#pragma unroll
+    for (int j = 0; j < RATIO_BATCH; j++) {
+        size_t i = i0 + j;
+        if (i >= n) {
+            num[j] = den[j] = fr_t::one();
+        } else {
+            fr_t w = ptable(tw_lo, tw_hi, (uint32_t)i << (NTT_MAX_LOG - logn));
+            fr_t bw = mul(beta, w);
+            fr_t a = add(pld(A + i), gamma), b = add(pld(B + i), gamma), c = add(pld(C + i), gamma);
+            num[j] = mul(mul(add(a, bw), add(b, mul(bw, k1))), add(c, mul(bw, k2)));
+            den[j] = mul(mul(add(a, mul(beta, pld(s1 + i))), add(b, mul(beta, pld(s2 + i)))),
+                         add(c, mul(beta, pld(s3 + i))));
+        }
+        pre[j] = run;             // product of den[0..j)
+        run = mul(run, den[j]);
     }
-    fr_t w = ptable(tw_lo, tw_hi, (uint32_t)i << (NTT_MAX_LOG - logn));
-    fr_t bw = mul(beta, w);
-    fr_t a = pld(A + i), b = pld(B + i), c = pld(C + i);
-    fr_t num = mul(mul(add(add(a, bw), gamma), add(add(b, mul(bw, k1)), gamma)), add(add(c, mul(bw, k2)), gamma));
-    fr_t den = mul(mul(add(add(a, mul(beta, pld(s1 + i))), gamma), add(add(b, mul(beta, pld(s2 + i))), gamma)),
-                   add(add(c, mul(beta, pld(s3 + i))), gamma));
-    pst(r + i, mul(num, inv(den)));
+    fr_t suffix_inv = inv(run);   // 1 / prod den
+#pragma unroll
+    for (int j = RATIO_BATCH - 1; j >= 0; j--) {
+        size_t i = i0 + j;
+        if (i < n) pst(r + i, mul(num[j], mul(suffix_inv, pre[j])));   // 1/den[j] = pre[j] / prod den[0..j]
+        suffix_inv = mul(suffix_inv, den[j]);
+    }
 }
 
 // ---- round 3: quotient evaluations on the coset g*<w_D> ------------------------------------------------
-// One fused pass over the D-point coset evaluations of the 15 prover polynomials (rows of `ev`, D apart):
-//   0 a  1 b  2 c  3 z  4 ql  5 qr  6 qm  7 qo  8 qc  9 PI  10 s1  11 s2  12 s3  13 L1  14 X
+// One fused pass over the D-point coset evaluations of the 15 prover polynomials, in two row groups (rows D
+// apart): per-proof rows `wv` = a b c z PI, per-circuit rows `cv` = ql qr qm qo qc s1 s2 s3 L1 X (these can
+// be kept in HBM across proofs).
 // t(x) = [ gate + alpha * perm + alpha^2 * (z - 1) L1 ] / Z_H(x)                      prover.rs:370-452
 //   gate = a ql + b qr + a b qm + c qo + PI + qc
 //   perm = (a + beta x + gamma)(b + beta k1 x + gamma)(c + beta k2 x + gamma) z
@@ -149,28 +168,30 @@ __global__ void __launch_bounds__(128) plonk_ratio_kernel(const fr_t* __restrict
 struct QuotientParams {
     fr_t beta, gamma, alpha, alpha2, k1, k2;
 };
-__global__ void __launch_bounds__(256) plonk_quotient_kernel(const fr_t* __restrict__ ev, size_t D, uint32_t ratio,
+__global__ void __launch_bounds__(256) plonk_quotient_kernel(const fr_t* __restrict__ wv, const fr_t* __restrict__ cv,
+                                                              size_t D, uint32_t ratio,
                                                               const fr_t* __restrict__ zh_inv, QuotientParams P,
                                                               fr_t* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t step = (size_t)gridDim.x * blockDim.x;
     for (; i < D; i += step) {
-        auto row = [&](int r) { return pld(ev + (size_t)r * D + i); };
-        fr_t a = row(0), b = row(1), c = row(2), z = row(3);
-        fr_t gate = mul(a, row(4));
-        gate = add(gate, mul(b, row(5)));
-        gate = add(gate, mul(mul(a, b), row(6)));
-        gate = add(gate, mul(c, row(7)));
-        gate = add(gate, add(row(8), row(9)));
-        fr_t bx = mul(P.beta, row(14));
+        auto wit = [&](int r) { return pld(wv + (size_t)r * D + i); };
+        auto cir = [&](int r) { return pld(cv + (size_t)r * D + i); };
+        fr_t a = wit(0), b = wit(1), c = wit(2), z = wit(3);
+        fr_t gate = mul(a, cir(0));
+        gate = add(gate, mul(b, cir(1)));
+        gate = add(gate, mul(mul(a, b), cir(2)));
+        gate = add(gate, mul(c, cir(3)));
+        gate = add(gate, add(cir(4), wit(4)));
+        fr_t bx = mul(P.beta, cir(9));
         fr_t ag = add(a, P.gamma), bg = add(b, P.gamma), cg = add(c, P.gamma);
         fr_t lhs = mul(mul(add(ag, bx), add(bg, mul(bx, P.k1))), mul(add(cg, mul(bx, P.k2)), z));
         size_t j = i + ratio;
         if (j >= D) j -= D;
-        fr_t zw = pld(ev + 3 * D + j);
-        fr_t rhs = mul(mul(add(ag, mul(P.beta, row(10))), add(bg, mul(P.beta, row(11)))),
-                       mul(add(cg, mul(P.beta, row(12))), zw));
-        fr_t first = mul(sub(z, fr_t::one()), row(13));
+        fr_t zw = pld(wv + 3 * D + j);
+        fr_t rhs = mul(mul(add(ag, mul(P.beta, cir(5))), add(bg, mul(P.beta, cir(6)))),
+                       mul(add(cg, mul(P.beta, cir(7))), zw));
+        fr_t first = mul(sub(z, fr_t::one()), cir(8));
         fr_t num = add(gate, add(mul(P.alpha, sub(lhs, rhs)), mul(P.alpha2, first)));
         pst(out + i, mul(num, pld(zh_inv + (i & (ratio - 1)))));
     }
@@ -294,9 +315,9 @@ int plonk_grand_product(bpk_ctx* ctx, const fr_t* A, const fr_t* B, const fr_t* 
     StageTimer t(ctx, "plonk.grand_product");
     fr_t* r;
     BPK_TRY(ws_reserve(ctx, 13, (n + 1) * sizeof(fr_t), (void**)&r));
-    plonk_ratio_kernel<<<(unsigned)((n + 1 + 127) / 128), 128, 0, ctx->stream>>>(A, B, C, s1, s2, s3, ctx->tw_lo[0],
-                                                                                ctx->tw_hi[0], logn, beta, gamma, k1, k2,
-                                                                                r, n);
+    size_t ratio_threads = (n + RATIO_BATCH - 1) / RATIO_BATCH;
+    plonk_ratio_kernel<<<(unsigned)((ratio_threads + 127) / 128), 128, 0, ctx->stream>>>(
+        A, B, C, s1, s2, s3, ctx->tw_lo[0], ctx->tw_hi[0], logn, beta, gamma, k1, k2, r, n);
     size_t bytes = 0;
     cub::DeviceScan::ExclusiveScan(nullptr, bytes, r, Z, FrMulOp(), fr_t::one(), (int)(n + 1), ctx->stream);
     void* cub_tmp;
@@ -308,7 +329,8 @@ int plonk_grand_product(bpk_ctx* ctx, const fr_t* A, const fr_t* B, const fr_t* 
     return BPK_OK;
 }
 
-int plonk_quotient_evals(bpk_ctx* ctx, const fr_t* ev, size_t D, size_t n, const fr_t& beta, const fr_t& gamma,
+int plonk_quotient_evals(bpk_ctx* ctx, const fr_t* wv, const fr_t* cv, size_t D, size_t n, const fr_t& beta,
+                         const fr_t& gamma,
                          const fr_t& alpha, const fr_t& k1, const fr_t& k2, const fr_t* zh_inv_host, fr_t* out) {
     if (D == 0 || (D & (D - 1)) || n == 0 || (n & (n - 1)) || D < n || D / n > 64) return BPK_ERR_INVALID_ARG;
     uint32_t ratio = (uint32_t)(D / n);
@@ -317,7 +339,7 @@ int plonk_quotient_evals(bpk_ctx* ctx, const fr_t* ev, size_t D, size_t n, const
     BPK_TRY(ws_reserve(ctx, 12, 64 * sizeof(fr_t), (void**)&d_zh));
     BPK_CUDA(cudaMemcpyAsync(d_zh, zh_inv_host, ratio * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
     QuotientParams P{beta, gamma, alpha, mul(alpha, alpha), k1, k2};
-    plonk_quotient_kernel<<<grid_for(ctx, D, 256), 256, 0, ctx->stream>>>(ev, D, ratio, d_zh, P, out);
+    plonk_quotient_kernel<<<grid_for(ctx, D, 256), 256, 0, ctx->stream>>>(wv, cv, D, ratio, d_zh, P, out);
     count_launch(ctx);
     BPK_CUDA(cudaGetLastError());
     // the pageable H2D copy above is staged by the runtime before it returns, so zh_inv_host may be reused

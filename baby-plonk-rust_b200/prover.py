@@ -103,8 +103,6 @@ class DeviceProver:
     every ``prove`` exactly as the reference does unless ``cache_preprocessed`` is set.
     """
 
-    ROWS = ("a", "b", "c", "z", "ql", "qr", "qm", "qo", "qc", "pi", "s1", "s2", "s3")
-
     def __init__(self, setup: Setup, group_order: int, selectors: Sequence[np.ndarray], sigmas: Sequence[np.ndarray],
                  cache_preprocessed: bool = False):
         import torch  # device memory only
@@ -128,7 +126,7 @@ class DeviceProver:
         cols = [np.ascontiguousarray(c, dtype=np.uint64).reshape(n, 4) for c in list(selectors) + list(sigmas)]
         self.pk_lagrange = self._upload(np.stack(cols))          # [8, n, 4]: ql qr qm qo qc s1 s2 s3
         self.cache_preprocessed = cache_preprocessed
-        self._pk_coeffs = None
+        self._pre = None
         w = root_of_unity(self.domain)
         gn = pow(COSET_SHIFT, n, Q)
         wn = pow(w, n, Q)
@@ -190,22 +188,46 @@ class DeviceProver:
         self._ck(self.lib.bpk_fr_poly_div_linear(self.ctx.handle, coeffs.data_ptr(), length, rm.ctypes.data,
                                                  out.data_ptr()), "bpk_fr_poly_div_linear")
 
-    def _preprocessed_coeffs(self):
-        """i_ntt of the eight pre-processed columns (prover.rs round 3 does this on every prove)"""
-        if self._pk_coeffs is not None:
-            return self._pk_coeffs
-        out = self._empty(8, self.n)
-        self._intt(self.pk_lagrange, out, self.n, 8)
+    def _preprocessed(self):
+        """Per-circuit data of round 3: coefficient forms of the eight pre-processed columns (the reference
+        runs these i_ntt_381 on every prove, prover.rs round 3) and the coset evaluations of
+        ql qr qm qo qc s1 s2 s3 L1 X on the quotient domain.  Kept across proofs with cache_preprocessed."""
+        if self._pre is not None:
+            return self._pre
+        n, D = self.n, self.domain
+        coeffs = self._empty(8, n)
+        self._intt(self.pk_lagrange, coeffs, n, 8)
+        cv = self._zeros(10, D)
+        cv[0:8, :n].copy_(coeffs)
+        cv[8, :n] = self.torch.from_numpy(_mont(pow(n, -1, Q)).view(np.int64)).to(self.dev)   # L1 = (1/n) sum X^i
+        cv[9, 1] = self.torch.from_numpy(self._one.view(np.int64)).to(self.dev)              # the polynomial X
+        self._ck(self.lib.bpk_ntt_fr_dev(self.ctx.handle, cv.data_ptr(), cv.data_ptr(), D, 10, 2,    # 2 = coset
+                                         self._shift.ctypes.data), "bpk_ntt_fr_dev")
+        pre = (coeffs, cv)
         if self.cache_preprocessed:
-            self._pk_coeffs = out
-        return out
+            self._pre = pre
+        return pre
+
+    def _wires_on_device(self, wires):
+        """(A, B, C) as one [3, n, 4] device tensor; accepts numpy columns or a CUDA int64 tensor"""
+        torch, n = self.torch, self.n
+        if isinstance(wires, torch.Tensor):
+            if wires.device != self.dev or wires.dtype != torch.int64 or tuple(wires.shape) != (3, n, 4):
+                raise ValueError("expected a CUDA int64 tensor of shape [3, n, 4]")
+            return wires.contiguous()
+        W = self._empty(3, n)
+        for k in range(3):
+            col = np.ascontiguousarray(wires[k], dtype=np.uint64).reshape(n, 4)
+            W[k].copy_(torch.from_numpy(col.view(np.int64)))
+        return W
 
     # ---- Prover::prove --------------------------------------------------------------------------
-    def prove(self, wires: Sequence[np.ndarray], public_inputs: Sequence[int], blinding: Sequence[int],
+    def prove(self, wires, public_inputs: Sequence[int], blinding: Sequence[int],
               trace: Optional[dict] = None) -> Proof:
-        """``wires`` = the (A, B, C) witness columns on H (uint64[n, 4] Montgomery, prover.rs:177-214 fills
-        them from the witness map); ``public_inputs`` the public values in declaration order;
-        ``blinding`` the 11 scalars b_1..b_11 the reference draws from thread_rng (prover.rs:108-110)."""
+        """``wires`` = the (A, B, C) witness columns on H (uint64[n, 4] Montgomery each, or one CUDA int64
+        tensor [3, n, 4]; prover.rs:177-214 fills them from the witness map); ``public_inputs`` the public
+        values in declaration order; ``blinding`` the 11 scalars b_1..b_11 the reference draws from
+        thread_rng (prover.rs:108-110)."""
         torch = self.torch
         n, D, L = self.n, self.domain, self.stride
         b = [int(x) % Q for x in blinding]
@@ -216,11 +238,13 @@ class DeviceProver:
         # blinding values in the order they are patched in: (b2 + b1 X) Z_H etc.
         blind = self._upload(scalars_from_ints([b[1], b[0], b[3], b[2], b[5], b[4], b[8], b[7], b[6], b[9], b[10]]))
 
-        coef = self._zeros(len(self.ROWS), L)     # coefficient forms, one row per polynomial
-        row = {name: coef[i] for i, name in enumerate(self.ROWS)}
+        # coefficient forms of the per-proof polynomials, zero-padded to the quotient domain so that the same
+        # rows are the input of the coset transform of round 3
+        wv = self._zeros(5, D)
+        row = {name: wv[i] for i, name in enumerate(("a", "b", "c", "z", "pi"))}
 
         # ---- round 1 (prover.rs:177-277)
-        W = self._upload(np.stack([np.ascontiguousarray(w, dtype=np.uint64).reshape(n, 4) for w in wires]))
+        W = self._wires_on_device(wires)
         tmp = self._empty(3, n)
         self._intt(W, tmp, n, 3)
         commits = []
@@ -257,26 +281,25 @@ class DeviceProver:
         alpha = tr.get_and_append_challenge(b"z_1")  # sic: src/transcript.rs:24 labels alpha "z_1"
 
         # ---- round 3 (prover.rs:370-500)
-        pk = self._preprocessed_coeffs()
-        coef[4:9, :n].copy_(pk[0:5])
-        coef[10:13, :n].copy_(pk[5:8])
+        pk, cv = self._preprocessed()
+        ql, qr, qm, qo, qc, s1c, s2c, s3c = (pk[i] for i in range(8))
         pi_l = self._zeros(n)
         if len(public_inputs):
             pi_l[:len(public_inputs)].copy_(self._upload(scalars_from_ints([(-int(v)) % Q for v in public_inputs])))
         self._intt(pi_l, row["pi"], n)
-
-        ev = self._zeros(15, D)
-        ev[0:13, :L].copy_(coef)
-        ev[13, :n] = torch.from_numpy(_mont(pow(n, -1, Q)).view(np.int64)).to(self.dev)   # L1 = (1/n) sum X^i
-        ev[14, 1] = torch.from_numpy(self._one.view(np.int64)).to(self.dev)              # the polynomial X
-        self._ck(self.lib.bpk_ntt_fr_dev(self.ctx.handle, ev.data_ptr(), ev.data_ptr(), D, 15, 2,   # 2 = coset
+        # keep the coefficient forms (rounds 4-5 need them), transform a copy
+        keep = self._empty(5, L)
+        keep.copy_(wv[:, :L])
+        self._ck(self.lib.bpk_ntt_fr_dev(self.ctx.handle, wv.data_ptr(), wv.data_ptr(), D, 5, 2,     # 2 = coset
                                          self._shift.ctypes.data), "bpk_ntt_fr_dev")
         t = self._empty(D)
         sc = _Scalars(beta, gamma, alpha, K1, K2)
         self._ck(self.lib.bpk_plonk_quotient_evals(
-            self.ctx.handle, ev.data_ptr(), D, n, *sc.ptrs(), self._zh_inv.ctypes.data, t.data_ptr()),
+            self.ctx.handle, wv.data_ptr(), cv.data_ptr(), D, n, *sc.ptrs(), self._zh_inv.ctypes.data, t.data_ptr()),
             "bpk_plonk_quotient_evals")
-        del ev
+        del wv, cv
+        row = {name: keep[i] for i, name in enumerate(("a", "b", "c", "z", "pi"))}
+        z = row["z"]
         self._ck(self.lib.bpk_ntt_fr_dev(self.ctx.handle, t.data_ptr(), t.data_ptr(), D, 1, 3,      # inverse | coset
                                          self._shift.ctypes.data), "bpk_ntt_fr_dev")
         # split_t_to_3pieces (prover.rs:454-500): t_lo + b10 X^n | t_mid - b10 + b11 X^n | t_hi - b11
@@ -302,8 +325,8 @@ class DeviceProver:
         a_bar = self._eval(row["a"], n + 2, zeta)
         b_bar = self._eval(row["b"], n + 2, zeta)
         c_bar = self._eval(row["c"], n + 2, zeta)
-        s1_bar = self._eval(row["s1"], n, zeta)
-        s2_bar = self._eval(row["s2"], n, zeta)
+        s1_bar = self._eval(s1c, n, zeta)
+        s2_bar = self._eval(s2c, n, zeta)
         z_omega_bar = self._eval(z, n + 3, zeta * self.omega % Q)       # z(omega X) at zeta
         for lab, v in ((b"a_eval", a_bar), (b"b_eval", b_bar), (b"c_eval", c_bar), (b"s1_eval", s1_bar),
                        (b"s2_eval", s2_bar), (b"z_shifted_eval", z_omega_bar)):
@@ -319,13 +342,13 @@ class DeviceProver:
         g = (a_bar + s1_bar * beta + gamma) * (b_bar + s2_bar * beta + gamma) % Q * z_omega_bar % Q
         a2 = alpha * alpha % Q
         r = self._zeros(L)
-        self._axpy(r, a_bar * b_bar, row["qm"], n)
-        self._axpy(r, a_bar, row["ql"], n)
-        self._axpy(r, b_bar, row["qr"], n)
-        self._axpy(r, c_bar, row["qo"], n)
-        self._axpy(r, 1, row["qc"], n)
+        self._axpy(r, a_bar * b_bar, qm, n)
+        self._axpy(r, a_bar, ql, n)
+        self._axpy(r, b_bar, qr, n)
+        self._axpy(r, c_bar, qo, n)
+        self._axpy(r, 1, qc, n)
         self._axpy(r, alpha * f + a2 * l1_zeta, z, n + 3)
-        self._axpy(r, -alpha * g * beta, row["s3"], n)
+        self._axpy(r, -alpha * g * beta, s3c, n)
         self._axpy(r, -zh_zeta, t_lo, n + 1)
         self._axpy(r, -zh_zeta * zeta_n, t_mid, n + 1)
         self._axpy(r, -zh_zeta * zeta_n * zeta_n, t_hi, n + 6)
@@ -333,8 +356,9 @@ class DeviceProver:
         if self._eval(r, n + 6, zeta) != 0:
             raise BpkPanic("assertion `left == right` failed: r.coeffs_evaluate(zeta) == Scalar::zero()")
         nus = [pow(nu, k, Q) for k in range(6)]
-        for k, name in enumerate(("a", "b", "c", "s1", "s2"), start=1):
-            self._axpy(r, nus[k], row[name], n + 2 if k <= 3 else n)
+        for k, (poly, length) in enumerate(((row["a"], n + 2), (row["b"], n + 2), (row["c"], n + 2), (s1c, n), (s2c, n)),
+                                           start=1):
+            self._axpy(r, nus[k], poly, length)
         self._add_const(r, 0, -(nus[1] * a_bar + nus[2] * b_bar + nus[3] * c_bar + nus[4] * s1_bar + nus[5] * s2_bar))
         w_zeta = self._empty(L)
         self._div_linear(r, n + 6, zeta, w_zeta)

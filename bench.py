@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--no-precompute", action="store_true", help="do not keep [2^(cw)]P_i levels next to the SRS")
     ap.add_argument("--pre-window", type=int, default=0)
     ap.add_argument("--fanin", type=int, default=0)
+    ap.add_argument("--reduce", type=int, default=0, help="1: running-sum tree instead of the bit-plane reduction")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -212,6 +213,8 @@ def main():
         ctx.set_option("msm.chunk", args.chunk)
     if args.fanin:
         ctx.set_option("msm.fanin", args.fanin)
+    if args.reduce:
+        ctx.set_option("msm.reduce", args.reduce)
     n_total = 1 << args.logn
     com = mg.ShardedCommitter(pkg, ctx, n_total, TAU, rank, world,
                               precompute=None if args.no_precompute else args.pre_window)

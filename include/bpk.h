@@ -150,14 +150,16 @@ int bpk_plonk_grand_product(bpk_ctx* ctx, const void* d_a, const void* d_b, cons
                             const void* d_s2, const void* d_s3, size_t n, const uint64_t beta[4],
                             const uint64_t gamma[4], const uint64_t k1[4], const uint64_t k2[4], void* d_z);
 
-/* Round 3 quotient (src/prover.rs:370-452) in evaluation form.  d_evals holds 15 rows of `domain` values
- * each: the evaluations on the coset g * <w_domain> of a, b, c, z, ql, qr, qm, qo, qc, PI, s1, s2, s3, L1, X
- * (in that order; produce them with bpk_ntt_fr_dev and a shift).  d_out receives the evaluations of
+/* Round 3 quotient (src/prover.rs:370-452) in evaluation form.  Inputs are evaluations on the coset
+ * g * <w_domain> (produce them with bpk_ntt_fr_dev and a shift), rows `domain` values apart:
+ *   d_witness_evals  5 rows, per proof:    a, b, c, z, PI
+ *   d_circuit_evals 10 rows, per circuit:  ql, qr, qm, qo, qc, s1, s2, s3, L1, X   (may stay resident)
+ * d_out receives the evaluations of
  *   t = [a ql + b qr + a b qm + c qo + PI + qc + alpha * perm + alpha^2 (z - 1) L1] / Z_H
  * on the same coset; zh_inv_mont holds the domain / n (<= 64) values 1 / Z_H(g w_domain^i), i < domain / n. */
-int bpk_plonk_quotient_evals(bpk_ctx* ctx, const void* d_evals, size_t domain, size_t n, const uint64_t beta[4],
-                             const uint64_t gamma[4], const uint64_t alpha[4], const uint64_t k1[4],
-                             const uint64_t k2[4], const uint64_t* zh_inv_mont, void* d_out);
+int bpk_plonk_quotient_evals(bpk_ctx* ctx, const void* d_witness_evals, const void* d_circuit_evals, size_t domain,
+                             size_t n, const uint64_t beta[4], const uint64_t gamma[4], const uint64_t alpha[4],
+                             const uint64_t k1[4], const uint64_t k2[4], const uint64_t* zh_inv_mont, void* d_out);
 
 /* ---- instrumentation (bench.py, tests) -------------------------------------------------------- */
 /* When enabled, every kernel stage is bracketed by CUDA events on the context's stream. */

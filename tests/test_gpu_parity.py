@@ -395,14 +395,34 @@ def test_msm_reduce_fanin(ctx, fanin):
     setup = bpk.Setup.generate_srs(n, 101, ctx)
     sc = O.random_fr(fanin, n)
     ctx.set_option("msm.fanin", fanin)
+    ctx.set_option("msm.reduce", 1)       # the running-sum tree kept for A/B runs
     try:
         for w in (0, 7, 12):
             ctx.set_option("msm.window", w)
             assert bpk.point_to_affine(setup.commit_scalars(S(sc))) == horner_expected(sc, 101)
     finally:
         ctx.set_option("msm.fanin", 8)
+        ctx.set_option("msm.reduce", 0)
         ctx.set_option("msm.window", 0)
         setup.free()
+
+
+@pytest.mark.parametrize("window", [2, 3, 5, 11, 12, 13, 16])
+def test_msm_bit_plane_reduction_all_window_sizes(ctx, window):
+    """default reduction: every plane count, with one chunk per plane (window <= 11), exactly one (12) and
+    several (13, 16), own windows and precomputed levels"""
+    n = 3000
+    setup = bpk.Setup.generate_srs(n, 101, ctx)
+    sc = O.random_fr(100 + window, n)
+    want = horner_expected(sc, 101)
+    ctx.set_option("msm.window", window)
+    try:
+        assert bpk.point_to_affine(setup.commit_scalars(S(sc))) == want
+    finally:
+        ctx.set_option("msm.window", 0)
+    setup.precompute(window)
+    assert bpk.point_to_affine(setup.commit_scalars(S(sc))) == want
+    setup.free()
 
 
 @pytest.mark.parametrize("dist", ["witness", "all_equal", "tiny", "qminus1", "two_values"])
