@@ -27,6 +27,14 @@ def shard_bounds(n: int, world_size: int, rank: int) -> Tuple[int, int]:
     return lo, hi
 
 
+def slice_of_prefix(lo: int, hi: int, length: int) -> Tuple[int, int]:
+    """the part of this rank's index range [lo, hi) that lies inside the first `length` indices, as
+    (offset, count); count == 0 when the prefix ends before the rank's range starts"""
+    if length <= lo:
+        return lo, 0
+    return lo, min(hi, length) - lo
+
+
 def all_gather_points(partial, group=None):
     """gather one 18-limb point per rank -> tensor [world, 18] in rank order (int64 carrier dtype)"""
     import torch
@@ -79,6 +87,26 @@ class ShardedCommitter:
         dist.all_gather_into_tensor(self.d_gather.view(-1), self.d_partial, group=self.group)
         self.ctx.check(lib.bpk_g1_sum_dev(h, self.d_gather.data_ptr(), self.world, self.d_out.data_ptr()),
                        "bpk_g1_sum_dev")
+        return self.d_out
+
+    def commit_prefix(self, d_coeffs, length: int) -> "torch.Tensor":
+        """Commitment to a polynomial of `length` <= n_total coefficients that is REPLICATED in every
+        rank's HBM (the device prover keeps identical state on all ranks): each rank multiplies only its own
+        index range of the coefficients with its SRS slice, then the partial sums are gathered and added.
+        d_coeffs: int64 tensor [>= length, 4].  Returns the normalised commitment, identical on every rank."""
+        import torch.distributed as dist
+
+        lib, h = self.ctx.lib, self.ctx.handle
+        first, count = slice_of_prefix(self.lo, self.hi, length)
+        src = d_coeffs[first:first + count] if count else d_coeffs[0:1]
+        final = 1 if self.world == 1 else 0
+        dst = self.d_out if self.world == 1 else self.d_partial
+        self.ctx.check(lib.bpk_msm_g1_dev(h, self.setup.handle, 0, src.data_ptr(), count, final, dst.data_ptr()),
+                       "bpk_msm_g1_dev")
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.d_gather.view(-1), self.d_partial, group=self.group)
+            self.ctx.check(lib.bpk_g1_sum_dev(h, self.d_gather.data_ptr(), self.world, self.d_out.data_ptr()),
+                           "bpk_g1_sum_dev")
         return self.d_out
 
     def commit_host(self, scalars: np.ndarray, d_staging) -> np.ndarray:

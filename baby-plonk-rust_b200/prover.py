@@ -104,7 +104,7 @@ class DeviceProver:
     """
 
     def __init__(self, setup: Setup, group_order: int, selectors: Sequence[np.ndarray], sigmas: Sequence[np.ndarray],
-                 cache_preprocessed: bool = False):
+                 cache_preprocessed: bool = False, committer=None):
         import torch  # device memory only
 
         if not is_power_of_two(group_order):
@@ -114,8 +114,12 @@ class DeviceProver:
         self.ctx: Context = setup.ctx
         self.lib = self.ctx.lib
         self.n = n = int(group_order)
-        if setup.n < n + 6:
-            raise BpkPanic(f"SRS too short: {setup.n} powers for polynomials of {n + 6} coefficients")
+        # multi-GPU: `committer` (multi_gpu.ShardedCommitter) owns this rank's slice of the SRS; every rank
+        # runs the same prover on replicated polynomials and only the nine commitments are sharded
+        self.committer = committer
+        srs_len = setup.n if committer is None else self._committer_total(committer)
+        if srs_len < n + 6:
+            raise BpkPanic(f"SRS too short: {srs_len} powers for polynomials of {n + 6} coefficients")
         self.dev = torch.device("cuda", self.ctx.device)
         self.domain = 1
         while self.domain < 3 * n + 6:
@@ -133,6 +137,16 @@ class DeviceProver:
         self._zh_inv = scalars_from_ints([pow((gn * pow(wn, i, Q) - 1) % Q, -1, Q) for i in range(self.ratio)])
         self._shift = _mont(COSET_SHIFT)
         self._one = _mont(1)
+
+    @staticmethod
+    def _committer_total(committer) -> int:
+        import torch.distributed as dist
+
+        if committer.world == 1:
+            return committer.hi
+        t = committer.d_partial.new_tensor([committer.hi])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=committer.group)
+        return int(t.item())
 
     # ---- plumbing -------------------------------------------------------------------------------
     def _upload(self, arr: np.ndarray):
@@ -178,6 +192,9 @@ class DeviceProver:
 
     def _commit(self, coeffs, length: int) -> bytes:
         """Setup::commit (src/setup.rs:32-37) on device-resident coefficients -> compressed G1"""
+        if self.committer is not None:
+            xyz = self.committer.commit_prefix(coeffs, length).cpu().numpy().view(np.uint64)
+            return point_to_compressed(xyz)
         self._ck(self.lib.bpk_msm_g1_dev(self.ctx.handle, self.setup.handle, 0, coeffs.data_ptr(), length, 1,
                                          self._pt.data_ptr()), "bpk_msm_g1_dev")
         xyz = self._pt.cpu().numpy().view(np.uint64)

@@ -179,6 +179,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--logn", type=int, default=24)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-prove", action="store_true", help="skip the device-resident PLONK prove line in `also`")
+    ap.add_argument("--prove-logn", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--window", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
@@ -308,6 +310,10 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_extras:
         also = extras(ctx, pkg, com, d_scalars, torch, args)
+    if not args.no_extras and not args.no_prove:
+        prove = prove_extra(ctx, pkg, mg, torch, args, rank, world)   # every rank takes part (sharded commitments)
+        if rank == 0:
+            also["prove_s_2^%d_gates" % args.prove_logn] = prove
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         n_s = min(n_total, threads << 13)
@@ -397,6 +403,49 @@ def extras(ctx, pkg, com, d_scalars, torch, args):
                     "imad_alg": (n / 2) * logn * 264 * batch}
         del x, y
     return out
+
+
+def prove_extra(ctx, pkg, mg, torch, args, rank, world):
+    """BASELINE.json configs[3]: PLONK prove at 2^20 gates (SURVEY 8d C4 circuit family), device-resident
+    prover with the nine commitments sharded over the ranks.  Wall clock per proof, witness columns starting
+    in host memory (H2D inside), proof bytes back on the host.  `prove_s` recomputes the circuit's
+    pre-processed polynomials in every proof as the reference does; `prove_cached_s` keeps them in HBM."""
+    import torch.distributed as dist
+
+    prover_mod = importlib.import_module("baby-plonk-rust_b200.prover")
+    synthetic = importlib.import_module("baby-plonk-rust_b200.synthetic")
+    n = 1 << args.prove_logn
+    t0 = time.time()
+    circ = synthetic.chain_circuit(n, n - 3, seed=2)
+    t_circ = time.time() - t0
+    com = mg.ShardedCommitter(pkg, ctx, n + 8, TAU, rank, world, precompute=None if args.no_precompute else 0)
+    blinding = [int.from_bytes(gen_scalars(11, 42)[i].tobytes(), "little") for i in range(11)]
+    res = {"gates": n, "circuit": "chain: out public; c_k <== c_{k-1} * y_k / c_{k-1} + y_k alternating",
+           "circuit_build_s": round(t_circ, 2), "n_gpus": world}
+    sha = None
+    for key, cache in (("prove_s", False), ("prove_cached_s", True)):
+        prover = prover_mod.DeviceProver(com.setup, n, circ["selectors"], circ["sigmas"], cache_preprocessed=cache,
+                                         committer=com)
+        ts = []
+        for it in range(4):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.time()
+            proof = prover.prove(circ["wires"], circ["public_inputs"], blinding)
+            ts.append(time.time() - t0)
+        if sha is None:
+            sha = proof.sha256()
+        assert proof.sha256() == sha
+        t = torch.tensor(ts[1:], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[key] = {"mean": float(t.mean()), "min": float(t.min())}
+        del prover
+    res["proof_sha256"] = sha
+    ctx.profile_reset()
+    com.setup.free()
+    return res
 
 
 def ncu_traffic(args, world):

@@ -78,3 +78,18 @@ def test_shard_bounds_tile_the_range():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         mg.shard_bounds(10, 2, 2)
+
+
+def test_slice_of_prefix_tiles_every_prefix():
+    """sharded commitment of a replicated polynomial: the per-rank slices of the first `length` indices are
+    disjoint, ordered and cover the prefix exactly"""
+    mg = importlib.import_module("baby-plonk-rust_b200.multi_gpu")
+    for n, world in ((14, 2), (1030, 4), (4104, 8), (5, 8)):
+        bounds = [mg.shard_bounds(n, world, r) for r in range(world)]
+        for length in (0, 1, n // 2, n - 1, n):
+            covered = []
+            for lo, hi in bounds:
+                first, count = mg.slice_of_prefix(lo, hi, length)
+                assert count >= 0 and first == lo and first + count <= hi
+                covered.extend(range(first, first + count))
+            assert covered == list(range(length))
