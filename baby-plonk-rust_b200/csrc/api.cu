@@ -360,13 +360,12 @@ extern "C" int bpk_srs_precompute(bpk_ctx* ctx, uint64_t handle, unsigned window
     if (e.pre_c != 0) return window_bits == 0 || window_bits == e.pre_c ? BPK_OK : BPK_ERR_INVALID_ARG;
     if (e.n == 0) return BPK_OK;
     unsigned c = window_bits;
-    if (c == 0) {  // adds W n, bucket tree ~4.2 * 2^(c-1) addition equivalents, ~0.25 ms of serial depth per 3 bits
-        double best = 1e300;
-        for (unsigned cc = 8; cc <= 23; cc++) {
-            double W = (256 + cc - 1) / cc;
-            double cost = W * (double)e.n + 4.2 * (double)(1u << (cc - 1)) + 7.0e5 * ((cc - 1) / 3.0);
-            if (cost < best) { best = cost; c = cc; }
-        }
+    if (c == 0) {
+        // measured optimum of the sweep in profiles/r1_precompute_window_sweep.md (c = 7..22 at 2^16..2^22, c = 21..23
+        // at 2^24): larger windows trade W n pair additions against 2^(c-1) bucket additions and tree depth
+        unsigned lg = 0;
+        while (((size_t)1 << lg) < e.n) lg++;
+        c = lg <= 16 ? 8 : lg == 17 ? 16 : lg <= 19 ? 19 : lg <= 22 ? 20 : lg == 23 ? 21 : 22;
     }
     if (c < 2 || c > 24) return BPK_ERR_INVALID_ARG;
     const unsigned W = (256 + c - 1) / c;

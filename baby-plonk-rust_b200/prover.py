@@ -27,6 +27,7 @@ imports ``oracle/``; there is no CPU fallback.
 from __future__ import annotations
 
 import hashlib
+import time
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -251,6 +252,7 @@ class DeviceProver:
         if len(b) != 11:
             raise BpkPanic("11 blinding scalars expected")
         tr = PlonkTranscript()
+        marks = [("start", time.perf_counter())]
         self._pt = torch.empty(18, dtype=torch.int64, device=self.dev)
         # blinding values in the order they are patched in: (b2 + b1 X) Z_H etc.
         blind = self._upload(scalars_from_ints([b[1], b[0], b[3], b[2], b[5], b[4], b[8], b[7], b[6], b[9], b[10]]))
@@ -278,6 +280,7 @@ class DeviceProver:
         tr.append_point(b"c_1", c_1)
         beta = tr.get_and_append_challenge(b"beta")
         gamma = tr.get_and_append_challenge(b"gamma")
+        marks.append(("round1", time.perf_counter()))
 
         # ---- round 2 (prover.rs:279-368)
         Z = self._empty(n + 1)
@@ -296,6 +299,7 @@ class DeviceProver:
         z_1 = self._commit(z, n + 3)
         tr.append_point(b"z_1", z_1)
         alpha = tr.get_and_append_challenge(b"z_1")  # sic: src/transcript.rs:24 labels alpha "z_1"
+        marks.append(("round2", time.perf_counter()))
 
         # ---- round 3 (prover.rs:370-500)
         pk, cv = self._preprocessed()
@@ -337,6 +341,7 @@ class DeviceProver:
         tr.append_point(b"t_mid_1", t_mid_1)
         tr.append_point(b"t_hi_1", t_hi_1)
         zeta = tr.get_and_append_challenge(b"zeta")
+        marks.append(("round3", time.perf_counter()))
 
         # ---- round 4 (prover.rs:502-541)
         a_bar = self._eval(row["a"], n + 2, zeta)
@@ -349,6 +354,7 @@ class DeviceProver:
                        (b"s2_eval", s2_bar), (b"z_shifted_eval", z_omega_bar)):
             tr.append_scalar(lab, v)
         nu = tr.get_and_append_challenge(b"nu")
+        marks.append(("round4", time.perf_counter()))
 
         # ---- round 5 (prover.rs:543-647): linearisation polynomial r(X), then the two opening quotients
         zeta_n = pow(zeta, n, Q)
@@ -387,6 +393,8 @@ class DeviceProver:
         tr.append_point(b"w_zeta_1", w_zeta_1)
         tr.append_point(b"w_zeta_omega_1", w_zeta_omega_1)
         mu = tr.get_and_append_challenge(b"mu")
+        marks.append(("round5", time.perf_counter()))
+        self.last_round_seconds = {marks[i][0]: marks[i][1] - marks[i - 1][1] for i in range(1, len(marks))}
         if trace is not None:
             trace.update(beta=beta, gamma=gamma, alpha=alpha, zeta=zeta, nu=nu, mu=mu)
         return Proof(a_1=a_1, b_1=b_1, c_1=c_1, z_1=z_1, t_lo_1=t_lo_1, t_mid_1=t_mid_1, t_hi_1=t_hi_1,

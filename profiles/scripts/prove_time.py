@@ -13,16 +13,26 @@ synthetic = importlib.import_module("baby-plonk-rust_b200.synthetic")
 logn = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 n = 1 << logn
-ctx = bpk.Context(0)
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+cache = os.environ.get("PROVE_CACHE", "0") == "1"
+if world > 1:
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+mg = importlib.import_module("baby-plonk-rust_b200.multi_gpu")
+ctx = bpk.Context(local)
 t0 = time.time()
 circ = synthetic.chain_circuit(n, n - 3, seed=2)
 t_circ = time.time() - t0
 t0 = time.time()
-setup = bpk.Setup.generate_srs(n + 8, 101, ctx)
-setup.precompute(0)
+com = mg.ShardedCommitter(bpk, ctx, n + 8, 101, rank, world, precompute=0)
+setup = com.setup
 ctx.synchronize()
 t_setup = time.time() - t0
-prover = prover_mod.DeviceProver(setup, n, circ["selectors"], circ["sigmas"])
+prover = prover_mod.DeviceProver(setup, n, circ["selectors"], circ["sigmas"], cache_preprocessed=cache, committer=com)
 blinding = list(range(11, 22))
 times = []
 for r in range(reps + 1):
@@ -41,6 +51,10 @@ for name in ("msm.recode", "msm.sort", "msm.accumulate", "msm.merge", "msm.reduc
             stages[name] = [round(ms, 3), cnt]
     except Exception:
         pass
-print(json.dumps({"logn": logn, "circuit_s": round(t_circ, 2), "srs_setup_s": round(t_setup, 2),
-                  "prove_s": [round(t, 4) for t in times], "proof_sha256": proof.sha256(), "stages_ms": stages,
+if rank == 0:
+  print(json.dumps({"logn": logn, "world": world, "cache": cache, "circuit_s": round(t_circ, 2), "srs_setup_s": round(t_setup, 2),
+                  "prove_s": [round(t, 4) for t in times], "proof_sha256": proof.sha256(), "rounds_s": {k: round(v, 4) for k, v in prover.last_round_seconds.items()}, "stages_ms": stages,
                   "plan": ctx.msm_last_plan()}))
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
