@@ -364,7 +364,8 @@ extern "C" int bpk_srs_precompute(bpk_ctx* ctx, uint64_t handle, unsigned window
         // measured optimum of the sweep in profiles/r1_precompute_window_sweep.md (c = 7..22 at 2^16..2^22, c = 21..23
         // at 2^24): larger windows trade W n pair additions against 2^(c-1) bucket additions and tree depth
         unsigned lg = 0;
-        while (((size_t)1 << lg) < e.n) lg++;
+        while (((size_t)2 << lg) <= e.n) lg++;          // floor(log2 n)
+        if (e.n - ((size_t)1 << lg) >= ((size_t)1 << lg) / 2) lg++;  // nearest power of two
         c = lg <= 16 ? 8 : lg == 17 ? 16 : lg <= 19 ? 19 : lg <= 22 ? 20 : lg == 23 ? 21 : 22;
     }
     if (c < 2 || c > 24) return BPK_ERR_INVALID_ARG;
