@@ -12,7 +12,7 @@ int cuda_fail(bpk_ctx* ctx, cudaError_t e, const char* what, const char* file, i
 }
 
 int ws_reserve(bpk_ctx* ctx, int slot, size_t bytes, void** out) {
-    DeviceBuffer& b = ctx->ws[slot];
+    DeviceBuffer& b = ctx->ws[slot + WS_SLOTS * ctx->ws_bank];
     if (bytes == 0) bytes = 16;
     if (b.bytes < bytes) {
         if (b.ptr) {
@@ -217,6 +217,11 @@ extern "C" void bpk_destroy(bpk_ctx* ctx) {
             if (t) cudaFree(t);
     }
     if (ctx->gen_table) cudaFree(ctx->gen_table);
+    for (int l = 0; l < MSM_LANES; l++) {
+        if (ctx->lane_stream[l]) cudaStreamDestroy(ctx->lane_stream[l]);
+        if (ctx->lane_done[l]) cudaEventDestroy(ctx->lane_done[l]);
+    }
+    if (ctx->lane_fork) cudaEventDestroy(ctx->lane_fork);
     delete ctx;
 }
 
@@ -242,6 +247,7 @@ extern "C" int bpk_set_option(bpk_ctx* ctx, const char* key, long value) {
     else if (k == "msm.chunk") ctx->opt_msm_chunk = value;
     else if (k == "msm.fanin") ctx->opt_msm_fanin = value;
     else if (k == "msm.reduce") ctx->opt_msm_reduce = value;
+    else if (k == "msm.lanes") ctx->opt_msm_lanes = value;
     else if (k == "ntt.tile_log2") {
         if (value < 1 || value > 12) return BPK_ERR_INVALID_ARG;
         ctx->opt_ntt_tile_log2 = value;
@@ -464,6 +470,56 @@ extern "C" int bpk_msm_g1_dev(bpk_ctx* ctx, uint64_t handle, size_t first, const
     BPK_CUDA(cudaSetDevice(ctx->device));
     return msm_run(ctx, msm_points_of(it->second, first), (const fr_t*)d_scalars_mont, n, 0, normalise != 0,
                    (uint64_t*)d_out_xyz);
+}
+
+extern "C" int bpk_msm_g1_dev_batch(bpk_ctx* ctx, uint64_t handle, size_t count, const void* const* d_scalars_mont,
+                                    const size_t* first, const size_t* n, int normalise, void* d_out_xyz) {
+    if (!ctx || !d_out_xyz || (count && (!d_scalars_mont || !first || !n))) return BPK_ERR_INVALID_ARG;
+    auto it = ctx->srs.find(handle);
+    if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
+    for (size_t i = 0; i < count; i++) {
+        if (n[i] && !d_scalars_mont[i]) return BPK_ERR_INVALID_ARG;
+        if (first[i] > it->second.n || n[i] > it->second.n - first[i]) return BPK_ERR_INVALID_ARG;
+    }
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    uint64_t* out = (uint64_t*)d_out_xyz;
+    if (count <= 1 || ctx->opt_msm_lanes <= 1) {
+        for (size_t i = 0; i < count; i++)
+            BPK_TRY(msm_run(ctx, msm_points_of(it->second, first[i]), (const fr_t*)d_scalars_mont[i], n[i], 0,
+                            normalise != 0, out + 18 * i));
+        return BPK_OK;
+    }
+    // Each MSM goes to its own stream and workspace bank.  The accumulate kernels share the SMs (they are
+    // arithmetic-bound, so nothing is lost), while the latency-bound stages of one MSM -- sort, merge, bucket
+    // reduction, normalisation -- run under the accumulation of the others instead of idling the GPU.
+    const int lanes = (int)(ctx->opt_msm_lanes < MSM_LANES ? ctx->opt_msm_lanes : MSM_LANES);
+    if (!ctx->lane_fork) BPK_CUDA(cudaEventCreateWithFlags(&ctx->lane_fork, cudaEventDisableTiming));
+    for (int l = 0; l < lanes; l++) {
+        if (!ctx->lane_stream[l]) BPK_CUDA(cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
+        if (!ctx->lane_done[l]) BPK_CUDA(cudaEventCreateWithFlags(&ctx->lane_done[l], cudaEventDisableTiming));
+    }
+    cudaStream_t main_stream = ctx->stream;
+    BPK_CUDA(cudaEventRecord(ctx->lane_fork, main_stream));
+    int status = BPK_OK;
+    for (size_t i = 0; i < count && status == BPK_OK; i++) {
+        const int l = (int)(i % lanes);
+        if (i < (size_t)lanes) {
+            cudaError_t e = cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_fork, 0);
+            if (e != cudaSuccess) { status = cuda_fail(ctx, e, "lane fork", __FILE__, __LINE__); break; }
+        }
+        ctx->stream = ctx->lane_stream[l];
+        ctx->ws_bank = l + 1;
+        status = msm_run(ctx, msm_points_of(it->second, first[i]), (const fr_t*)d_scalars_mont[i], n[i], 0,
+                         normalise != 0, out + 18 * i);
+        ctx->stream = main_stream;
+        ctx->ws_bank = 0;
+    }
+    for (int l = 0; l < lanes; l++) {  // join, also on the error path so that the caller's stream stays ordered
+        cudaError_t e = cudaEventRecord(ctx->lane_done[l], ctx->lane_stream[l]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(main_stream, ctx->lane_done[l], 0);
+        if (e != cudaSuccess && status == BPK_OK) status = cuda_fail(ctx, e, "lane join", __FILE__, __LINE__);
+    }
+    return status;
 }
 
 extern "C" int bpk_g1_sum(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n, uint64_t out_xyz[18]) {

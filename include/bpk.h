@@ -95,6 +95,13 @@ int bpk_msm_g1_points(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n_points,
  * over NCCL and added by bpk_g1_sum. */
 int bpk_msm_g1_dev(bpk_ctx* ctx, uint64_t handle, size_t first, const void* d_scalars_mont,
                    size_t n, int normalise, void* d_out_xyz);
+/* `count` independent commitments on the same SRS in one call (the three wire commitments of round 1, the three
+ * quotient pieces of round 3, the two opening proofs of round 5: src/prover.rs:253-262, 487-497, 640-646).
+ * d_scalars_mont, first and n are host arrays of `count` device pointers / slice starts / lengths; d_out_xyz
+ * receives count x 18 u64.  The MSMs run on separate streams, so the latency-bound stages of one overlap the
+ * accumulation of the others; results are those of `count` bpk_msm_g1_dev calls. */
+int bpk_msm_g1_dev_batch(bpk_ctx* ctx, uint64_t handle, size_t count, const void* const* d_scalars_mont,
+                         const size_t* first, const size_t* n, int normalise, void* d_out_xyz);
 /* Sum of n projective points (host pointers, 18 u64 each), normalised: the post-gather step. */
 int bpk_g1_sum(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n, uint64_t out_xyz[18]);
 /* Same with device pointers (the gathered partials stay in HBM). */

@@ -204,10 +204,13 @@ def test_device_proofs_are_byte_identical(ctx, n, used, seed, cache):
     proof = prover.prove(wires, pub, blinding)
     cpu = P.prove(prog, wit, blinding, P.OracleBackend(srs, reference_msm=False))
     assert proof.to_bytes() == cpu.to_bytes()
-    if cache:   # second proof from cached pre-processed coefficients, different blinding
+    if cache:   # second proof from cached pre-processed coefficients, different blinding; witness handed over
+        import torch   # as a pinned host tensor and as a device tensor
         blinding = O.random_fr(43, 11)
-        assert prover.prove(wires, pub, blinding).to_bytes() == \
-            P.prove(prog, wit, blinding, P.OracleBackend(srs, reference_msm=False)).to_bytes()
+        want = P.prove(prog, wit, blinding, P.OracleBackend(srs, reference_msm=False)).to_bytes()
+        host = torch.from_numpy(np.stack(wires).view(np.int64)).pin_memory()
+        assert prover.prove(host, pub, blinding).to_bytes() == want
+        assert prover.prove(host.cuda(), pub, blinding).to_bytes() == want
 
 
 def test_zero_blinding_and_panics(ctx):

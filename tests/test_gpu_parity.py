@@ -550,3 +550,39 @@ def test_kernels_really_launch(ctx):
     assert l_acc == 1 and ms_acc > 0
     assert ctx.launch_count() >= 8
     setup.free()
+
+
+@pytest.mark.parametrize("lanes", [1, 3])
+def test_msm_batch_on_streams_matches_single_calls(ctx, lanes):
+    """bpk_msm_g1_dev_batch: several commitments on one SRS, concurrently on separate streams / workspace banks;
+    five MSMs over three lanes, different slices and lengths incl. an empty one"""
+    import ctypes
+
+    import torch
+
+    n = 5000
+    setup = bpk.Setup.generate_srs(n, 101, ctx).precompute(0)
+    srs = None
+    specs = [(0, n), (0, 1234), (100, 4000), (4999, 1), (7, 0)]
+    sc = [O.random_fr(200 + i, max(cnt, 1)) for i, (_, cnt) in enumerate(specs)]
+    d = [torch.from_numpy(S(v).view(np.int64)).cuda() for v in sc]
+    k = len(specs)
+    ptrs = (ctypes.c_void_p * k)(*[t.data_ptr() for t in d])
+    firsts = (ctypes.c_size_t * k)(*[f for f, _ in specs])
+    lens = (ctypes.c_size_t * k)(*[c for _, c in specs])
+    out = torch.zeros((k, 18), dtype=torch.int64, device="cuda")
+    ctx.set_option("msm.lanes", lanes)
+    try:
+        for _ in range(2):   # second round reuses the lane workspaces
+            ctx.check(ctx.lib.bpk_msm_g1_dev_batch(ctx.handle, setup.handle, k, ptrs, firsts, lens, 1, out.data_ptr()),
+                      "batch")
+            got = out.cpu().numpy().view(np.uint64)
+            for i, (first, cnt) in enumerate(specs):
+                acc = 0
+                for j in reversed(range(cnt)):
+                    acc = (acc * 101 + sc[i][j]) % O.Q
+                want = O.g1_mul(O.G1_GEN, acc * pow(101, first, O.Q) % O.Q) if cnt else None
+                assert bpk.point_to_affine(got[i]) == want, (lanes, i)
+    finally:
+        ctx.set_option("msm.lanes", 3)
+        setup.free()
