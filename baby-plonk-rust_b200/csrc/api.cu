@@ -252,7 +252,7 @@ extern "C" int bpk_set_option(bpk_ctx* ctx, const char* key, long value) {
         if (value < 1 || value > 12) return BPK_ERR_INVALID_ARG;
         ctx->opt_ntt_tile_log2 = value;
     } else if (k == "ntt.max_radix_log2") {
-        if (value < 1 || value > 12) return BPK_ERR_INVALID_ARG;
+        if (value < 0 || value > 12) return BPK_ERR_INVALID_ARG;
         ctx->opt_ntt_max_radix_log2 = value;
     } else if (k == "ntt.direct_max_log2") {
         if (value < 0 || value > 28) return BPK_ERR_INVALID_ARG;
@@ -260,7 +260,8 @@ extern "C" int bpk_set_option(bpk_ctx* ctx, const char* key, long value) {
     } else if (k == "ntt.threads") {
         if (value != 0 && (value < 32 || value > 1024 || (value & 31))) return BPK_ERR_INVALID_ARG;
         ctx->opt_ntt_threads = value;
-    } else if (k == "imad.mode") ctx->opt_imad_mode = value;
+    } else if (k == "ntt.kernel") ctx->opt_ntt_kernel = value;
+    else if (k == "imad.mode") ctx->opt_imad_mode = value;
     else return BPK_ERR_INVALID_ARG;
     return BPK_OK;
 }

@@ -91,8 +91,9 @@ struct bpk_ctx {
     long opt_msm_lanes = bpk::MSM_LANES;  // 1: bpk_msm_g1_dev_batch runs its MSMs one after the other
     long opt_msm_reduce = 0;  // 0: bit-plane reduction, 1: fan-in running-sum tree (kept for A/B runs)
     long opt_ntt_tile_log2 = 10;  // R x C elements per CTA tile (32 KiB): best of the sweep in profiles/
-    long opt_ntt_max_radix_log2 = 10;
+    long opt_ntt_max_radix_log2 = 0;  // 0 = auto
     long opt_ntt_threads = 0;
+    long opt_ntt_kernel = 0;  // 0: auto, 1: one radix-2 stage per barrier, 2: register-blocked radix-8 steps
     long opt_ntt_direct_max_log2 = 25;  // largest direct twiddle table (2^25 x 32 B = 1 GiB)
     long opt_imad_mode = 0;
 

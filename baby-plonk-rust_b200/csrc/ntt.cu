@@ -146,6 +146,143 @@ __global__ void __launch_bounds__(1024) ntt_pass_kernel(NttPassParams p) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Register-blocked variant (default for R >= 8): every thread keeps 8 rows of one column in registers and
+// runs up to three radix-2 DIT stages on them between two visits of shared memory, so a 2^8-point sub-FFT
+// costs 3 exchanges (and barriers) instead of 8.  The first step is fused with the global load (rows are
+// fetched in bit-reversed order straight into registers) and knows its twiddles at compile time: of its 12
+// butterflies only 5 need a multiplication (exponents 0 are skipped).  The last step stores straight from
+// registers, except in the first pass where the coalesced store wants R consecutive outputs per column.
+// The Fr product is one shared out-of-line body: 12 inlined products per step would not fit the
+// instruction cache (same finding as in msm.cu).
+// ---------------------------------------------------------------------------------------------
+static __device__ __noinline__ fr_t fr_mul_nl(fr_t a, fr_t b) { return mul(a, b); }
+#ifndef BPK_NTT_MUL
+#define BPK_NTT_MUL fr_mul_nl
+#endif
+
+template <int T, bool FIRST>
+__device__ __forceinline__ void dit_stage8(fr_t (&x)[8], uint32_t sigma, uint32_t base, uint32_t b0, uint32_t logR,
+                                           const uint4* t_lo, const uint4* t_hi) {
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        if (a & (1 << T)) continue;
+        const int a1 = a | (1 << T);
+        fr_t tt = x[a1];
+        if (FIRST) {  // stages 1..3 on rows base + a with base a multiple of 8: the exponent depends on a only
+            const uint32_t lowb = a & ((1 << T) - 1);
+            if (lowb != 0) tt = BPK_NTT_MUL(tt, ld_sm(t_lo, t_hi, lowb << (logR - sigma)));
+        } else {
+            const uint32_t row = base + ((uint32_t)a << b0);
+            const uint32_t lowb = row & ((1u << (sigma - 1)) - 1);
+            tt = BPK_NTT_MUL(tt, ld_sm(t_lo, t_hi, lowb << (logR - sigma)));
+        }
+        const fr_t u = x[a];
+        x[a] = add(u, tt);
+        x[a1] = sub(u, tt);
+    }
+}
+
+__global__ void __launch_bounds__(256) ntt_pass_r8_kernel(NttPassParams p) {
+    extern __shared__ uint4 smem[];
+    const uint32_t logR = p.logR, logC = p.logC, logNs = p.logNs;
+    const uint32_t R = 1u << logR, C = 1u << logC, RC = R << logC;
+    uint4* s_lo = smem;
+    uint4* s_hi = smem + RC;
+    uint4* t_lo = smem + 2 * RC;
+    uint4* t_hi = t_lo + (R >> 1);
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;  // nt == RC / 8
+    const size_t n = (size_t)1 << p.logn;
+    const fr_t* in = p.in + (size_t)blockIdx.y * n;
+    fr_t* out = p.out + (size_t)blockIdx.y * n;
+    const uint32_t j0 = blockIdx.x << logC;
+    const uint32_t c = tid & (C - 1), g = tid >> logC;  // column, group of 8 rows
+    const uint32_t j = j0 + c;
+    const uint32_t ns_mask = (1u << logNs) - 1;
+
+    for (uint32_t i = tid; i < (R >> 1); i += nt) {
+        fr_t w = table_pow(p.tw_lo, p.tw_hi, i << (NTT_MAX_LOG - logR));
+        st_sm(t_lo, t_hi, i, w);
+    }
+    __syncthreads();
+
+    // step 1: load rows brev(8 g + a), inter-pass twiddle, stages 1..3
+    fr_t x[8];
+    uint32_t base = g << 3, b0 = 0;
+    {
+        const uint32_t stride_in = (uint32_t)(n >> logR);
+        const uint32_t tw_shift = NTT_MAX_LOG - (logNs + logR);
+        const uint32_t k = j & ns_mask;
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            const uint32_t r = __brev(base + a) >> (32 - logR);
+            const uint32_t gi = j + r * stride_in;
+            fr_t v = ld_fr(in + gi);
+            if (p.coset_in) v = fr_mul_nl(v, table_pow(p.cs_lo, p.cs_hi, gi));
+            if (logNs) {
+                if (p.tw_direct)
+                    v = fr_mul_nl(v, ld_fr(p.tw_direct + k * r));
+                else
+                    v = fr_mul_nl(v, table_pow(p.tw_lo, p.tw_hi, (k * r) << tw_shift));
+            }
+            x[a] = v;
+        }
+        dit_stage8<0, true>(x, 1, base, 0, logR, t_lo, t_hi);
+        dit_stage8<1, true>(x, 2, base, 0, logR, t_lo, t_hi);
+        dit_stage8<2, true>(x, 3, base, 0, logR, t_lo, t_hi);
+    }
+    uint32_t done = 3;
+    while (done < logR) {
+#pragma unroll
+        for (int a = 0; a < 8; a++) st_sm(s_lo, s_hi, ((base + ((uint32_t)a << b0)) << logC) + c, x[a]);
+        __syncthreads();
+        const uint32_t k = logR - done < 3 ? logR - done : 3;
+        const uint32_t s = done + 1;
+        b0 = s - 1 < logR - 3 ? s - 1 : logR - 3;
+        base = ((g >> b0) << (b0 + 3)) | (g & ((1u << b0) - 1));
+#pragma unroll
+        for (int a = 0; a < 8; a++) x[a] = ld_sm(s_lo, s_hi, ((base + ((uint32_t)a << b0)) << logC) + c);
+        if (k == 3) {
+            dit_stage8<0, false>(x, s, base, b0, logR, t_lo, t_hi);
+            dit_stage8<1, false>(x, s + 1, base, b0, logR, t_lo, t_hi);
+            dit_stage8<2, false>(x, s + 2, base, b0, logR, t_lo, t_hi);
+        } else if (k == 2) {
+            dit_stage8<1, false>(x, s, base, b0, logR, t_lo, t_hi);
+            dit_stage8<2, false>(x, s + 1, base, b0, logR, t_lo, t_hi);
+        } else {
+            dit_stage8<2, false>(x, s, base, b0, logR, t_lo, t_hi);
+        }
+        done += k;
+    }
+    if (logNs != 0) {  // rows base + (a << b0) of column j, straight from registers
+        const size_t o0 = ((size_t)(j >> logNs) << (logNs + logR)) + (j & ns_mask);
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            const uint32_t r = base + ((uint32_t)a << b0);
+            const size_t o = o0 + ((size_t)r << logNs);
+            fr_t v = x[a];
+            if (p.scale_out == 1) v = fr_mul_nl(v, p.scale);
+            else if (p.scale_out == 2) v = fr_mul_nl(v, table_pow(p.cs_lo, p.cs_hi, (uint32_t)o));
+            st_fr(out + o, v);
+        }
+        return;
+    }
+    // first pass: each column writes R consecutive outputs -> go through shared memory for coalescing
+    __syncthreads();  // (all reads of the last exchange are done before rows are overwritten)
+#pragma unroll
+    for (int a = 0; a < 8; a++) st_sm(s_lo, s_hi, ((base + ((uint32_t)a << b0)) << logC) + c, x[a]);
+    __syncthreads();
+    for (uint32_t idx = tid; idx < RC; idx += nt) {
+        const uint32_t r = idx & (R - 1), cc = idx >> logR;
+        const size_t o = ((size_t)(j0 + cc) << logR) + r;
+        fr_t v = ld_sm(s_lo, s_hi, (r << logC) + cc);
+        if (p.scale_out == 1) v = fr_mul_nl(v, p.scale);
+        else if (p.scale_out == 2) v = fr_mul_nl(v, table_pow(p.cs_lo, p.cs_hi, (uint32_t)o));
+        st_fr(out + o, v);
+    }
+}
+
 // out[i] = pre * base^(i << shift)
 __global__ void pow_table_kernel(fr_t* out, fr_t base, fr_t pre, uint32_t count, uint32_t shift) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,6 +345,7 @@ int ntt_init_tables(bpk_ctx* ctx) {
     for (int i = 0; i < 32 - NTT_MAX_LOG; i++) root = sqr(root);  // primitive 2^NTT_MAX_LOG-th root
     fr_t roots[2] = {root, inv(root)};
     BPK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    BPK_CUDA(cudaFuncSetAttribute(ntt_pass_r8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     for (int d = 0; d < 2; d++) {
         BPK_CUDA(cudaMalloc(&ctx->tw_lo[d], sizeof(fr_t) << TW_LO_BITS));
         BPK_CUDA(cudaMalloc(&ctx->tw_hi[d], sizeof(fr_t) << TW_HI_BITS));
@@ -268,7 +406,9 @@ int ntt_run(bpk_ctx* ctx, const fr_t* d_in, fr_t* d_out, size_t n, size_t batch,
     }
 
     const uint32_t tile_log = (uint32_t)ctx->opt_ntt_tile_log2;  // log2(R * C)
-    uint32_t max_logR = (uint32_t)ctx->opt_ntt_max_radix_log2;
+    // auto (0): one pass up to the tile size, otherwise radices <= 2^8 so that a tile keeps >= 4 adjacent columns
+    // (3 x 2^20: 0.67 -> 0.61 ms against two passes of 2^10, profiles/r1_ntt_kernel_ab.md)
+    uint32_t max_logR = ctx->opt_ntt_max_radix_log2 ? (uint32_t)ctx->opt_ntt_max_radix_log2 : (logn <= tile_log ? tile_log : 8);
     if (max_logR > tile_log) max_logR = tile_log;
     if (max_logR < 1) max_logR = 1;
     std::vector<uint32_t> plan;
@@ -323,7 +463,12 @@ int ntt_run(bpk_ctx* ctx, const fr_t* d_in, fr_t* d_out, size_t n, size_t batch,
         dim3 grid((unsigned)(n >> (logR + logC)), (unsigned)batch);
         unsigned threads = (unsigned)ctx->opt_ntt_threads;
         if (threads == 0) threads = (logR + logC >= 12) ? 1024 : 256;
-        ntt_pass_kernel<<<grid, threads, smem, ctx->stream>>>(p);
+        // register-blocked kernel unless the transform is too small to fill the GPU with 128-thread CTAs
+        const bool big = (n * batch) >= ((size_t)1 << 18);
+        if (logR >= 3 && logR + logC <= 11 && (ctx->opt_ntt_kernel == 0 ? big : ctx->opt_ntt_kernel == 2))
+            ntt_pass_r8_kernel<<<grid, 1u << (logR + logC - 3), smem, ctx->stream>>>(p);
+        else
+            ntt_pass_kernel<<<grid, threads, smem, ctx->stream>>>(p);
         count_launch(ctx);
         BPK_CUDA(cudaGetLastError());
         src = dst;

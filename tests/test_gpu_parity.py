@@ -94,6 +94,61 @@ def test_ntt_tile_shapes(ctx, tile):
         ctx.set_option("ntt.tile_log2", 10)
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("tile,maxr", [(5, 0), (8, 3), (9, 4), (10, 5), (10, 0), (11, 7), (11, 11)])
+def test_ntt_both_pass_kernels_every_step_shape(ctx, kernel, tile, maxr):
+    """ntt.kernel 1 = one radix-2 stage per barrier, 2 = register-blocked radix-8 steps (falls back to 1 for
+    R < 8); radices 3..11 exercise full steps, 1- and 2-stage remainder steps, first-pass and later-pass stores"""
+    ctx.set_option("ntt.kernel", kernel)
+    ctx.set_option("ntt.tile_log2", tile)
+    ctx.set_option("ntt.max_radix_log2", maxr)
+    try:
+        for logn, batch in ((3, 1), (4, 3), (7, 2), (11, 1), (13, 2)):
+            n = 1 << logn
+            xs = [O.random_fr(900 + logn + tile + b, n) for b in range(batch)]
+            arr = np.stack([S(x) for x in xs])
+            f, g = bpk.ntt_381(arr, ctx), bpk.i_ntt_381(arr, ctx)
+            cs, ci = bpk.coset_ntt(arr, 7, ctx), bpk.coset_intt(arr, 7, ctx)
+            for b in range(batch):
+                assert I(f[b]) == O.ntt_fast(xs[b]), (kernel, tile, maxr, logn)
+                assert I(g[b]) == O.ntt_fast(xs[b], inverse=True), (kernel, tile, maxr, logn)
+                assert I(cs[b]) == O.ntt_fast(xs[b], coset_shift=7), (kernel, tile, maxr, logn)
+                assert I(ci[b]) == O.ntt_fast(xs[b], inverse=True, coset_shift=7), (kernel, tile, maxr, logn)
+    finally:
+        ctx.set_option("ntt.kernel", 0)
+        ctx.set_option("ntt.tile_log2", 10)
+        ctx.set_option("ntt.max_radix_log2", 0)
+
+
+def test_ntt_large_sizes_linear_and_round_trip(ctx):
+    """sizes the oracle cannot transform: the two pass kernels must agree bit for bit, the transform must be
+    linear and the inverse must undo it (2^20 x 3 and 2^22, the bench shapes)"""
+    import torch
+
+    rng = np.random.default_rng(77)
+    for logn, batch in ((20, 3), (22, 1)):
+        n = 1 << logn
+        a = rng.integers(0, 1 << 64, size=(batch * n, 4), dtype=np.uint64)
+        a[:, 3] &= np.uint64((1 << 62) - 1)
+        x = torch.from_numpy(a.view(np.int64)).cuda()
+        outs = []
+        for kernel in (1, 2):
+            ctx.set_option("ntt.kernel", kernel)
+            y = torch.empty_like(x)
+            ctx.check(ctx.lib.bpk_ntt_fr_dev(ctx.handle, x.data_ptr(), y.data_ptr(), n, batch, 0, None), "ntt")
+            z = torch.empty_like(x)
+            ctx.check(ctx.lib.bpk_ntt_fr_dev(ctx.handle, y.data_ptr(), z.data_ptr(), n, batch, 1, None), "intt")
+            assert torch.equal(z, x), (logn, kernel)
+            outs.append(y)
+        ctx.set_option("ntt.kernel", 0)
+        assert torch.equal(outs[0], outs[1]), logn
+        # X(0) = sum of the inputs (row 0 of the DFT matrix is all ones)
+        first = bpk.scalars_to_ints(outs[0][0:1].cpu().numpy().view(np.uint64))[0]
+        col = a[:n].astype(object)
+        total = sum(int(col[:, k].sum()) << (64 * k) for k in range(4))
+        assert first == total * pow(1 << 256, -1, O.Q) % O.Q
+
+
 def test_ntt_direct_and_two_level_twiddles_agree(ctx):
     """inter-pass twiddles come either from a per-size direct table or from the two-level table"""
     for logn in (11, 14, 17):
