@@ -133,3 +133,23 @@ def test_curve_ops(exe):
     for l, g, e in zip(lines, got, exp):
         x, y = (int(t, 16) * O.FP_RINV % O.P for t in g.split())
         assert ((x, y) if (x, y) != (0, 0) else None) == e, l
+
+
+def test_dedicated_fp_squaring(exe):
+    """sqr_cc (off-diagonal products doubled + reduction-only rows) against big-int squaring: random values and
+    carry-heavy limb patterns (all-ones limbs, single bits, p - small)"""
+    rng = random.Random(7)
+    mod, R = O.P, O.FP_R
+    Rinv = pow(R, -1, mod)
+    vals = [rng.randrange(mod) for _ in range(1500)]
+    vals += [mod - k for k in range(1, 40)] + [k for k in range(40)]
+    vals += [(1 << b) % mod for b in range(0, 381, 7)] + [((1 << b) - 1) % mod for b in range(1, 381, 5)]
+    for _ in range(300):   # limbs drawn from {0, 1, 0xffffffff, 0x80000000, random}
+        v = 0
+        for k in range(12):
+            limb = rng.choice([0, 1, 0xFFFFFFFF, 0x80000000, 0xFFFFFFFE, rng.getrandbits(32)])
+            v |= limb << (32 * k)
+        vals.append(v % mod)
+    got = run(exe, [f"fp sqr {hx(a)}" for a in vals])
+    for a, g in zip(vals, got):
+        assert int(g, 16) == a * a * Rinv % mod, hx(a)
