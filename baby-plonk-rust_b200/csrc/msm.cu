@@ -506,31 +506,49 @@ __global__ void msm_finalize_kernel(const xyzz_t* A, const xyzz_t* V, uint32_t W
     write_projective(out, acc, normalise != 0);
 }
 
-// plane form: thread w folds its window's L plane sums (Horner in 2), thread 0 then folds the windows
+// plane form: the L plane sums of a window are folded by Horner in 2.  With few windows (precomputed levels:
+// one) the planes are split into groups of GROUP consecutive planes, one thread per group, and the group values
+// are folded in 2^GROUP -- the same doublings, but a third of the additions on the serial path.
+constexpr uint32_t FIN_GROUP = 4;
 __global__ void __launch_bounds__(128) msm_finalize_planes_kernel(const xyzz_t* __restrict__ plane_sums,
                                                                    const xyzz_t* __restrict__ totals, uint32_t W,
-                                                                   uint32_t L, uint32_t c, int normalise,
-                                                                   uint64_t* out) {
-    __shared__ xyzz_t win[128];
-    const uint32_t w = threadIdx.x;
-    if (w < W) {
+                                                                   uint32_t L, uint32_t c, uint32_t groups,
+                                                                   int normalise, uint64_t* out) {
+    __shared__ xyzz_t part[128];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = groups > 1 ? FIN_GROUP : L;  // planes per thread
+    if (t < W * groups) {
+        const uint32_t w = t / groups, g = t % groups;
+        const int lo = (int)(g * per);
+        int hi = lo + (int)per;
+        if (hi > (int)L) hi = (int)L;
         xyzz_t acc = xyzz_t::inf();
-        for (int p = (int)L - 1; p >= 0; p--) {
+        for (int p = hi - 1; p >= lo; p--) {
             xyzz_dbl(acc);
-            xyzz_t t = ld_xyzz(plane_sums + (size_t)w * L + p);
-            xyzz_add(acc, t);
+            xyzz_t v = ld_xyzz(plane_sums + (size_t)w * L + p);
+            xyzz_add(acc, v);
         }
-        xyzz_t t = ld_xyzz(totals + w);
-        xyzz_add(acc, t);
-        win[w] = acc;
+        part[t] = acc;
     }
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    xyzz_t acc = win[W - 1];
+    if (t < W) {  // fold the groups of window t, add the plain bucket sum
+        xyzz_t acc = part[t * groups + groups - 1];
+        for (int g = (int)groups - 2; g >= 0; g--) {
+            for (uint32_t i = 0; i < FIN_GROUP; i++) xyzz_dbl(acc);
+            xyzz_t v = part[t * groups + g];
+            xyzz_add(acc, v);
+        }
+        xyzz_t v = ld_xyzz(totals + t);
+        xyzz_add(acc, v);
+        part[t * groups] = acc;  // only this thread reads or writes the slots of window t in this phase
+    }
+    __syncthreads();
+    if (t != 0) return;
+    xyzz_t acc = part[(W - 1) * groups];
     for (int k = (int)W - 2; k >= 0; k--) {
         for (uint32_t i = 0; i < c; i++) xyzz_dbl(acc);
-        xyzz_t t = win[k];
-        xyzz_add(acc, t);
+        xyzz_t v = part[(size_t)k * groups];
+        xyzz_add(acc, v);
     }
     write_projective(out, acc, normalise != 0);
 }
@@ -727,7 +745,10 @@ int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n,
         }
         {
             StageTimer t(ctx, "msm.finalize");
-            msm_finalize_planes_kernel<<<1, 128, 0, ctx->stream>>>(plane_sums, totals, WB, L, c, normalise ? 1 : 0, d_out);
+            uint32_t groups = (L + FIN_GROUP - 1) / FIN_GROUP;
+            if (groups == 0 || WB * groups > 128) groups = 1;
+            msm_finalize_planes_kernel<<<1, 128, 0, ctx->stream>>>(plane_sums, totals, WB, L, c, groups,
+                                                                   normalise ? 1 : 0, d_out);
             count_launch(ctx);
             BPK_CUDA(cudaGetLastError());
             t.end();

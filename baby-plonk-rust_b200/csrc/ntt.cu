@@ -161,13 +161,6 @@ static __device__ __noinline__ fr_t fr_mul_nl(fr_t a, fr_t b) { return mul(a, b)
 #ifndef BPK_NTT_MUL
 #define BPK_NTT_MUL fr_mul_nl
 #endif
-// table_pow with the shared product body (the unrolled load / store loops would otherwise inline 24 products)
-__device__ __forceinline__ fr_t table_pow_nl(const fr_t* lo, const fr_t* hi, uint32_t E) {
-    fr_t a = ld_fr(lo + (E & ((1u << TW_LO_BITS) - 1)));
-    uint32_t h = E >> TW_LO_BITS;
-    if (h == 0) return a;
-    return fr_mul_nl(a, ld_fr(hi + h));
-}
 
 template <int T, bool FIRST>
 __device__ __forceinline__ void dit_stage8(fr_t (&x)[8], uint32_t sigma, uint32_t base, uint32_t b0, uint32_t logR,
@@ -209,7 +202,7 @@ __global__ void __launch_bounds__(256) ntt_pass_r8_kernel(NttPassParams p) {
     const uint32_t ns_mask = (1u << logNs) - 1;
 
     for (uint32_t i = tid; i < (R >> 1); i += nt) {
-        fr_t w = table_pow_nl(p.tw_lo, p.tw_hi, i << (NTT_MAX_LOG - logR));
+        fr_t w = table_pow(p.tw_lo, p.tw_hi, i << (NTT_MAX_LOG - logR));
         st_sm(t_lo, t_hi, i, w);
     }
     __syncthreads();
@@ -226,12 +219,12 @@ __global__ void __launch_bounds__(256) ntt_pass_r8_kernel(NttPassParams p) {
             const uint32_t r = __brev(base + a) >> (32 - logR);
             const uint32_t gi = j + r * stride_in;
             fr_t v = ld_fr(in + gi);
-            if (p.coset_in) v = fr_mul_nl(v, table_pow_nl(p.cs_lo, p.cs_hi, gi));
+            if (p.coset_in) v = fr_mul_nl(v, table_pow(p.cs_lo, p.cs_hi, gi));
             if (logNs) {
                 if (p.tw_direct)
                     v = fr_mul_nl(v, ld_fr(p.tw_direct + k * r));
                 else
-                    v = fr_mul_nl(v, table_pow_nl(p.tw_lo, p.tw_hi, (k * r) << tw_shift));
+                    v = fr_mul_nl(v, table_pow(p.tw_lo, p.tw_hi, (k * r) << tw_shift));
             }
             x[a] = v;
         }
@@ -270,7 +263,7 @@ __global__ void __launch_bounds__(256) ntt_pass_r8_kernel(NttPassParams p) {
             const size_t o = o0 + ((size_t)r << logNs);
             fr_t v = x[a];
             if (p.scale_out == 1) v = fr_mul_nl(v, p.scale);
-            else if (p.scale_out == 2) v = fr_mul_nl(v, table_pow_nl(p.cs_lo, p.cs_hi, (uint32_t)o));
+            else if (p.scale_out == 2) v = fr_mul_nl(v, table_pow(p.cs_lo, p.cs_hi, (uint32_t)o));
             st_fr(out + o, v);
         }
         return;
@@ -285,7 +278,7 @@ __global__ void __launch_bounds__(256) ntt_pass_r8_kernel(NttPassParams p) {
         const size_t o = ((size_t)(j0 + cc) << logR) + r;
         fr_t v = ld_sm(s_lo, s_hi, (r << logC) + cc);
         if (p.scale_out == 1) v = fr_mul_nl(v, p.scale);
-        else if (p.scale_out == 2) v = fr_mul_nl(v, table_pow_nl(p.cs_lo, p.cs_hi, (uint32_t)o));
+        else if (p.scale_out == 2) v = fr_mul_nl(v, table_pow(p.cs_lo, p.cs_hi, (uint32_t)o));
         st_fr(out + o, v);
     }
 }
