@@ -367,102 +367,32 @@ __global__ void __launch_bounds__(128) msm_reduce_level_kernel(const xyzz_t* __r
 // ------------------------------------------------------------------------------------------
 // K4 (default): bucket reduction by bit planes.  With B_k the bucket of digit k + 1 (k < half = 2^L),
 //     sum_k (k + 1) B_k = sum_k B_k + sum_{p < L} 2^p T_p,      T_p = sum_{k : bit p of k set} B_k.
-// A pairwise tree gives level p = sums of 2^p consecutive buckets; T_p is the sum of the ODD entries of
-// level p and the last level is sum_k B_k.  Every addition is unweighted (no doublings inside the tree,
-// no running-sum chains): the wide levels run at arithmetic throughput, the narrow ones cost one addition
-// of latency each.  2^p is applied once, in the final Horner pass over the L plane sums.
+// One pairwise tree carries the plane sums along: a level-k node covers 2^k consecutive buckets and holds
+// k + 1 points [S, T_0 .. T_{k-1}] restricted to its range.  Merging the children (c0, c1) of a node:
+//     S' = S(c0) + S(c1),   T_p' = T_p(c0) + T_p(c1) for p < k - 1,   T_{k-1}' = S(c1)
+// (the upper child is exactly the set of buckets whose bit k - 1 is set).  One thread per (node, slot): every
+// level is one launch of independent additions -- 2 unweighted additions per bucket in total, no doublings, no
+// running-sum chains; the wide levels run at arithmetic throughput, each narrow level costs one addition of
+// latency.  2^p is applied once, in the final Horner pass over the root's L plane sums.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) msm_pair_level_kernel(const xyzz_t* __restrict__ in, xyzz_t* __restrict__ out,
-                                                              size_t count_out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count_out) return;
-    xyzz_t a = ld_xyzz(in + 2 * i);
-    xyzz_t b = ld_xyzz(in + 2 * i + 1);
+__global__ void __launch_bounds__(128) msm_plane_tree_level_kernel(const xyzz_t* __restrict__ in,
+                                                                    xyzz_t* __restrict__ out, uint32_t k,
+                                                                    size_t nodes_out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t slots = k + 1;
+    if (t >= nodes_out * slots) return;
+    const size_t node = t / slots;
+    const uint32_t s = (uint32_t)(t - node * slots);
+    const xyzz_t* c0 = in + 2 * node * k;  // children hold k points each
+    const xyzz_t* c1 = c0 + k;
+    if (s == k) {
+        st_xyzz(out + t, ld_xyzz(c1));
+        return;
+    }
+    xyzz_t a = ld_xyzz(c0 + s);
+    xyzz_t b = ld_xyzz(c1 + s);
     xyzz_add(a, b);
-    st_xyzz(out + i, a);
-}
-
-// sum over the 128 threads of a block, result valid in thread 0
-__device__ __forceinline__ xyzz_t block_sum_128(xyzz_t acc, xyzz_t* sm /* [4] */) {
-    for (int off = 16; off >= 1; off >>= 1) {
-        xyzz_t q;
-        q.X = shfl_down_fp(acc.X, off);
-        q.Y = shfl_down_fp(acc.Y, off);
-        q.ZZ = shfl_down_fp(acc.ZZ, off);
-        q.ZZZ = shfl_down_fp(acc.ZZZ, off);
-        xyzz_add(acc, q);
-    }
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) sm[warp] = acc;
-    __syncthreads();
-    if (threadIdx.x < 2) {  // (0 + 1), (2 + 3) on two threads, then one more addition
-        acc = sm[2 * threadIdx.x];
-        xyzz_t q = sm[2 * threadIdx.x + 1];
-        xyzz_add(acc, q);
-        sm[2 * threadIdx.x] = acc;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        xyzz_t q = sm[2];
-        xyzz_add(acc, q);
-    }
-    return acc;
-}
-
-constexpr uint32_t PLANE_CHUNK = 1024;  // entries per block of the plane sums (128 threads x 8)
-
-// level p (p >= 1) starts at lvl + level_offset(p); level 0 is the bucket array itself
-__host__ __device__ inline size_t plane_level_offset(uint32_t WB, uint32_t half, uint32_t p) {
-    // sum_{q=1}^{p-1} WB * (half >> q) = WB * (half - (half >> (p - 1)))
-    return p <= 1 ? 0 : (size_t)WB * (half - (half >> (p - 1)));
-}
-__host__ __device__ inline uint32_t plane_chunks(uint32_t half, uint32_t p) {
-    uint32_t n = half >> (p + 1);
-    return n > PLANE_CHUNK ? n / PLANE_CHUNK : 1;
-}
-
-// stage 1: one block per (window, plane, chunk): partial sum of up to PLANE_CHUNK odd entries of level p
-__global__ void __launch_bounds__(128) msm_plane_partial_kernel(const xyzz_t* __restrict__ buckets,
-                                                                 const xyzz_t* __restrict__ lvl, uint32_t half,
-                                                                 uint32_t WB, uint32_t L, uint32_t chunks_per_window,
-                                                                 uint32_t max_chunks, xyzz_t* __restrict__ partials) {
-    __shared__ xyzz_t sm[4];
-    const uint32_t w = blockIdx.x / chunks_per_window;
-    uint32_t r = blockIdx.x % chunks_per_window;
-    uint32_t p = 0;
-    for (; p < L; p++) {
-        uint32_t ch = plane_chunks(half, p);
-        if (r < ch) break;
-        r -= ch;
-    }
-    const uint32_t n_p = half >> (p + 1);                 // odd entries of this window at level p
-    const xyzz_t* src = (p == 0 ? buckets : lvl + plane_level_offset(WB, half, p)) + (size_t)w * (half >> p);
-    const uint32_t first = r * PLANE_CHUNK;
-    const uint32_t count = n_p - first < PLANE_CHUNK ? n_p - first : PLANE_CHUNK;
-    xyzz_t acc = xyzz_t::inf();
-    for (uint32_t j = threadIdx.x; j < count; j += 128) {
-        xyzz_t q = ld_xyzz(src + 2 * (size_t)(first + j) + 1);
-        xyzz_add(acc, q);
-    }
-    acc = block_sum_128(acc, sm);
-    if (threadIdx.x == 0) st_xyzz(partials + ((size_t)w * L + p) * max_chunks + r, acc);
-}
-
-// stage 2: one block per (window, plane): sum of that plane's partials
-__global__ void __launch_bounds__(128) msm_plane_total_kernel(const xyzz_t* __restrict__ partials, uint32_t half,
-                                                               uint32_t L, uint32_t max_chunks,
-                                                               xyzz_t* __restrict__ plane_sums) {
-    __shared__ xyzz_t sm[4];
-    const uint32_t p = blockIdx.x % L;
-    const uint32_t ch = plane_chunks(half, p);
-    const xyzz_t* src = partials + (size_t)blockIdx.x * max_chunks;
-    xyzz_t acc = xyzz_t::inf();
-    for (uint32_t j = threadIdx.x; j < ch; j += 128) {
-        xyzz_t q = ld_xyzz(src + j);
-        xyzz_add(acc, q);
-    }
-    acc = block_sum_128(acc, sm);
-    if (threadIdx.x == 0) st_xyzz(plane_sums + blockIdx.x, acc);
+    st_xyzz(out + t, a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -510,10 +440,13 @@ __global__ void msm_finalize_kernel(const xyzz_t* A, const xyzz_t* V, uint32_t W
 // one) the planes are split into groups of GROUP consecutive planes, one thread per group, and the group values
 // are folded in 2^GROUP -- the same doublings, but a third of the additions on the serial path.
 constexpr uint32_t FIN_GROUP = 4;
-__global__ void __launch_bounds__(128) msm_finalize_planes_kernel(const xyzz_t* __restrict__ plane_sums,
-                                                                   const xyzz_t* __restrict__ totals, uint32_t W,
+__global__ void __launch_bounds__(128) msm_finalize_planes_kernel(const xyzz_t* __restrict__ roots, uint32_t W,
                                                                    uint32_t L, uint32_t c, uint32_t groups,
                                                                    int normalise, uint64_t* out) {
+    // roots: per window L + 1 points [S, T_0 .. T_{L-1}] (the root of the plane tree)
+    const xyzz_t* plane_sums = roots + 1;
+    const xyzz_t* totals = roots;
+    const uint32_t stride = L + 1;
     __shared__ xyzz_t part[128];
     const uint32_t t = threadIdx.x;
     const uint32_t per = groups > 1 ? FIN_GROUP : L;  // planes per thread
@@ -525,7 +458,7 @@ __global__ void __launch_bounds__(128) msm_finalize_planes_kernel(const xyzz_t* 
         xyzz_t acc = xyzz_t::inf();
         for (int p = hi - 1; p >= lo; p--) {
             xyzz_dbl(acc);
-            xyzz_t v = ld_xyzz(plane_sums + (size_t)w * L + p);
+            xyzz_t v = ld_xyzz(plane_sums + (size_t)w * stride + p);
             xyzz_add(acc, v);
         }
         part[t] = acc;
@@ -538,7 +471,7 @@ __global__ void __launch_bounds__(128) msm_finalize_planes_kernel(const xyzz_t* 
             xyzz_t v = part[t * groups + g];
             xyzz_add(acc, v);
         }
-        xyzz_t v = ld_xyzz(totals + t);
+        xyzz_t v = ld_xyzz(totals + (size_t)t * stride);
         xyzz_add(acc, v);
         part[t * groups] = acc;  // only this thread reads or writes the slots of window t in this phase
     }
@@ -706,40 +639,26 @@ int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n,
         t.end();
     }
     if (ctx->opt_msm_reduce == 0) {
-        // bit-plane reduction (see K4): pairwise levels, plane sums, Horner over the planes
-        uint32_t L = c - 1;  // half == 1 << L
-        const uint32_t max_chunks = L ? plane_chunks(half, 0) : 1;
-        uint32_t chunks_per_window = 0;
-        for (uint32_t p = 0; p < L; p++) chunks_per_window += plane_chunks(half, p);
+        // bit-plane reduction (see K4): one tree whose nodes carry the plane sums, then Horner over the planes
+        const uint32_t L = c - 1;  // half == 1 << L
+        // ping-pong level buffers: level k holds WB * (half >> k) * (k + 1) points, largest at k = 1 and k = 2
+        const size_t buf_a = (size_t)WB * half;                    // odd levels  (k = 1: WB * half points)
+        const size_t buf_b = (size_t)WB * (half / 4 + 1) * 3;      // even levels (k = 2: 3/4 WB * half points)
         xyzz_t* lvl;
-        const size_t lvl_elems = (size_t)WB * half;  // levels 1..L: WB * (half - 1) entries
-        const size_t part_elems = (size_t)WB * (L ? L : 1) * max_chunks;
-        const size_t sum_elems = (size_t)WB * (L ? L : 1);
-        BPK_TRY(ws_reserve(ctx, 6, (lvl_elems + part_elems + sum_elems) * sizeof(xyzz_t), (void**)&lvl));
-        xyzz_t* partials = lvl + lvl_elems;
-        xyzz_t* plane_sums = partials + part_elems;
-        const xyzz_t* totals = buckets;
+        BPK_TRY(ws_reserve(ctx, 6, (buf_a + buf_b + 1) * sizeof(xyzz_t), (void**)&lvl));
+        const xyzz_t* roots = buckets;  // L == 0: the single bucket of each window is its own root
         {
             StageTimer t(ctx, "msm.reduce");
             const xyzz_t* in = buckets;
-            for (uint32_t p = 1; p <= L; p++) {
-                xyzz_t* out = lvl + plane_level_offset(WB, half, p);
-                size_t count = (size_t)WB * (half >> p);
-                msm_pair_level_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(in, out, count);
+            for (uint32_t k = 1; k <= L; k++) {
+                xyzz_t* out = (k & 1) ? lvl : lvl + buf_a;
+                const size_t nodes = (size_t)WB * (half >> k);
+                const size_t threads = nodes * (k + 1);
+                msm_plane_tree_level_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(in, out, k, nodes);
                 count_launch(ctx);
                 in = out;
             }
-            totals = in;
-            if (L) {
-                xyzz_t* stage1_out = max_chunks == 1 ? plane_sums : partials;
-                msm_plane_partial_kernel<<<WB * chunks_per_window, 128, 0, ctx->stream>>>(
-                    buckets, lvl, half, WB, L, chunks_per_window, max_chunks, stage1_out);
-                count_launch(ctx);
-                if (max_chunks > 1) {
-                    msm_plane_total_kernel<<<WB * L, 128, 0, ctx->stream>>>(partials, half, L, max_chunks, plane_sums);
-                    count_launch(ctx);
-                }
-            }
+            roots = in;
             BPK_CUDA(cudaGetLastError());
             t.end();
         }
@@ -747,8 +666,7 @@ int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n,
             StageTimer t(ctx, "msm.finalize");
             uint32_t groups = (L + FIN_GROUP - 1) / FIN_GROUP;
             if (groups == 0 || WB * groups > 128) groups = 1;
-            msm_finalize_planes_kernel<<<1, 128, 0, ctx->stream>>>(plane_sums, totals, WB, L, c, groups,
-                                                                   normalise ? 1 : 0, d_out);
+            msm_finalize_planes_kernel<<<1, 128, 0, ctx->stream>>>(roots, WB, L, c, groups, normalise ? 1 : 0, d_out);
             count_launch(ctx);
             BPK_CUDA(cudaGetLastError());
             t.end();
