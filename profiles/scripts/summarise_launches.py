@@ -17,7 +17,8 @@ for r in rows[1:]:
 if "--seq" in sys.argv:
     key = sys.argv[sys.argv.index("--seq") + 1]
     idx = [i for i, (n, _) in enumerate(launches) if key in n]
-    a, b = idx[-2], idx[-1]
+    k = int(sys.argv[sys.argv.index("--seq") + 2]) if len(sys.argv) > sys.argv.index("--seq") + 2 else len(idx) - 2
+    a, b = idx[k], idx[k + 1]
     for n, us in launches[a:b]:
         print("%-60s %10.1f us" % (n[-60:], us))
     print("total %.1f us in %d launches" % (sum(us for _, us in launches[a:b]), b - a))
