@@ -881,8 +881,10 @@ BPK_HD Fe<P> inv(const Fe<P>& a) {
 template <class P>
 BPK_HD Fe<P> pow_u64(const Fe<P>& a, uint64_t e) {
     Fe<P> r = Fe<P>::one();
+    int top = 63;
+    while (top > 0 && !((e >> top) & 1ull)) top--;  // skip the leading zero bits (squarings of one)
 #pragma unroll 1
-    for (int b = 63; b >= 0; b--) {
+    for (int b = top; b >= 0; b--) {
         r = sqr(r);
         if ((e >> b) & 1ull) r = mul(r, a);
     }

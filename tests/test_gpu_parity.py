@@ -641,3 +641,48 @@ def test_msm_batch_on_streams_matches_single_calls(ctx, lanes):
     finally:
         ctx.set_option("msm.lanes", 3)
         setup.free()
+
+
+def test_msm_and_ntt_at_the_largest_practical_sizes(ctx):
+    """2^26 pairs (4x the bench size; 6.4 GiB SRS, 8 x 10^8 sorted pairs) and a ragged 2^25 + 12345, against the
+    closed form [sum s_i tau^i] G with scalars of period 2^16; NTT 2^26 forward + inverse round trip.
+    Guards 32-bit index arithmetic; skipped when the GPU has less than 100 GiB free."""
+    import torch
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100 << 30:
+        pytest.skip("needs 100 GiB of free HBM")
+    period = 1 << 16
+    block = O.random_fr(2626, period)
+    d_block = torch.from_numpy(S(block).view(np.int64)).cuda()
+    base = 0
+    for j in reversed(range(period)):
+        base = (base * 101 + block[j]) % O.Q
+    step = pow(101, period, O.Q)
+    out = torch.zeros(18, dtype=torch.int64, device="cuda")
+    for n, pre in (((1 << 25) + 12345, False), (1 << 26, True)):
+        setup = bpk.Setup.generate_srs(n, 101, ctx)
+        if pre:
+            setup.precompute(0)
+        reps = (n + period - 1) // period
+        d_sc = d_block.repeat(reps, 1)[:n].contiguous()
+        ctx.check(ctx.lib.bpk_msm_g1_dev(ctx.handle, setup.handle, 0, d_sc.data_ptr(), n, 1, out.data_ptr()), "msm")
+        got = bpk.point_to_affine(out.cpu().numpy().view(np.uint64))
+        full, rem = divmod(n, period)
+        geo = (pow(step, full, O.Q) - 1) * pow(step - 1, -1, O.Q) % O.Q      # sum_k tau^(k period), k < full
+        tail = 0
+        for j in reversed(range(rem)):
+            tail = (tail * 101 + block[j]) % O.Q
+        want = (base * geo + tail * pow(step, full, O.Q)) % O.Q
+        assert got == O.g1_mul(O.G1_GEN, want), n
+        del d_sc
+        setup.free()
+    n = 1 << 26
+    x = d_block.repeat(n // period, 1).contiguous()
+    y = torch.empty_like(x)
+    ctx.check(ctx.lib.bpk_ntt_fr_dev(ctx.handle, x.data_ptr(), y.data_ptr(), n, 1, 0, None), "ntt")
+    # a sequence of period 2^16 has a spectrum supported on multiples of 2^10
+    probe = y.view(n // 1024, 1024, 4)[:, 1:, :]
+    assert int(torch.count_nonzero(probe)) == 0
+    ctx.check(ctx.lib.bpk_ntt_fr_dev(ctx.handle, y.data_ptr(), y.data_ptr(), n, 1, 1, None), "intt")
+    assert torch.equal(x, y)
