@@ -181,7 +181,14 @@ uint64_t bpk_launch_count(bpk_ctx* ctx);
 int bpk_msm_last_plan(bpk_ctx* ctx, unsigned out[4]);
 /* Register-only IMAD.WIDE throughput probe: returns 32x32+64 multiply-adds per second. */
 int bpk_imad_peak(bpk_ctx* ctx, double* wide_imad_per_s_out, double* seconds_out);
-/* Tunables: "msm.window" (0 = auto), "msm.chunk", "ntt.tile_log2". */
+/* Tunables (A/B measurements and tests; the defaults are the measured optima):
+ *   "msm.window" window bits of the non-precomputed MSM (0 = auto), "msm.chunk" pairs per accumulate thread (0 = auto),
+ *   "msm.reduce" 0 = bit-plane bucket reduction, 1 = fan-in running-sum tree ("msm.fanin" 2..32),
+ *   "msm.lanes" 1..3 concurrent MSMs of bpk_msm_g1_dev_batch,
+ *   "ntt.tile_log2" log2 of the R x C tile per CTA (default 10), "ntt.max_radix_log2" (0 = auto), "ntt.threads",
+ *   "ntt.kernel" 0 = auto, 1 = one radix-2 stage per barrier, 2 = register-blocked radix-8 steps,
+ *   "ntt.direct_max_log2" largest per-size inter-pass twiddle table, "imad.mode" probe form of bpk_imad_peak.
+ * Unknown keys and out-of-range values return BPK_ERR_INVALID_ARG. */
 int bpk_set_option(bpk_ctx* ctx, const char* key, long value);
 
 #ifdef __cplusplus
