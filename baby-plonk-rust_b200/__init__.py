@@ -81,6 +81,8 @@ _SIGNATURES = {
                                          ctypes.c_size_t, ctypes.c_void_p]),
     "bpk_msm_g1_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_void_p,
                                       ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "bpk_msm_g1_from_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_void_p,
+                                            ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
     "bpk_msm_g1_dev_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_void_p,
                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "bpk_g1_sum": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),

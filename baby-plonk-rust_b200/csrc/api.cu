@@ -222,6 +222,8 @@ extern "C" void bpk_destroy(bpk_ctx* ctx) {
         if (ctx->lane_done[l]) cudaEventDestroy(ctx->lane_done[l]);
     }
     if (ctx->lane_fork) cudaEventDestroy(ctx->lane_fork);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     delete ctx;
 }
 
@@ -248,6 +250,7 @@ extern "C" int bpk_set_option(bpk_ctx* ctx, const char* key, long value) {
     else if (k == "msm.fanin") ctx->opt_msm_fanin = value;
     else if (k == "msm.reduce") ctx->opt_msm_reduce = value;
     else if (k == "msm.lanes") ctx->opt_msm_lanes = value;
+    else if (k == "msm.host_slices") ctx->opt_msm_host_slices = value;
     else if (k == "ntt.tile_log2") {
         if (value < 1 || value > 12) return BPK_ERR_INVALID_ARG;
         ctx->opt_ntt_tile_log2 = value;
@@ -428,8 +431,7 @@ static int msm_host_scalars(bpk_ctx* ctx, const SrsEntry& srs, const uint64_t* s
     BPK_TRY(ws_reserve(ctx, 9, (n ? n : 1) * sizeof(fr_t), (void**)&d_scalars));
     uint64_t* d_out;
     BPK_TRY(ws_reserve(ctx, 10, 18 * sizeof(uint64_t), (void**)&d_out));
-    if (n) BPK_CUDA(cudaMemcpyAsync(d_scalars, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
-    BPK_TRY(msm_run(ctx, d_points, d_scalars, n, rshift, true, d_out));
+    BPK_TRY(msm_run_from_host(ctx, d_points, scalars, d_scalars, n, rshift, true, d_out));
     BPK_CUDA(cudaMemcpyAsync(out_xyz, d_out, 18 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     BPK_CUDA(cudaStreamSynchronize(ctx->stream));
     return BPK_OK;
@@ -471,6 +473,19 @@ extern "C" int bpk_msm_g1_dev(bpk_ctx* ctx, uint64_t handle, size_t first, const
     BPK_CUDA(cudaSetDevice(ctx->device));
     return msm_run(ctx, msm_points_of(it->second, first), (const fr_t*)d_scalars_mont, n, 0, normalise != 0,
                    (uint64_t*)d_out_xyz);
+}
+
+extern "C" int bpk_msm_g1_from_host(bpk_ctx* ctx, uint64_t handle, size_t first, const uint64_t* scalars_mont,
+                                    size_t n, int normalise, void* d_out_xyz) {
+    if (!ctx || !d_out_xyz || (n && !scalars_mont)) return BPK_ERR_INVALID_ARG;
+    auto it = ctx->srs.find(handle);
+    if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
+    if (first > it->second.n || n > it->second.n - first) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    fr_t* d_scalars;
+    BPK_TRY(ws_reserve(ctx, 9, (n ? n : 1) * sizeof(fr_t), (void**)&d_scalars));
+    return msm_run_from_host(ctx, msm_points_of(it->second, first), scalars_mont, d_scalars, n, 0, normalise != 0,
+                             (uint64_t*)d_out_xyz);
 }
 
 extern "C" int bpk_msm_g1_dev_batch(bpk_ctx* ctx, uint64_t handle, size_t count, const void* const* d_scalars_mont,

@@ -77,6 +77,8 @@ struct bpk_ctx {
     cudaStream_t lane_stream[bpk::MSM_LANES] = {};
     cudaEvent_t lane_done[bpk::MSM_LANES] = {};
     cudaEvent_t lane_fork = nullptr;
+    cudaStream_t copy_stream = nullptr;  // uploads the tail of a host-resident MSM input under the head's accumulation
+    cudaEvent_t copy_done = nullptr;
 
     std::map<uint64_t, bpk::SrsEntry> srs;
     uint64_t next_handle = 1;
@@ -89,6 +91,7 @@ struct bpk_ctx {
     long opt_msm_chunk = 0;
     long opt_msm_fanin = 8;
     long opt_msm_lanes = bpk::MSM_LANES;  // 1: bpk_msm_g1_dev_batch runs its MSMs one after the other
+    long opt_msm_host_slices = 1;  // 0: upload all scalars before the MSM starts
     long opt_msm_reduce = 0;  // 0: bit-plane reduction, 1: fan-in running-sum tree (kept for A/B runs)
     long opt_ntt_tile_log2 = 10;  // R x C elements per CTA tile (32 KiB): best of the sweep in profiles/
     long opt_ntt_max_radix_log2 = 0;  // 0 = auto
@@ -162,6 +165,8 @@ int plonk_quotient_evals(bpk_ctx* ctx, const fr_t* wv, const fr_t* cv, size_t D,
 // ---- msm.cu ----
 int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n, unsigned rshift,
             bool normalise, uint64_t* d_out_xyz /* 18 u64 on device */);
+int msm_run_from_host(bpk_ctx* ctx, const MsmPoints& pts, const uint64_t* h_scalars, fr_t* d_stage, size_t n,
+                      unsigned rshift, bool normalise, uint64_t* d_out_xyz);
 int g1_sum_run(bpk_ctx* ctx, const uint64_t* d_points_xyz, size_t n, uint64_t* d_out_xyz);
 
 // ---- srs.cu ----

@@ -524,28 +524,69 @@ static uint32_t pick_window(bpk_ctx* ctx, size_t n) {
     return best_c;
 }
 
-int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n, unsigned rshift,
-            bool normalise, uint64_t* d_out) {
-    const affine_t* d_points = pts.base;
-    const bool pre = pts.pre_c != 0;  // all windows share one bucket set (precomputed SRS levels)
+// ---- plan: window geometry shared by the phases of one MSM ----
+struct MsmPlan {
+    bool pre;        // all windows share one bucket set (precomputed SRS levels)
+    uint32_t c, W, half, WB, nb_total;
+};
+
+static int msm_make_plan(bpk_ctx* ctx, const MsmPoints& pts, size_t n, MsmPlan* plan) {
     if (n >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
-    if (n == 0) {  // empty sum: identity (0, R, 0)
-        xyzz_t* zero;
-        BPK_TRY(ws_reserve(ctx, 5, 2 * sizeof(xyzz_t), (void**)&zero));
-        BPK_CUDA(cudaMemsetAsync(zero, 0, 2 * sizeof(xyzz_t), ctx->stream));
-        msm_finalize_kernel<<<1, 1, 0, ctx->stream>>>(zero, zero + 1, 1, 1, 1, d_out);
-        count_launch(ctx);
-        BPK_CUDA(cudaGetLastError());
-        return BPK_OK;
+    plan->pre = pts.pre_c != 0;
+    plan->c = plan->pre ? pts.pre_c : pick_window(ctx, n);
+    plan->W = plan->pre ? pts.pre_W : (256 + plan->c - 1) / plan->c;
+    plan->half = 1u << (plan->c - 1);
+    plan->WB = plan->pre ? 1 : plan->W;
+    plan->nb_total = plan->WB * plan->half;
+    if ((size_t)plan->W * n >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
+    if (plan->pre && (size_t)plan->W * pts.level_stride >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
+    return BPK_OK;
+}
+
+static int msm_empty_result(bpk_ctx* ctx, uint64_t* d_out) {  // empty sum: identity (0, R, 0)
+    xyzz_t* zero;
+    BPK_TRY(ws_reserve(ctx, 5, 2 * sizeof(xyzz_t), (void**)&zero));
+    BPK_CUDA(cudaMemsetAsync(zero, 0, 2 * sizeof(xyzz_t), ctx->stream));
+    msm_finalize_kernel<<<1, 1, 0, ctx->stream>>>(zero, zero + 1, 1, 1, 1, d_out);
+    count_launch(ctx);
+    BPK_CUDA(cudaGetLastError());
+    return BPK_OK;
+}
+
+static uint32_t msm_chunk(bpk_ctx* ctx, size_t M) {  // sorted pairs per accumulate thread
+    uint32_t chunk = (uint32_t)ctx->opt_msm_chunk;
+    if (chunk == 0) {
+        size_t target = M / ((size_t)ctx->sm_count * 2048);
+        chunk = (uint32_t)(target < 16 ? 16 : (target > 256 ? 256 : target));
     }
-    const uint32_t c = pre ? pts.pre_c : pick_window(ctx, n);
-    const uint32_t W = pre ? pts.pre_W : (256 + c - 1) / c;
-    const uint32_t half = 1u << (c - 1);
-    const uint32_t WB = pre ? 1 : W;  // number of bucket sets
-    const uint32_t nb_total = WB * half;
+    return chunk;
+}
+
+// grow the per-MSM workspaces for `n` pairs up front (growing later would synchronise the stream)
+static int msm_reserve(bpk_ctx* ctx, const MsmPlan& pl, size_t n) {
+    const size_t M = (size_t)pl.W * n;
+    void* p;
+    BPK_TRY(ws_reserve(ctx, 2, 4 * M * sizeof(uint32_t), &p));
+    int end_bit = 1;
+    while (((uint64_t)1 << end_bit) <= pl.nb_total) end_bit++;
+    size_t sort_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint32_t*)p, (uint32_t*)p, (uint32_t*)p, (uint32_t*)p, (int)M, 0,
+                                    end_bit, ctx->stream);
+    BPK_TRY(ws_reserve(ctx, 3, sort_bytes, &p));
+    const uint32_t chunk = msm_chunk(ctx, M);
+    const size_t num_chunks = (M + chunk - 1) / chunk;
+    BPK_TRY(ws_reserve(ctx, 5, 2 * num_chunks * (sizeof(xyzz_t) + sizeof(uint32_t)), &p));
+    BPK_TRY(ws_reserve(ctx, 11, 2 * (num_chunks / MERGE_SERIAL_MAX + 2) * sizeof(LongRun) + 16, &p));
+    return BPK_OK;
+}
+
+// phase 1: recode, sort, accumulate, merge: `buckets` (nb_total entries) receives the bucket sums of the n pairs
+static int msm_fill_buckets(bpk_ctx* ctx, const MsmPlan& pl, const MsmPoints& pts, const fr_t* d_scalars, size_t n,
+                            unsigned rshift, xyzz_t* buckets) {
+    const affine_t* d_points = pts.base;
+    const bool pre = pl.pre;
+    const uint32_t c = pl.c, W = pl.W, half = pl.half, nb_total = pl.nb_total;
     const size_t M = (size_t)W * n;
-    if (M >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
-    if (pre && (size_t)W * pts.level_stride >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
 
     // workspace carve-up
     uint32_t *keys_in, *vals_in, *keys_out, *vals_out;
@@ -566,19 +607,13 @@ int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n,
     void* sort_tmp;
     BPK_TRY(ws_reserve(ctx, 3, sort_bytes, &sort_tmp));
 
-    uint32_t chunk = (uint32_t)ctx->opt_msm_chunk;
-    if (chunk == 0) {
-        size_t target = M / ((size_t)ctx->sm_count * 2048);
-        chunk = (uint32_t)(target < 16 ? 16 : (target > 256 ? 256 : target));
-    }
+    const uint32_t chunk = msm_chunk(ctx, M);
     const size_t num_chunks = (M + chunk - 1) / chunk;
     ctx->last_c = c;
     ctx->last_W = W;
     ctx->last_chunk = chunk;
     ctx->last_buckets = nb_total;
 
-    xyzz_t* buckets;
-    BPK_TRY(ws_reserve(ctx, 4, (size_t)nb_total * sizeof(xyzz_t), (void**)&buckets));
     uint32_t* pkeys;
     xyzz_t* pvals;
     {
@@ -638,6 +673,24 @@ int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n,
         BPK_CUDA(cudaGetLastError());
         t.end();
     }
+    return BPK_OK;
+}
+
+// buckets_a[i] += buckets_b[i]: joins the bucket sets of two slices of one MSM
+__global__ void __launch_bounds__(128) msm_add_buckets_kernel(xyzz_t* __restrict__ a, const xyzz_t* __restrict__ b,
+                                                               size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    xyzz_t y = ld_xyzz(b + i);
+    if (y.is_inf()) return;
+    xyzz_t x = ld_xyzz(a + i);
+    xyzz_add(x, y);
+    st_xyzz(a + i, x);
+}
+
+// phase 2: bucket reduction + window Horner + output
+static int msm_reduce_buckets(bpk_ctx* ctx, const MsmPlan& pl, xyzz_t* buckets, bool normalise, uint64_t* d_out) {
+    const uint32_t c = pl.c, W = pl.W, half = pl.half, WB = pl.WB;
     if (ctx->opt_msm_reduce == 0) {
         // bit-plane reduction (see K4): one tree whose nodes carry the plane sums, then Horner over the planes
         const uint32_t L = c - 1;  // half == 1 << L
@@ -721,6 +774,62 @@ int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n,
         t.end();
     }
     return BPK_OK;
+}
+
+int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n, unsigned rshift,
+            bool normalise, uint64_t* d_out) {
+    if (n >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
+    if (n == 0) return msm_empty_result(ctx, d_out);
+    MsmPlan pl;
+    BPK_TRY(msm_make_plan(ctx, pts, n, &pl));
+    xyzz_t* buckets;
+    BPK_TRY(ws_reserve(ctx, 4, (size_t)pl.nb_total * sizeof(xyzz_t), (void**)&buckets));
+    BPK_TRY(msm_fill_buckets(ctx, pl, pts, d_scalars, n, rshift, buckets));
+    return msm_reduce_buckets(ctx, pl, buckets, normalise, d_out);
+}
+
+// Scalars in HOST memory.  Large MSMs are cut into a small head slice and the rest: the head is uploaded and its
+// bucket sums are accumulated while the copy engine brings the rest over PCIe on a second stream; the two bucket
+// sets are added and reduced once.  With pinned host memory only the head's upload (1/8 of the bytes) stays
+// exposed.  d_stage: device buffer for n scalars.
+int msm_run_from_host(bpk_ctx* ctx, const MsmPoints& pts, const uint64_t* h_scalars, fr_t* d_stage, size_t n,
+                      unsigned rshift, bool normalise, uint64_t* d_out) {
+    if (n >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
+    const size_t head = n / 8;
+    if (n < ((size_t)1 << 22) || ctx->opt_msm_host_slices == 0) {
+        if (n) BPK_CUDA(cudaMemcpyAsync(d_stage, h_scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+        return msm_run(ctx, pts, d_stage, n, rshift, normalise, d_out);
+    }
+    MsmPlan pl;
+    BPK_TRY(msm_make_plan(ctx, pts, n, &pl));
+    xyzz_t *buckets, *buckets_b;
+    BPK_TRY(ws_reserve(ctx, 4, (size_t)pl.nb_total * sizeof(xyzz_t), (void**)&buckets));
+    BPK_TRY(ws_reserve(ctx, 15, (size_t)pl.nb_total * sizeof(xyzz_t), (void**)&buckets_b));
+    BPK_TRY(msm_reserve(ctx, pl, n - head));
+    if (!ctx->copy_stream) BPK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->copy_done) BPK_CUDA(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+    if (!ctx->lane_fork) BPK_CUDA(cudaEventCreateWithFlags(&ctx->lane_fork, cudaEventDisableTiming));
+    // the staging buffer may still be read by earlier work on the main stream
+    BPK_CUDA(cudaEventRecord(ctx->lane_fork, ctx->stream));
+    BPK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->lane_fork, 0));
+    BPK_CUDA(cudaMemcpyAsync(d_stage, h_scalars, head * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    BPK_TRY(msm_fill_buckets(ctx, pl, pts, d_stage, head, rshift, buckets));
+    BPK_CUDA(cudaMemcpyAsync(d_stage + head, h_scalars + 4 * head, (n - head) * sizeof(fr_t), cudaMemcpyHostToDevice,
+                             ctx->copy_stream));
+    BPK_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+    BPK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
+    MsmPoints rest = pts;
+    rest.base = pts.base + head;
+    BPK_TRY(msm_fill_buckets(ctx, pl, rest, d_stage + head, n - head, rshift, buckets_b));
+    {
+        StageTimer t(ctx, "msm.join");
+        msm_add_buckets_kernel<<<(unsigned)(((size_t)pl.nb_total + 127) / 128), 128, 0, ctx->stream>>>(buckets, buckets_b,
+                                                                                                pl.nb_total);
+        count_launch(ctx);
+        BPK_CUDA(cudaGetLastError());
+        t.end();
+    }
+    return msm_reduce_buckets(ctx, pl, buckets, normalise, d_out);
 }
 
 int g1_sum_run(bpk_ctx* ctx, const uint64_t* d_points_xyz, size_t n, uint64_t* d_out_xyz) {

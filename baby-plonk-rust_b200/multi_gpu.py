@@ -142,11 +142,20 @@ class ShardedCommitter:
                            "bpk_g1_sum_dev")
         return out.cpu().numpy().view(np.uint64)
 
-    def commit_host(self, scalars: np.ndarray, d_staging) -> np.ndarray:
-        """end-to-end: this rank's scalars in (pinned) host memory -> H2D -> sharded MSM -> D2H."""
-        import torch
+    def commit_host(self, scalars: np.ndarray, d_staging=None) -> np.ndarray:
+        """end-to-end: this rank's scalars in (pinned) host memory -> sharded MSM -> commitment on the host.
+        The upload is pipelined with the accumulation inside bpk_msm_g1_from_host (include/bpk.h)."""
+        import torch.distributed as dist
 
-        src = torch.from_numpy(scalars.view(np.int64).reshape(-1))
-        d_staging[: src.numel()].copy_(src, non_blocking=True)
-        out = self.commit_device(d_staging)
-        return out.cpu().numpy().view(np.uint64)
+        lib, h = self.ctx.lib, self.ctx.handle
+        sc = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+        n = sc.shape[0]
+        final = 1 if self.world == 1 else 0
+        dst = self.d_out if self.world == 1 else self.d_partial
+        self.ctx.check(lib.bpk_msm_g1_from_host(h, self.setup.handle, 0, sc.ctypes.data, n, final, dst.data_ptr()),
+                       "bpk_msm_g1_from_host")
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.d_gather.view(-1), self.d_partial, group=self.group)
+            self.ctx.check(lib.bpk_g1_sum_dev(h, self.d_gather.data_ptr(), self.world, self.d_out.data_ptr()),
+                           "bpk_g1_sum_dev")
+        return self.d_out.cpu().numpy().view(np.uint64)

@@ -95,6 +95,12 @@ int bpk_msm_g1_points(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n_points,
  * over NCCL and added by bpk_g1_sum. */
 int bpk_msm_g1_dev(bpk_ctx* ctx, uint64_t handle, size_t first, const void* d_scalars_mont,
                    size_t n, int normalise, void* d_out_xyz);
+/* Scalars in HOST memory, result on the device (normalise as in bpk_msm_g1_dev).  For n >= 2^22 the upload is
+ * pipelined with the computation: a head slice of n / 8 scalars is uploaded and accumulated while the copy engine
+ * brings the rest over on a second stream; with pinned host memory only the head's upload stays exposed.
+ * bpk_bucket_msm / bpk_msm_g1 (the Setup::commit path, src/setup.rs:32-37) use the same pipeline. */
+int bpk_msm_g1_from_host(bpk_ctx* ctx, uint64_t handle, size_t first, const uint64_t* scalars_mont, size_t n,
+                         int normalise, void* d_out_xyz);
 /* `count` independent commitments on the same SRS in one call (the three wire commitments of round 1, the three
  * quotient pieces of round 3, the two opening proofs of round 5: src/prover.rs:253-262, 487-497, 640-646).
  * d_scalars_mont, first and n are host arrays of `count` device pointers / slice starts / lengths; d_out_xyz
@@ -184,7 +190,7 @@ int bpk_imad_peak(bpk_ctx* ctx, double* wide_imad_per_s_out, double* seconds_out
 /* Tunables (A/B measurements and tests; the defaults are the measured optima):
  *   "msm.window" window bits of the non-precomputed MSM (0 = auto), "msm.chunk" pairs per accumulate thread (0 = auto),
  *   "msm.reduce" 0 = bit-plane bucket reduction, 1 = fan-in running-sum tree ("msm.fanin" 2..32),
- *   "msm.lanes" 1..3 concurrent MSMs of bpk_msm_g1_dev_batch,
+ *   "msm.lanes" 1..3 concurrent MSMs of bpk_msm_g1_dev_batch, "msm.host_slices" 0 = no upload / compute overlap,
  *   "ntt.tile_log2" log2 of the R x C tile per CTA (default 10), "ntt.max_radix_log2" (0 = auto), "ntt.threads",
  *   "ntt.kernel" 0 = auto, 1 = one radix-2 stage per barrier, 2 = register-blocked radix-8 steps,
  *   "ntt.direct_max_log2" largest per-size inter-pass twiddle table, "imad.mode" probe form of bpk_imad_peak.

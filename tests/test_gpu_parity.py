@@ -686,3 +686,40 @@ def test_msm_and_ntt_at_the_largest_practical_sizes(ctx):
     assert int(torch.count_nonzero(probe)) == 0
     ctx.check(ctx.lib.bpk_ntt_fr_dev(ctx.handle, y.data_ptr(), y.data_ptr(), n, 1, 1, None), "intt")
     assert torch.equal(x, y)
+
+
+def test_msm_from_host_pipelined_upload_matches_device_path(ctx):
+    """bpk_msm_g1_from_host / bpk_msm_g1 at n >= 2^22: head slice + rest on two streams, bucket sets joined;
+    must equal the device-resident MSM and the closed form, pinned or pageable memory, overlap on or off"""
+    import torch
+
+    n = (1 << 22) + 77
+    period = 1 << 12
+    block = O.random_fr(4242, period)
+    reps = (n + period - 1) // period
+    host = torch.from_numpy(np.tile(S(block), (reps, 1))[:n].copy().view(np.int64))
+    pinned = host.pin_memory()
+    base = 0
+    for j in reversed(range(period)):
+        base = (base * 101 + block[j]) % O.Q
+    step = pow(101, period, O.Q)
+    full, rem = divmod(n, period)
+    tail = 0
+    for j in reversed(range(rem)):
+        tail = (tail * 101 + block[j]) % O.Q
+    want = O.g1_mul(O.G1_GEN, (base * (pow(step, full, O.Q) - 1) * pow(step - 1, -1, O.Q) + tail * pow(step, full, O.Q)) % O.Q)
+    out = torch.zeros(18, dtype=torch.int64, device="cuda")
+    for pre in (False, True):
+        setup = bpk.Setup.generate_srs(n, 101, ctx)
+        if pre:
+            setup.precompute(0)
+        for slices in (1, 0):
+            ctx.set_option("msm.host_slices", slices)
+            for src in (pinned, host):
+                ctx.check(ctx.lib.bpk_msm_g1_from_host(ctx.handle, setup.handle, 0, src.data_ptr(), n, 1, out.data_ptr()),
+                          "from_host")
+                assert bpk.point_to_affine(out.cpu().numpy().view(np.uint64)) == want, (pre, slices)
+        ctx.set_option("msm.host_slices", 1)
+        # Setup::commit path (host in, host out) and a slice of the SRS with an un-normalised partial
+        assert bpk.point_to_affine(setup.commit_scalars(host.numpy().view(np.uint64))) == want
+        setup.free()
