@@ -150,26 +150,35 @@ __global__ void __launch_bounds__(128, BPK_ACC_MINBLOCKS) msm_accumulate_kernel(
     bool left_open = false;
     xyzz_t acc = xyzz_t::inf();
 
-    // software pipeline: entry e+1 is fetched while entry e is added
-    uint32_t k_next = keys[a];
+    // software pipeline: the point of entry e+1 is fetched while entry e is added, and the (key, value) pair of
+    // entry e+2 is already in registers, so the gather never waits behind the two strided index loads
+    uint32_t k_next = keys[a], v_next = vals[a];
+    uint32_t k_next2 = INVALID_KEY, v_next2 = 0;
+    if (a + 1 < b) {
+        k_next2 = keys[a + 1];
+        v_next2 = vals[a + 1];
+    }
     affine_t p_next = affine_t::inf();
     if (k_next < nb_total) {
-        uint32_t v = vals[a];
-        p_next = ld_affine(points + (v & 0x7fffffffu));
-        if (v >> 31) p_next.y = neg(p_next.y);
+        p_next = ld_affine(points + (v_next & 0x7fffffffu));
+        if (v_next >> 31) p_next.y = neg(p_next.y);
     }
     size_t e = a;
     for (; e < b; e++) {
         uint32_t k = k_next;
         if (k >= nb_total) break;
         affine_t p = p_next;
-        if (e + 1 < b) {
-            k_next = keys[e + 1];
-            if (k_next < nb_total) {
-                uint32_t v = vals[e + 1];
-                p_next = ld_affine(points + (v & 0x7fffffffu));
-                if (v >> 31) p_next.y = neg(p_next.y);
-            }
+        k_next = k_next2;
+        v_next = v_next2;
+        if (e + 2 < b) {
+            k_next2 = keys[e + 2];
+            v_next2 = vals[e + 2];
+        } else {
+            k_next2 = INVALID_KEY;
+        }
+        if (e + 1 < b && k_next < nb_total) {
+            p_next = ld_affine(points + (v_next & 0x7fffffffu));
+            if (v_next >> 31) p_next.y = neg(p_next.y);
         }
         if (k != cur) {
             if (cur != INVALID_KEY) {  // close the previous run (cannot be right-open)
