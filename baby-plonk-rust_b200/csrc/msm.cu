@@ -384,7 +384,10 @@ __global__ void __launch_bounds__(128) msm_reduce_level_kernel(const xyzz_t* __r
 // running-sum chains; the wide levels run at arithmetic throughput, each narrow level costs one addition of
 // latency.  2^p is applied once, in the final Horner pass over the root's L plane sums.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) msm_plane_tree_level_kernel(const xyzz_t* __restrict__ in,
+#ifndef BPK_TREE_MINBLOCKS
+#define BPK_TREE_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(128, BPK_TREE_MINBLOCKS) msm_plane_tree_level_kernel(const xyzz_t* __restrict__ in,
                                                                     xyzz_t* __restrict__ out, uint32_t k,
                                                                     size_t nodes_out) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -686,7 +689,7 @@ static int msm_fill_buckets(bpk_ctx* ctx, const MsmPlan& pl, const MsmPoints& pt
 }
 
 // buckets_a[i] += buckets_b[i]: joins the bucket sets of two slices of one MSM
-__global__ void __launch_bounds__(128) msm_add_buckets_kernel(xyzz_t* __restrict__ a, const xyzz_t* __restrict__ b,
+__global__ void __launch_bounds__(128, 3) msm_add_buckets_kernel(xyzz_t* __restrict__ a, const xyzz_t* __restrict__ b,
                                                                size_t count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
