@@ -223,7 +223,7 @@ struct LongRun {
     uint32_t key, t0, t1, pad;
 };
 
-__global__ void __launch_bounds__(128) msm_merge_partials_kernel(const uint32_t* __restrict__ pkeys,
+__global__ void __launch_bounds__(128, 3) msm_merge_partials_kernel(const uint32_t* __restrict__ pkeys,
                                                                   const xyzz_t* __restrict__ pvals,
                                                                   size_t num_chunks, xyzz_t* __restrict__ buckets,
                                                                   const uint32_t* __restrict__ keys, uint32_t chunk,
