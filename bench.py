@@ -145,7 +145,7 @@ def run_reference(args):
     n = 1 << args.logn
     threads = os.cpu_count() or 1
     from oracle import cref
-    n_s = min(n, threads << 13)
+    n_s = min(n, threads << 15)   # ~4 s of work on every host thread per step
     pts = cref.g1_iota(n_s)
     sc = gen_scalars(n_s, 999)
     times = []
@@ -315,7 +315,7 @@ def main():
             also["prove_s_2^%d_gates" % args.prove_logn] = prove
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        n_s = min(n_total, threads << 13)
+        n_s = min(n_total, threads << 15)   # ~4-8 s on every host thread: a bounded sample, extrapolated linearly
         pts = com.setup.powers_of_x(0, n_s)
         ms, info = cpu_reference_msm(n_total, threads, points_xyz=pts, scalars=h_scalars[:n_s])
         cpu_baseline = {"value": ms, "unit": "ms", "cores": threads, "kind": "port",
