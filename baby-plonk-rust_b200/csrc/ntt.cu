@@ -283,6 +283,157 @@ __global__ void __launch_bounds__(256) ntt_pass_r8_kernel(NttPassParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Experimental variant (ntt.kernel = 3): 4 rows per thread, two stages per exchange, and the two butterflies of a
+// stage share ONE out-of-line call that forms both products -- four interleaved carry chains per warp instead
+// of two, at a register budget that still allows 16+ warps per SM.
+// ---------------------------------------------------------------------------------------------
+struct fr_pair_t {
+    fr_t a, b;
+};
+static __device__ __noinline__ fr_pair_t fr_mul2_nl(fr_t a0, fr_t b0, fr_t a1, fr_t b1) {
+    fr_pair_t r;
+    r.a = mul(a0, b0);
+    r.b = mul(a1, b1);
+    return r;
+}
+
+template <int T>
+__device__ __forceinline__ void dit_stage4(fr_t (&x)[4], uint32_t sigma, uint32_t base, uint32_t b0, uint32_t logR,
+                                           const uint4* t_lo, const uint4* t_hi) {
+    constexpr int a = 0, c = T == 0 ? 2 : 1;            // lower rows of the two butterflies
+    constexpr int a1 = a | (1 << T), c1 = c | (1 << T);
+    const uint32_t mask = (1u << (sigma - 1)) - 1;
+    const uint32_t ea = ((base + ((uint32_t)a << b0)) & mask) << (logR - sigma);
+    const uint32_t ec = ((base + ((uint32_t)c << b0)) & mask) << (logR - sigma);
+    const fr_pair_t pr = fr_mul2_nl(x[a1], ld_sm(t_lo, t_hi, ea), x[c1], ld_sm(t_lo, t_hi, ec));
+    const fr_t ua = x[a], uc = x[c];
+    x[a] = add(ua, pr.a);
+    x[a1] = sub(ua, pr.a);
+    x[c] = add(uc, pr.b);
+    x[c1] = sub(uc, pr.b);
+}
+
+__global__ void __launch_bounds__(256) ntt_pass_r4d_kernel(NttPassParams p) {
+    extern __shared__ uint4 smem[];
+    const uint32_t logR = p.logR, logC = p.logC, logNs = p.logNs;
+    const uint32_t R = 1u << logR, C = 1u << logC, RC = R << logC;
+    uint4* s_lo = smem;
+    uint4* s_hi = smem + RC;
+    uint4* t_lo = smem + 2 * RC;
+    uint4* t_hi = t_lo + (R >> 1);
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;  // nt == RC / 4
+    const size_t n = (size_t)1 << p.logn;
+    const fr_t* in = p.in + (size_t)blockIdx.y * n;
+    fr_t* out = p.out + (size_t)blockIdx.y * n;
+    const uint32_t j0 = blockIdx.x << logC;
+    const uint32_t c = tid & (C - 1), g = tid >> logC;  // column, group of 4 rows
+    const uint32_t j = j0 + c;
+    const uint32_t ns_mask = (1u << logNs) - 1;
+
+    for (uint32_t i = tid; i < (R >> 1); i += nt) {
+        fr_t w = table_pow(p.tw_lo, p.tw_hi, i << (NTT_MAX_LOG - logR));
+        st_sm(t_lo, t_hi, i, w);
+    }
+    __syncthreads();
+
+    // step 1: rows brev(4 g + a), inter-pass twiddle (two products per call), stages 1..2
+    fr_t x[4];
+    uint32_t base = g << 2, b0 = 0;
+    {
+        const uint32_t stride_in = (uint32_t)(n >> logR);
+        const uint32_t tw_shift = NTT_MAX_LOG - (logNs + logR);
+        const uint32_t k = j & ns_mask;
+        uint32_t rr[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            rr[a] = __brev(base + a) >> (32 - logR);
+            const uint32_t gi = j + rr[a] * stride_in;
+            fr_t v = ld_fr(in + gi);
+            if (p.coset_in) v = fr_mul_nl(v, table_pow(p.cs_lo, p.cs_hi, gi));
+            x[a] = v;
+        }
+        if (logNs) {
+#pragma unroll
+            for (int a = 0; a < 4; a += 2) {
+                fr_t w0, w1;
+                if (p.tw_direct) {
+                    w0 = ld_fr(p.tw_direct + k * rr[a]);
+                    w1 = ld_fr(p.tw_direct + k * rr[a + 1]);
+                } else {
+                    w0 = table_pow(p.tw_lo, p.tw_hi, (k * rr[a]) << tw_shift);
+                    w1 = table_pow(p.tw_lo, p.tw_hi, (k * rr[a + 1]) << tw_shift);
+                }
+                const fr_pair_t pr = fr_mul2_nl(x[a], w0, x[a + 1], w1);
+                x[a] = pr.a;
+                x[a + 1] = pr.b;
+            }
+        }
+        // stage 1: twiddles 1; stage 2: pairs (0,2) twiddle 1, (1,3) twiddle w_R^(R/4)
+        {
+            fr_t u = x[0], t = x[1];
+            x[0] = add(u, t);
+            x[1] = sub(u, t);
+            u = x[2];
+            t = x[3];
+            x[2] = add(u, t);
+            x[3] = sub(u, t);
+            u = x[0];
+            t = x[2];
+            x[0] = add(u, t);
+            x[2] = sub(u, t);
+            u = x[1];
+            t = fr_mul_nl(x[3], ld_sm(t_lo, t_hi, 1u << (logR - 2)));
+            x[1] = add(u, t);
+            x[3] = sub(u, t);
+        }
+    }
+    uint32_t done = 2;
+    while (done < logR) {
+#pragma unroll
+        for (int a = 0; a < 4; a++) st_sm(s_lo, s_hi, ((base + ((uint32_t)a << b0)) << logC) + c, x[a]);
+        __syncthreads();
+        const uint32_t k = logR - done < 2 ? 1 : 2;
+        const uint32_t s = done + 1;
+        b0 = s - 1 < logR - 2 ? s - 1 : logR - 2;
+        base = ((g >> b0) << (b0 + 2)) | (g & ((1u << b0) - 1));
+#pragma unroll
+        for (int a = 0; a < 4; a++) x[a] = ld_sm(s_lo, s_hi, ((base + ((uint32_t)a << b0)) << logC) + c);
+        if (k == 2) {
+            dit_stage4<0>(x, s, base, b0, logR, t_lo, t_hi);
+            dit_stage4<1>(x, s + 1, base, b0, logR, t_lo, t_hi);
+        } else {
+            dit_stage4<1>(x, s, base, b0, logR, t_lo, t_hi);
+        }
+        done += k;
+    }
+    if (logNs != 0) {
+        const size_t o0 = ((size_t)(j >> logNs) << (logNs + logR)) + (j & ns_mask);
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const uint32_t r = base + ((uint32_t)a << b0);
+            const size_t o = o0 + ((size_t)r << logNs);
+            fr_t v = x[a];
+            if (p.scale_out == 1) v = fr_mul_nl(v, p.scale);
+            else if (p.scale_out == 2) v = fr_mul_nl(v, table_pow(p.cs_lo, p.cs_hi, (uint32_t)o));
+            st_fr(out + o, v);
+        }
+        return;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; a++) st_sm(s_lo, s_hi, ((base + ((uint32_t)a << b0)) << logC) + c, x[a]);
+    __syncthreads();
+    for (uint32_t idx = tid; idx < RC; idx += nt) {
+        const uint32_t r = idx & (R - 1), cc = idx >> logR;
+        const size_t o = ((size_t)(j0 + cc) << logR) + r;
+        fr_t v = ld_sm(s_lo, s_hi, (r << logC) + cc);
+        if (p.scale_out == 1) v = fr_mul_nl(v, p.scale);
+        else if (p.scale_out == 2) v = fr_mul_nl(v, table_pow(p.cs_lo, p.cs_hi, (uint32_t)o));
+        st_fr(out + o, v);
+    }
+}
+
 // out[i] = pre * base^(i << shift)
 __global__ void pow_table_kernel(fr_t* out, fr_t base, fr_t pre, uint32_t count, uint32_t shift) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -346,6 +497,7 @@ int ntt_init_tables(bpk_ctx* ctx) {
     fr_t roots[2] = {root, inv(root)};
     BPK_CUDA(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     BPK_CUDA(cudaFuncSetAttribute(ntt_pass_r8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    BPK_CUDA(cudaFuncSetAttribute(ntt_pass_r4d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     for (int d = 0; d < 2; d++) {
         BPK_CUDA(cudaMalloc(&ctx->tw_lo[d], sizeof(fr_t) << TW_LO_BITS));
         BPK_CUDA(cudaMalloc(&ctx->tw_hi[d], sizeof(fr_t) << TW_HI_BITS));
@@ -405,7 +557,12 @@ int ntt_run(bpk_ctx* ctx, const fr_t* d_in, fr_t* d_out, size_t n, size_t batch,
         return BPK_OK;
     }
 
-    const uint32_t tile_log = (uint32_t)ctx->opt_ntt_tile_log2;  // log2(R * C)
+    // transforms too small to fill the GPU with the 8-row kernel: 4 rows per thread on 2^9-element tiles
+    // (2^16: 0.046 -> 0.033 ms, profiles/r1_ntt_kernel_ab.md)
+    const bool big = (n * batch) >= ((size_t)1 << 18);
+    const bool small_auto = !big && ctx->opt_ntt_kernel == 0 && logn > 9;
+    uint32_t tile_log = (uint32_t)ctx->opt_ntt_tile_log2;  // log2(R * C)
+    if (small_auto && tile_log > 9) tile_log = 9;
     // auto (0): one pass up to the tile size, otherwise radices <= 2^8 so that a tile keeps >= 4 adjacent columns
     // (3 x 2^20: 0.67 -> 0.61 ms against two passes of 2^10, profiles/r1_ntt_kernel_ab.md)
     uint32_t max_logR = ctx->opt_ntt_max_radix_log2 ? (uint32_t)ctx->opt_ntt_max_radix_log2 : (logn <= tile_log ? tile_log : 8);
@@ -464,8 +621,9 @@ int ntt_run(bpk_ctx* ctx, const fr_t* d_in, fr_t* d_out, size_t n, size_t batch,
         unsigned threads = (unsigned)ctx->opt_ntt_threads;
         if (threads == 0) threads = (logR + logC >= 12) ? 1024 : 256;
         // register-blocked kernel unless the transform is too small to fill the GPU with 128-thread CTAs
-        const bool big = (n * batch) >= ((size_t)1 << 18);
-        if (logR >= 3 && logR + logC <= 11 && (ctx->opt_ntt_kernel == 0 ? big : ctx->opt_ntt_kernel == 2))
+        if ((ctx->opt_ntt_kernel == 3 || small_auto) && logR >= 2 && logR + logC <= 10)
+            ntt_pass_r4d_kernel<<<grid, 1u << (logR + logC - 2), smem, ctx->stream>>>(p);
+        else if (logR >= 3 && logR + logC <= 11 && (ctx->opt_ntt_kernel == 0 ? big : ctx->opt_ntt_kernel == 2))
             ntt_pass_r8_kernel<<<grid, 1u << (logR + logC - 3), smem, ctx->stream>>>(p);
         else
             ntt_pass_kernel<<<grid, threads, smem, ctx->stream>>>(p);

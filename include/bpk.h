@@ -192,7 +192,8 @@ int bpk_imad_peak(bpk_ctx* ctx, double* wide_imad_per_s_out, double* seconds_out
  *   "msm.reduce" 0 = bit-plane bucket reduction, 1 = fan-in running-sum tree ("msm.fanin" 2..32),
  *   "msm.lanes" 1..3 concurrent MSMs of bpk_msm_g1_dev_batch, "msm.host_slices" 0 = no upload / compute overlap,
  *   "ntt.tile_log2" log2 of the R x C tile per CTA (default 10), "ntt.max_radix_log2" (0 = auto), "ntt.threads",
- *   "ntt.kernel" 0 = auto, 1 = one radix-2 stage per barrier, 2 = register-blocked radix-8 steps,
+ *   "ntt.kernel" 0 = auto, 1 = one radix-2 stage per barrier, 2 = register-blocked radix-8 steps, 3 = 4 rows per
+ *   thread with two products per call (auto uses it below 2^18 elements),
  *   "ntt.direct_max_log2" largest per-size inter-pass twiddle table, "imad.mode" probe form of bpk_imad_peak.
  * Unknown keys and out-of-range values return BPK_ERR_INVALID_ARG. */
 int bpk_set_option(bpk_ctx* ctx, const char* key, long value);

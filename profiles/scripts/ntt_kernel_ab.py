@@ -13,7 +13,7 @@ for logn, batch in ((22, 1), (24, 1), (20, 3), (16, 1)):
     a = rng.integers(0, 1 << 64, size=(n * batch, 4), dtype=np.uint64); a[:, 3] &= np.uint64((1 << 62) - 1)
     x = torch.from_numpy(a.view(np.int64).reshape(-1)).cuda(); y = torch.empty_like(x)
     ref = None
-    for kern, tile, maxr in ((1, 10, 10), (0, 10, 10), (0, 10, 8), (0, 11, 11), (0, 11, 10), (0, 11, 8), (0, 10, 9), (0, 11, 9), (0, 9, 9), (0, 10, 6), (0, 11, 6)):
+    for kern, tile, maxr in ((1, 10, 10), (0, 10, 10), (0, 10, 8), (0, 11, 11), (0, 11, 10), (0, 11, 8), (0, 10, 9), (0, 11, 9), (0, 9, 9), (0, 10, 6), (0, 11, 6), (3, 10, 8), (3, 10, 10), (3, 9, 8), (3, 9, 9), (3, 10, 6), (3, 8, 8)):
         ctx.set_option("ntt.kernel", kern); ctx.set_option("ntt.tile_log2", tile); ctx.set_option("ntt.max_radix_log2", maxr)
         ts = []
         for it in range(7):

@@ -94,7 +94,7 @@ def test_ntt_tile_shapes(ctx, tile):
         ctx.set_option("ntt.tile_log2", 10)
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 @pytest.mark.parametrize("tile,maxr", [(5, 0), (8, 3), (9, 4), (10, 5), (10, 0), (11, 7), (11, 11)])
 def test_ntt_both_pass_kernels_every_step_shape(ctx, kernel, tile, maxr):
     """ntt.kernel 1 = one radix-2 stage per barrier, 2 = register-blocked radix-8 steps (falls back to 1 for
