@@ -184,6 +184,8 @@ __device__ __forceinline__ void dit_stage8(fr_t (&x)[8], uint32_t sigma, uint32_
     }
 }
 
+// (register caps for 5 or 6 CTAs per SM were measured: 1.05 / 1.02 ms at 2^22 against 0.875 ms -- spills cost more than
+// the extra warps bring; even spelling the bound as (256, 1) changes ptxas' allocation to 140 registers and 0.925 ms)
 __global__ void __launch_bounds__(256) ntt_pass_r8_kernel(NttPassParams p) {
     extern __shared__ uint4 smem[];
     const uint32_t logR = p.logR, logC = p.logC, logNs = p.logNs;

@@ -13,7 +13,7 @@ result replication) is testable on CPU with world_size 2 over gloo.
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Tuple
+from typing import Callable, Tuple
 
 import numpy as np
 
