@@ -723,3 +723,29 @@ def test_msm_from_host_pipelined_upload_matches_device_path(ctx):
         # Setup::commit path (host in, host out) and a slice of the SRS with an un-normalised partial
         assert bpk.point_to_affine(setup.commit_scalars(host.numpy().view(np.uint64))) == want
         setup.free()
+
+
+def test_msm_from_host_slice_and_partial(ctx):
+    """bpk_msm_g1_from_host on a slice of the SRS (first > 0) with an un-normalised partial as output: the
+    per-rank leg of the sharded end-to-end path; partials of two halves must add up to the whole commitment"""
+    import torch
+
+    n = 3001
+    setup = bpk.Setup.generate_srs(n, 101, ctx)
+    sc = O.random_fr(5151, n)
+    host = S(sc)
+    parts = torch.zeros((2, 18), dtype=torch.int64, device="cuda")
+    lo = n // 2
+    ctx.check(ctx.lib.bpk_msm_g1_from_host(ctx.handle, setup.handle, 0, host[:lo].ctypes.data, lo, 0,
+                                           parts[0].data_ptr()), "from_host")
+    tail = np.ascontiguousarray(host[lo:])
+    ctx.check(ctx.lib.bpk_msm_g1_from_host(ctx.handle, setup.handle, lo, tail.ctypes.data, n - lo, 0,
+                                           parts[1].data_ptr()), "from_host")
+    total = bpk.g1_sum(parts.cpu().numpy().view(np.uint64), ctx)
+    assert bpk.point_to_affine(total) == horner_expected(sc, 101)
+    # argument checks: slice beyond the SRS, null scalars
+    assert ctx.lib.bpk_msm_g1_from_host(ctx.handle, setup.handle, n - 1, host.ctypes.data, 2, 1, parts[0].data_ptr()) == -3
+    assert ctx.lib.bpk_msm_g1_from_host(ctx.handle, setup.handle, 0, None, 2, 1, parts[0].data_ptr()) == -3
+    assert ctx.lib.bpk_msm_g1_from_host(ctx.handle, setup.handle, 0, None, 0, 1, parts[0].data_ptr()) == 0
+    assert bpk.point_to_affine(parts[0].cpu().numpy().view(np.uint64)) is None
+    setup.free()
