@@ -649,6 +649,61 @@ extern "C" int bpk_poly_mul_fr_dev(bpk_ctx* ctx, const void* d_a, size_t la, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// device memory for callers without a CUDA runtime binding of their own (Rust / C++ hosts of the
+// device-resident entry points); all transfers are ordered on the context's stream
+// ------------------------------------------------------------------------------------------------
+extern "C" int bpk_dev_alloc(bpk_ctx* ctx, size_t bytes, void** d_out) {
+    if (!ctx || !d_out) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    *d_out = nullptr;
+    cudaError_t e = cudaMalloc(d_out, bytes ? bytes : 16);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return BPK_ERR_OOM;
+    }
+    BPK_CUDA(e);
+    return BPK_OK;
+}
+
+extern "C" int bpk_dev_free(bpk_ctx* ctx, void* d_ptr) {
+    if (!ctx) return BPK_ERR_INVALID_ARG;
+    if (!d_ptr) return BPK_OK;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    BPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    BPK_CUDA(cudaFree(d_ptr));
+    return BPK_OK;
+}
+
+extern "C" int bpk_dev_upload(bpk_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+    if (!ctx || (bytes && (!d_dst || !h_src))) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    if (bytes) BPK_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return BPK_OK;
+}
+
+extern "C" int bpk_dev_download(bpk_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+    if (!ctx || (bytes && (!h_dst || !d_src))) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    if (bytes) BPK_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    BPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BPK_OK;
+}
+
+extern "C" int bpk_dev_copy(bpk_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
+    if (!ctx || (bytes && (!d_dst || !d_src))) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    if (bytes) BPK_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return BPK_OK;
+}
+
+extern "C" int bpk_dev_zero(bpk_ctx* ctx, void* d_dst, size_t bytes) {
+    if (!ctx || (bytes && !d_dst)) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    if (bytes) BPK_CUDA(cudaMemsetAsync(d_dst, 0, bytes, ctx->stream));
+    return BPK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // device-resident Fr vector / polynomial primitives (prover rounds)
 // ------------------------------------------------------------------------------------------------
 extern "C" int bpk_fr_vec_op(bpk_ctx* ctx, int op, const void* d_a, const void* d_b, const uint64_t* scalar_mont,

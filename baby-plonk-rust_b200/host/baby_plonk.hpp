@@ -69,6 +69,7 @@ struct Scalar {
     Scalar operator+(const Scalar& o) const { return from_fe(bpk::add(to_fe(*this), to_fe(o))); }
     Scalar operator-(const Scalar& o) const { return from_fe(bpk::sub(to_fe(*this), to_fe(o))); }
     Scalar neg() const { return from_fe(bpk::neg(to_fe(*this))); }
+    Scalar invert() const { return from_fe(bpk::inv(to_fe(*this))); }  // scalar.rs:394-..., zero maps to zero
     Scalar pow(uint64_t e) const { return from_fe(bpk::pow_u64(to_fe(*this), e)); }  // pow(&[e,0,0,0])
     bool operator==(const Scalar& o) const { return std::memcmp(l, o.l, sizeof l) == 0; }
     bool operator!=(const Scalar& o) const { return !(*this == o); }

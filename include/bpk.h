@@ -139,6 +139,16 @@ int bpk_poly_mul_fr(bpk_ctx* ctx, const uint64_t* a, size_t la, const uint64_t* 
 /* Same with device pointers (la, lb >= 1; d_out holds la + lb - 1 coefficients; may not alias the inputs). */
 int bpk_poly_mul_fr_dev(bpk_ctx* ctx, const void* d_a, size_t la, const void* d_b, size_t lb, void* d_out);
 
+/* ---- device memory (for hosts without a CUDA binding of their own: the Rust / C++ callers of the d_* entry points) ----
+ * Transfers and fills are ordered on the context's stream; bpk_dev_download returns when the bytes have arrived;
+ * bpk_dev_upload from pageable memory returns when the source may be reused. */
+int bpk_dev_alloc(bpk_ctx* ctx, size_t bytes, void** d_out);
+int bpk_dev_free(bpk_ctx* ctx, void* d_ptr);
+int bpk_dev_upload(bpk_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int bpk_dev_download(bpk_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+int bpk_dev_copy(bpk_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
+int bpk_dev_zero(bpk_ctx* ctx, void* d_dst, size_t bytes);
+
 /* ---- device-resident Fr vector / polynomial primitives (the callers' O(n) work) ----
  * All pointers named d_* are device pointers to n x 4 u64 Montgomery limbs; scalars are host pointers to
  * 4 u64.  These keep the prover's polynomials in HBM between the NTTs and the commitments. */
