@@ -217,6 +217,9 @@ extern "C" void bpk_destroy(bpk_ctx* ctx) {
             if (t) cudaFree(t);
     }
     if (ctx->gen_table) cudaFree(ctx->gen_table);
+    for (auto& kv : ctx->dev_pool)
+        for (void* p : kv.second) cudaFree(p);
+    for (auto& kv : ctx->dev_live) cudaFree(kv.first);
     for (int l = 0; l < MSM_LANES; l++) {
         if (ctx->lane_stream[l]) cudaStreamDestroy(ctx->lane_stream[l]);
         if (ctx->lane_done[l]) cudaEventDestroy(ctx->lane_done[l]);
@@ -656,21 +659,38 @@ extern "C" int bpk_dev_alloc(bpk_ctx* ctx, size_t bytes, void** d_out) {
     if (!ctx || !d_out) return BPK_ERR_INVALID_ARG;
     BPK_CUDA(cudaSetDevice(ctx->device));
     *d_out = nullptr;
-    cudaError_t e = cudaMalloc(d_out, bytes ? bytes : 16);
-    if (e == cudaErrorMemoryAllocation) {
-        cudaGetLastError();
-        return BPK_ERR_OOM;
+    bytes = (bytes + 255) / 256 * 256;
+    if (bytes == 0) bytes = 256;
+    auto it = ctx->dev_pool.find(bytes);
+    if (it != ctx->dev_pool.end() && !it->second.empty()) {  // reuse is ordered by the context's stream
+        *d_out = it->second.back();
+        it->second.pop_back();
+    } else {
+        cudaError_t e = cudaMalloc(d_out, bytes);
+        if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and retry once
+            cudaGetLastError();
+            for (auto& kv : ctx->dev_pool)
+                for (void* p : kv.second) cudaFree(p);
+            ctx->dev_pool.clear();
+            e = cudaMalloc(d_out, bytes);
+            if (e == cudaErrorMemoryAllocation) {
+                cudaGetLastError();
+                return BPK_ERR_OOM;
+            }
+        }
+        BPK_CUDA(e);
     }
-    BPK_CUDA(e);
+    ctx->dev_live[*d_out] = bytes;
     return BPK_OK;
 }
 
 extern "C" int bpk_dev_free(bpk_ctx* ctx, void* d_ptr) {
     if (!ctx) return BPK_ERR_INVALID_ARG;
     if (!d_ptr) return BPK_OK;
-    BPK_CUDA(cudaSetDevice(ctx->device));
-    BPK_CUDA(cudaStreamSynchronize(ctx->stream));
-    BPK_CUDA(cudaFree(d_ptr));
+    auto it = ctx->dev_live.find(d_ptr);
+    if (it == ctx->dev_live.end()) return BPK_ERR_INVALID_ARG;  // not from bpk_dev_alloc (or freed twice)
+    ctx->dev_pool[it->second].push_back(d_ptr);
+    ctx->dev_live.erase(it);
     return BPK_OK;
 }
 

@@ -80,6 +80,11 @@ struct bpk_ctx {
     cudaStream_t copy_stream = nullptr;  // uploads the tail of a host-resident MSM input under the head's accumulation
     cudaEvent_t copy_done = nullptr;
 
+    // bpk_dev_alloc / bpk_dev_free: freed blocks are kept by size and handed out again (a prover allocates the same
+    // sizes for every proof; cudaMalloc / cudaFree would synchronise the device each time)
+    std::map<size_t, std::vector<void*>> dev_pool;
+    std::map<void*, size_t> dev_live;
+
     std::map<uint64_t, bpk::SrsEntry> srs;
     uint64_t next_handle = 1;
 

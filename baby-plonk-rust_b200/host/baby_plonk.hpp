@@ -233,6 +233,8 @@ struct Setup {
         if (powers) check(bpk_srs_read(ctx(), s.handle, 0, powers, s.powers_of_x[0].x), "generate_srs: read");
         return s;
     }
+    // optional: keep the window levels [2^(c w)] P_i next to the SRS (bpk_srs_precompute); results are unchanged
+    void precompute(unsigned window_bits = 0) const { check(bpk_srs_precompute(ctx(), handle, window_bits), "precompute"); }
     G1Projective commit(const Polynomial& polynomial) const {      // setup.rs:32-37
         if (polynomial.basis != Basis::Monomial) throw Panic("assertion `left == right` failed: basis == Monomial");
         G1Projective out = G1Projective::identity();

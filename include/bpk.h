@@ -141,7 +141,8 @@ int bpk_poly_mul_fr_dev(bpk_ctx* ctx, const void* d_a, size_t la, const void* d_
 
 /* ---- device memory (for hosts without a CUDA binding of their own: the Rust / C++ callers of the d_* entry points) ----
  * Transfers and fills are ordered on the context's stream; bpk_dev_download returns when the bytes have arrived;
- * bpk_dev_upload from pageable memory returns when the source may be reused. */
+ * bpk_dev_upload from pageable memory returns when the source may be reused.  Freed blocks are cached by size and
+ * reused (stream-ordered, no device synchronisation); everything is released by bpk_destroy. */
 int bpk_dev_alloc(bpk_ctx* ctx, size_t bytes, void** d_out);
 int bpk_dev_free(bpk_ctx* ctx, void* d_ptr);
 int bpk_dev_upload(bpk_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);

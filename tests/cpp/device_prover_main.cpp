@@ -3,6 +3,7 @@
 // prints the 624 proof bytes as hex.  Layout of the input file:
 //   u64 n, u64 n_pub, u64 srs_powers, u64 cache, u64 reps, Scalar tau,
 //   5 selector columns, 3 sigma columns, 3 wire columns (n Scalars each), n_pub public inputs, 11 blinding scalars
+#include <chrono>
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -38,9 +39,13 @@ int main(int argc, char** argv) {
         std::vector<Scalar> pub = read_col(f, n_pub), blinding = read_col(f, 11);
         if (!f) throw Panic("short instance file");
         Setup setup = Setup::generate_srs(powers, tau);
+        if (n >= 64) setup.precompute();
         DeviceProver prover(setup, n, sel, sig, cache);
         for (int r = 0; r < reps; r++) {
+            auto t0 = std::chrono::steady_clock::now();
             Proof proof = prover.prove(wires, pub, blinding);
+            double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            std::fprintf(stderr, "prove_ms %.3f\n", ms);
             auto bytes = proof.to_bytes();
             for (uint8_t b : bytes) std::printf("%02x", b);
             std::printf("\n");
