@@ -749,3 +749,33 @@ def test_msm_from_host_slice_and_partial(ctx):
     assert ctx.lib.bpk_msm_g1_from_host(ctx.handle, setup.handle, 0, None, 0, 1, parts[0].data_ptr()) == 0
     assert bpk.point_to_affine(parts[0].cpu().numpy().view(np.uint64)) is None
     setup.free()
+
+
+def test_device_memory_helpers(ctx):
+    """bpk_dev_alloc / free / upload / download / copy / zero: round trip, pooled reuse of a freed block, error codes"""
+    import ctypes
+
+    lib, h = ctx.lib, ctx.handle
+    a = ctypes.c_void_p()
+    b = ctypes.c_void_p()
+    ctx.check(lib.bpk_dev_alloc(h, 1000, ctypes.byref(a)), "alloc")
+    ctx.check(lib.bpk_dev_alloc(h, 1000, ctypes.byref(b)), "alloc")
+    assert a.value and b.value and a.value != b.value
+    src = np.arange(125, dtype=np.uint64)
+    dst = np.zeros(125, dtype=np.uint64)
+    ctx.check(lib.bpk_dev_upload(h, a, src.ctypes.data, 1000), "upload")
+    ctx.check(lib.bpk_dev_copy(h, b, a, 1000), "copy")
+    ctx.check(lib.bpk_dev_zero(h, a, 496), "zero")
+    ctx.check(lib.bpk_dev_download(h, dst.ctypes.data, b, 1000), "download")
+    assert np.array_equal(dst, src)
+    ctx.check(lib.bpk_dev_download(h, dst.ctypes.data, a, 1000), "download")
+    assert not dst[:62].any() and np.array_equal(dst[62:], src[62:])
+    ctx.check(lib.bpk_dev_free(h, a), "free")
+    assert lib.bpk_dev_free(h, a) == -3                      # double free / foreign pointer
+    c = ctypes.c_void_p()
+    ctx.check(lib.bpk_dev_alloc(h, 900, ctypes.byref(c)), "alloc")   # same 256-byte size class: the block comes back
+    assert c.value == a.value
+    ctx.check(lib.bpk_dev_free(h, b), "free")
+    ctx.check(lib.bpk_dev_free(h, c), "free")
+    assert lib.bpk_dev_free(h, None) == 0
+    assert lib.bpk_dev_alloc(h, 16, None) == -3
