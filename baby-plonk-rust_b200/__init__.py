@@ -111,6 +111,8 @@ _SIGNATURES = {
                                            ctypes.c_void_p, ctypes.c_size_t]),
     "bpk_fr_poly_eval": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                         ctypes.c_void_p]),
+    "bpk_fr_poly_eval_many": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p]),
     "bpk_fr_poly_div_linear": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                               ctypes.c_void_p]),
     "bpk_fr_poly_div_vanishing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
@@ -119,6 +121,7 @@ _SIGNATURES = {
                                 [ctypes.c_void_p] * 5),
     "bpk_plonk_quotient_evals": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                                 ctypes.c_size_t] + [ctypes.c_void_p] * 7),
+    "bpk_keccak_f1600": (None, [ctypes.c_void_p]),
     "bpk_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "bpk_profile_reset": (ctypes.c_int, [ctypes.c_void_p]),
     "bpk_profile_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double),

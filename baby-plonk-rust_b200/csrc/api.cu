@@ -756,6 +756,21 @@ extern "C" int bpk_fr_poly_eval(bpk_ctx* ctx, const void* d_coeffs, size_t n, co
     return BPK_OK;
 }
 
+extern "C" int bpk_fr_poly_eval_many(bpk_ctx* ctx, size_t count, const void* const* d_coeffs, const size_t* n,
+                                     const uint64_t x_mont[4], uint64_t* out_mont) {
+    if (!ctx || !x_mont || (count && (!d_coeffs || !n || !out_mont)) || count > 64) return BPK_ERR_INVALID_ARG;
+    for (size_t i = 0; i < count; i++)
+        if (n[i] && !d_coeffs[i]) return BPK_ERR_INVALID_ARG;
+    if (count == 0) return BPK_OK;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    fr_t* d_out;
+    BPK_TRY(ws_reserve(ctx, 10, sizeof(fr_t) * 64, (void**)&d_out));
+    BPK_TRY(fr_poly_eval_many(ctx, count, (const fr_t* const*)d_coeffs, n, fr_from_host(x_mont), d_out));
+    BPK_CUDA(cudaMemcpyAsync(out_mont, d_out, count * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    BPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BPK_OK;
+}
+
 extern "C" int bpk_fr_poly_div_linear(bpk_ctx* ctx, const void* d_coeffs, size_t n, const uint64_t root_mont[4],
                                       void* d_quotient) {
     if (!ctx || !root_mont || (n >= 2 && (!d_coeffs || !d_quotient))) return BPK_ERR_INVALID_ARG;
@@ -792,6 +807,39 @@ extern "C" int bpk_plonk_quotient_evals(bpk_ctx* ctx, const void* d_witness_eval
     for (size_t i = 0; i < domain / n; ++i) zh[i] = fr_from_host(zh_inv_mont + 4 * i);
     return plonk_quotient_evals(ctx, (const fr_t*)d_witness_evals, (const fr_t*)d_circuit_evals, domain, n, fr_from_host(beta), fr_from_host(gamma),
                                 fr_from_host(alpha), fr_from_host(k1), fr_from_host(k2), zh, (fr_t*)d_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host utility: keccak-f[1600] for the Fiat-Shamir transcript of the host layers (merlin / STROBE-128 sits on it;
+// a few dozen permutations per proof, which cost ~10 ms when done in interpreted Python)
+// ------------------------------------------------------------------------------------------------
+extern "C" void bpk_keccak_f1600(uint64_t s[25]) {
+    static const int rho[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+    uint64_t lfsr = 1;
+    for (int round = 0; round < 24; round++) {
+        uint64_t rc = 0;
+        for (int j = 0; j < 7; j++) {
+            if (lfsr & 1) rc |= (uint64_t)1 << ((1 << j) - 1);
+            lfsr <<= 1;
+            if (lfsr & 0x100) lfsr ^= 0x171;
+        }
+        uint64_t c[5], m[25];
+        for (int x = 0; x < 5; x++) c[x] = s[x] ^ s[x + 5] ^ s[x + 10] ^ s[x + 15] ^ s[x + 20];
+        for (int x = 0; x < 5; x++) {
+            uint64_t r = c[(x + 1) % 5];
+            uint64_t d = c[(x + 4) % 5] ^ ((r << 1) | (r >> 63));
+            for (int y = 0; y < 25; y += 5) s[x + y] ^= d;
+        }
+        for (int x = 0; x < 5; x++)
+            for (int y = 0; y < 5; y++) {
+                int k = rho[x + 5 * y];
+                uint64_t v = s[x + 5 * y];
+                m[y + 5 * ((2 * x + 3 * y) % 5)] = k ? (v << k) | (v >> (64 - k)) : v;
+            }
+        for (int y = 0; y < 25; y += 5)
+            for (int x = 0; x < 5; x++) s[x + y] = m[x + y] ^ (~m[(x + 1) % 5 + y] & m[(x + 2) % 5 + y]);
+        s[0] ^= rc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

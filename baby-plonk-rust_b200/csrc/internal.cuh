@@ -159,6 +159,7 @@ int launch_pow_table(bpk_ctx* ctx, fr_t* d_out, const fr_t& base, const fr_t& pr
 int fr_vec_op(bpk_ctx* ctx, int op, const fr_t* a, const fr_t* b, const fr_t& s, fr_t* out, size_t n);
 int fr_scale_powers(bpk_ctx* ctx, const fr_t* a, const fr_t& g, const fr_t& c0, fr_t* out, size_t n);
 int fr_poly_eval(bpk_ctx* ctx, const fr_t* c, size_t n, const fr_t& x, fr_t* d_out);
+int fr_poly_eval_many(bpk_ctx* ctx, size_t count, const fr_t* const* c, const size_t* n, const fr_t& x, fr_t* d_out);
 int fr_poly_div_linear(bpk_ctx* ctx, const fr_t* c, size_t n, const fr_t& root, fr_t* q);
 int fr_poly_div_vanishing(bpk_ctx* ctx, const fr_t* c, size_t len, size_t n, fr_t* q);
 int plonk_grand_product(bpk_ctx* ctx, const fr_t* A, const fr_t* B, const fr_t* C, const fr_t* s1, const fr_t* s2,

@@ -265,6 +265,30 @@ int fr_poly_eval(bpk_ctx* ctx, const fr_t* c, size_t n, const fr_t& x, fr_t* d_o
     return BPK_OK;
 }
 
+// several polynomials at the same point: one pair of power tables, the partial sums of all polynomials side by side
+int fr_poly_eval_many(bpk_ctx* ctx, size_t count, const fr_t* const* c, const size_t* n, const fr_t& x, fr_t* d_out) {
+    size_t n_max = 1;
+    for (size_t i = 0; i < count; i++) {
+        if (n[i] > ((size_t)1 << NTT_MAX_LOG)) return BPK_ERR_TOO_LARGE;
+        if (n[i] > n_max) n_max = n[i];
+    }
+    StageTimer t(ctx, "fr.eval");
+    fr_t *lo, *hi;
+    BPK_TRY(power_tables(ctx, x, fr_t::one(), n_max, &lo, &hi));
+    const unsigned stride = grid_for(ctx, n_max, 256);
+    fr_t* partial;
+    BPK_TRY(ws_reserve(ctx, 13, (size_t)stride * (count ? count : 1) * sizeof(fr_t), (void**)&partial));
+    for (size_t i = 0; i < count; i++) {
+        const unsigned blocks = grid_for(ctx, n[i] ? n[i] : 1, 256);
+        fr_eval_partial_kernel<<<blocks, 256, 0, ctx->stream>>>(c[i], lo, hi, n[i], partial + (size_t)i * stride);
+        fr_sum_kernel<<<1, 256, 0, ctx->stream>>>(partial + (size_t)i * stride, blocks, d_out + i);
+    }
+    count_launch(ctx, 2 * count);
+    BPK_CUDA(cudaGetLastError());
+    t.end();
+    return BPK_OK;
+}
+
 // q = c / (X - root), remainder dropped; c has n coefficients, q gets n - 1
 int fr_poly_div_linear(bpk_ctx* ctx, const fr_t* c, size_t n, const fr_t& root, fr_t* q) {
     if (n < 2) return BPK_OK;

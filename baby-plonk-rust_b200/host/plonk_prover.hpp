@@ -445,11 +445,19 @@ public:
         const Scalar zeta = tr.get_and_append_challenge("zeta");
 
         // ---- round 4 (prover.rs:502-541)
-        pf.a_bar = eval(kc(0), n + 2, zeta);
-        pf.b_bar = eval(kc(1), n + 2, zeta);
-        pf.c_bar = eval(kc(2), n + 2, zeta);
-        pf.s1_bar = eval(pkc(5), n, zeta);
-        pf.s2_bar = eval(pkc(6), n, zeta);
+        Scalar pi_zeta;
+        {
+            const void* ptrs[6] = {kc(0), kc(1), kc(2), pkc(5), pkc(6), kc(4)};
+            const size_t lens[6] = {n + 2, n + 2, n + 2, n, n, n};
+            Scalar ev[6];
+            check(bpk_fr_poly_eval_many(ctx(), 6, ptrs, lens, zeta.l, ev[0].l), "bpk_fr_poly_eval_many");
+            pf.a_bar = ev[0];
+            pf.b_bar = ev[1];
+            pf.c_bar = ev[2];
+            pf.s1_bar = ev[3];
+            pf.s2_bar = ev[4];
+            pi_zeta = ev[5];
+        }
         pf.z_omega_bar = eval(z, n + 3, zeta * omega);
         tr.append_scalar("a_eval", pf.a_bar);
         tr.append_scalar("b_eval", pf.b_bar);
@@ -463,7 +471,6 @@ public:
         const Scalar one = Scalar::one();
         const Scalar zeta_n = zeta.pow(n), zh_zeta = zeta_n - one;
         const Scalar l1_zeta = zh_zeta * (Scalar::from(n) * (zeta - one)).invert();
-        const Scalar pi_zeta = eval(kc(4), n, zeta);
         const Scalar f = (pf.a_bar + zeta * beta + gamma) * (pf.b_bar + zeta * beta * k1 + gamma) *
                          (pf.c_bar + zeta * beta * k2 + gamma);
         const Scalar g = (pf.a_bar + pf.s1_bar * beta + gamma) * (pf.b_bar + pf.s2_bar * beta + gamma) * pf.z_omega_bar;

@@ -192,6 +192,17 @@ class DeviceProver:
                                            out.ctypes.data), "bpk_fr_poly_eval")
         return _from_mont(out)
 
+    def _eval_many(self, items, x: int) -> list:
+        """[(coeffs, length), ...] at one point: one pair of power tables, one device -> host copy"""
+        k = len(items)
+        ptrs = (ctypes.c_void_p * k)(*[t.data_ptr() for t, _ in items])
+        lens = (ctypes.c_size_t * k)(*[length for _, length in items])
+        out = np.empty((k, 4), dtype=np.uint64)
+        xm = _mont(x)
+        self._ck(self.lib.bpk_fr_poly_eval_many(self.ctx.handle, k, ptrs, lens, xm.ctypes.data, out.ctypes.data),
+                 "bpk_fr_poly_eval_many")
+        return [_from_mont(out[i]) for i in range(k)]
+
     def _commit(self, coeffs, length: int) -> bytes:
         """Setup::commit (src/setup.rs:32-37) on device-resident coefficients -> compressed G1"""
         if self.committer is not None:
@@ -361,11 +372,8 @@ class DeviceProver:
         marks.append(("round3", time.perf_counter()))
 
         # ---- round 4 (prover.rs:502-541)
-        a_bar = self._eval(row["a"], n + 2, zeta)
-        b_bar = self._eval(row["b"], n + 2, zeta)
-        c_bar = self._eval(row["c"], n + 2, zeta)
-        s1_bar = self._eval(s1c, n, zeta)
-        s2_bar = self._eval(s2c, n, zeta)
+        a_bar, b_bar, c_bar, s1_bar, s2_bar, pi_zeta = self._eval_many(
+            [(row["a"], n + 2), (row["b"], n + 2), (row["c"], n + 2), (s1c, n), (s2c, n), (row["pi"], n)], zeta)
         z_omega_bar = self._eval(z, n + 3, zeta * self.omega % Q)       # z(omega X) at zeta
         for lab, v in ((b"a_eval", a_bar), (b"b_eval", b_bar), (b"c_eval", c_bar), (b"s1_eval", s1_bar),
                        (b"s2_eval", s2_bar), (b"z_shifted_eval", z_omega_bar)):
@@ -377,7 +385,6 @@ class DeviceProver:
         zeta_n = pow(zeta, n, Q)
         zh_zeta = (zeta_n - 1) % Q
         l1_zeta = zh_zeta * pow(n * (zeta - 1) % Q, -1, Q) % Q            # = (1/n) sum zeta^i
-        pi_zeta = self._eval(row["pi"], n, zeta)
         f = (a_bar + zeta * beta + gamma) * (b_bar + zeta * beta * K1 + gamma) % Q * (c_bar + zeta * beta * K2 + gamma) % Q
         g = (a_bar + s1_bar * beta + gamma) * (b_bar + s2_bar * beta + gamma) % Q * z_omega_bar % Q
         a2 = alpha * alpha % Q

@@ -7,9 +7,13 @@ Scalar, then appended back under the same label.
 
 merlin 3.0.0 is a Cargo dependency of the reference, not part of its tree; what is implemented here is its
 published construction: STROBE-128 (rate 166, operations meta-AD / AD / PRF) over keccak-f[1600].
-A few hundred bytes per proof pass through this, so it stays on the host.
+A few hundred bytes per proof pass through this, so it stays on the host.  The permutation itself is the library's
+``bpk_keccak_f1600`` (C++, host): interpreted, the ~25 permutations of a proof cost ~10 ms, a tenth of a 2^20-gate
+proof.  ``keccak_f1600`` below is the same permutation in plain Python, kept as the cross-check of the native one.
 """
 from __future__ import annotations
+
+import ctypes
 
 FR_MODULUS = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 
@@ -67,6 +71,21 @@ def keccak_f1600(lanes: list) -> list:
     return s
 
 
+_native = None
+
+
+def _native_keccak():
+    """bpk_keccak_f1600 from libbpk.so (dlopen works without a GPU); None if the library is not built"""
+    global _native
+    if _native is None:
+        try:
+            from . import load_library
+            _native = load_library().bpk_keccak_f1600
+        except Exception:
+            _native = False
+    return _native or None
+
+
 class _Strobe:
     """STROBE-128/1600 duplex restricted to the three operations merlin uses"""
     RATE = 166
@@ -82,6 +101,10 @@ class _Strobe:
         self.operate(self.M | self.A, protocol)
 
     def _permute(self):
+        fn = _native_keccak()
+        if fn is not None:
+            fn((ctypes.c_uint8 * 200).from_buffer(self.buf))
+            return
         lanes = [int.from_bytes(self.buf[8 * i:8 * i + 8], "little") for i in range(25)]
         self.buf = bytearray(b"".join(v.to_bytes(8, "little") for v in keccak_f1600(lanes)))
 

@@ -162,6 +162,10 @@ int bpk_fr_scale_powers(bpk_ctx* ctx, const void* d_a, const uint64_t g_mont[4],
                         void* d_out, size_t n);
 /* Polynomial::coeffs_evaluate (src/polynomial.rs:34-45): sum_i c_i x^i. */
 int bpk_fr_poly_eval(bpk_ctx* ctx, const void* d_coeffs, size_t n, const uint64_t x_mont[4], uint64_t out_mont[4]);
+/* The same for `count` (<= 64) polynomials at one point (round 4 evaluates a, b, c, s1, s2 at zeta, src/prover.rs:502-541):
+ * d_coeffs and n are host arrays of device pointers / lengths, out_mont receives count x 4 u64. */
+int bpk_fr_poly_eval_many(bpk_ctx* ctx, size_t count, const void* const* d_coeffs, const size_t* n,
+                          const uint64_t x_mont[4], uint64_t* out_mont);
 /* impl Div by the linear polynomial X - root (src/polynomial.rs:314-380 as used at src/prover.rs:623-638):
  * n coefficients in, n - 1 quotient coefficients out, remainder dropped. */
 int bpk_fr_poly_div_linear(bpk_ctx* ctx, const void* d_coeffs, size_t n, const uint64_t root_mont[4],
@@ -184,6 +188,12 @@ int bpk_plonk_grand_product(bpk_ctx* ctx, const void* d_a, const void* d_b, cons
 int bpk_plonk_quotient_evals(bpk_ctx* ctx, const void* d_witness_evals, const void* d_circuit_evals, size_t domain,
                              size_t n, const uint64_t beta[4], const uint64_t gamma[4], const uint64_t alpha[4],
                              const uint64_t k1[4], const uint64_t k2[4], const uint64_t* zh_inv_mont, void* d_out);
+
+/* ---- host utility ---------------------------------------------------------------------------------
+ * keccak-f[1600] on 25 little-endian 64-bit lanes (lane x + 5 y), in place; runs on the host.  The Fiat-Shamir
+ * transcript of the reference (src/transcript.rs over merlin / STROBE-128) sits on it; the Python host layer calls
+ * it instead of permuting in the interpreter. */
+void bpk_keccak_f1600(uint64_t lanes[25]);
 
 /* ---- instrumentation (bench.py, tests) -------------------------------------------------------- */
 /* When enabled, every kernel stage is bracketed by CUDA events on the context's stream. */

@@ -90,6 +90,22 @@ def test_scale_powers_and_eval(ctx, torch, n):
     assert bpk.scalars_to_ints(res)[0] == P.p_eval(a, x)
 
 
+def test_eval_many(ctx, torch):
+    """bpk_fr_poly_eval_many: polynomials of different lengths (incl. empty) at one point"""
+    import ctypes
+
+    lens = [1, 0, 7, 9000, 20001]
+    polys = [O.random_fr(20 + i, max(k, 1)) for i, k in enumerate(lens)]
+    d = [up(torch, p) for p in polys]
+    x = O.random_fr(30, 1)[0]
+    k = len(lens)
+    ptrs = (ctypes.c_void_p * k)(*[t.data_ptr() for t in d])
+    ls = (ctypes.c_size_t * k)(*lens)
+    out = np.zeros((k, 4), dtype=np.uint64)
+    ctx.check(ctx.lib.bpk_fr_poly_eval_many(ctx.handle, k, ptrs, ls, m(x).ctypes.data, out.ctypes.data), "eval_many")
+    assert bpk.scalars_to_ints(out) == [P.p_eval(p[:ln], x) for p, ln in zip(polys, lens)]
+
+
 @pytest.mark.parametrize("n", [2, 3, 9, 4099, 66000])
 def test_div_linear_matches_reference_long_division(ctx, torch, n):
     """impl Div (polynomial.rs:314-380) by X - root; non-exact division: the remainder is dropped"""

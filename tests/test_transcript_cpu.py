@@ -46,3 +46,18 @@ def test_plonk_transcript_schedule_matches_oracle():
     a.append_scalar(b"a_eval", 12345)
     b.append_scalar(b"a_eval", 12345)
     assert a.get_and_append_challenge(b"nu") == b.get_and_append_challenge(b"nu")
+
+
+def test_native_keccak_matches_the_python_permutation():
+    """bpk_keccak_f1600 (libbpk.so, host code) is what the transcript calls; the plain-Python permutation is its check"""
+    import ctypes
+    import random
+
+    fn = T._native_keccak()
+    assert fn is not None, "libbpk.so must be built (python __graft_entry__.py build)"
+    rng = random.Random(5)
+    for _ in range(20):
+        state = bytearray(rng.getrandbits(8) for _ in range(200))
+        lanes = [int.from_bytes(state[8 * i:8 * i + 8], "little") for i in range(25)]
+        fn((ctypes.c_uint8 * 200).from_buffer(state))
+        assert bytes(state) == b"".join(v.to_bytes(8, "little") for v in T.keccak_f1600(lanes))
