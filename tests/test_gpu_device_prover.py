@@ -209,6 +209,12 @@ def test_reference_test_program_on_device(ctx):
     assert trace == cpu_trace
     assert proof.to_bytes() == cpu.to_bytes()
     assert proof.sha256() == "479cc377c535fd831b5fcaf30af5c2756c535a3ddbc20589ab6759843e974967"
+    # second run of SURVEY 8d's C1: blinding drawn from SplitMix64(seed 42) as Scalar::random would
+    blinding = O.random_fr(42, 11)
+    again = prover.prove(wires, pub, blinding)
+    assert again.to_bytes() == P.prove(prog, wit, blinding, P.OracleBackend(O.generate_srs_points(14, 101))).to_bytes()
+    assert P.verify(prog, as_oracle_proof(again), pub, 101,
+                    lambda c: bpk.point_to_affine(setup.commit(bpk.Polynomial.from_ints(c))))
 
 
 @pytest.mark.parametrize("n,used,seed,cache", [(16, 10, 7, False), (64, 64, 8, True), (256, 200, 9, False)])
