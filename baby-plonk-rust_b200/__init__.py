@@ -158,21 +158,13 @@ def load_library() -> ctypes.CDLL:
 # ---------------------------------------------------------------------------------------------
 def scalars_from_ints(values: Iterable[int]) -> np.ndarray:
     """canonical integers -> uint64[n, 4] Montgomery limbs (what Vec<Scalar> holds)"""
-    vals = list(values)
-    out = np.empty((len(vals), 4), dtype=np.uint64)
-    for i, v in enumerate(vals):
-        m = (v % FR_MODULUS) * _FR_R % FR_MODULUS
-        out[i] = [(m >> (64 * k)) & _MASK64 for k in range(4)]
-    return out
+    raw = b"".join(((v % FR_MODULUS) * _FR_R % FR_MODULUS).to_bytes(32, "little") for v in values)
+    return np.frombuffer(raw, dtype="<u8").reshape(-1, 4).astype(np.uint64)
 
 
 def scalars_to_ints(arr: np.ndarray) -> list:
-    arr = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
-    out = []
-    for row in arr:
-        m = int(row[0]) | (int(row[1]) << 64) | (int(row[2]) << 128) | (int(row[3]) << 192)
-        out.append(m * _FR_RINV % FR_MODULUS)
-    return out
+    raw = np.ascontiguousarray(arr, dtype="<u8").reshape(-1, 4).tobytes()
+    return [int.from_bytes(raw[k:k + 32], "little") * _FR_RINV % FR_MODULUS for k in range(0, len(raw), 32)]
 
 
 def _fp_limbs(v: int) -> list:
