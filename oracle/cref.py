@@ -34,6 +34,16 @@ def lib():
         L.oracle_g1_double.argtypes = [vp, vp]
         L.oracle_fr_horner.restype = None
         L.oracle_fr_horner.argtypes = [vp, sz, vp, vp]
+        L.oracle_poly_mul.restype = ci
+        L.oracle_poly_mul.argtypes = [vp, sz, vp, sz, vp]
+        L.oracle_g1_powers_small.restype = None
+        L.oracle_g1_powers_small.argtypes = [vp, ctypes.c_uint64, sz, vp]
+        L.oracle_fr_ntt_fast.restype = ci
+        L.oracle_fr_ntt_fast.argtypes = [vp, vp, sz, ci, ci]
+        L.oracle_fr_poly_at.restype = ci
+        L.oracle_fr_poly_at.argtypes = [vp, sz, vp, ci, vp]
+        L.oracle_msm_pippenger_mt.restype = ci
+        L.oracle_msm_pippenger_mt.argtypes = [vp, sz, vp, sz, ci, ci, vp]
         _lib = L
     return _lib
 
@@ -88,6 +98,23 @@ def binop(name, a, b, n):
     return out
 
 
+def poly_mul(a, b):
+    """impl Mul for Polynomial (Monomial) by the reference's own algorithm -> uint64[la + lb - 1, 4]"""
+    a, b = _u64(a).reshape(-1, 4), _u64(b).reshape(-1, 4)
+    out = np.zeros((a.shape[0] + b.shape[0] - 1, 4), dtype=np.uint64)
+    rc = lib().oracle_poly_mul(a.ctypes.data, a.shape[0], b.ctypes.data, b.shape[0], out.ctypes.data)
+    assert rc == 0
+    return out
+
+
+def g1_powers_small(start_xyz, k, n):
+    """start, [k]start, [k^2]start, ... as uint64[n,18] projective points (not normalised)"""
+    s = _u64(start_xyz).reshape(18)
+    out = np.zeros((n, 18), dtype=np.uint64)
+    lib().oracle_g1_powers_small(s.ctypes.data, k, n, out.ctypes.data)
+    return out
+
+
 def g1_iota(n):
     """[1]G .. [n]G as uint64[n,18] projective points (not normalised)"""
     L = lib()
@@ -95,4 +122,37 @@ def g1_iota(n):
     L.oracle_g1_iota.argtypes = [ctypes.c_size_t, ctypes.c_void_p]
     out = np.zeros((n, 18), dtype=np.uint64)
     L.oracle_g1_iota(n, out.ctypes.data)
+    return out
+
+
+# ---- optimised CPU baseline (oracle/fast_cpu.c): NOT the reference's algorithms -------------------------------
+def ntt_fast(elements, inverse=False, threads=0):
+    """radix-2 NTT on all host cores; same contract as ntt_381 / i_ntt_381 (natural order, Montgomery limbs)"""
+    e = _u64(elements).reshape(-1, 4)
+    out = np.empty_like(e)
+    rc = lib().oracle_fr_ntt_fast(e.ctypes.data, out.ctypes.data, e.shape[0], 1 if inverse else 0,
+                                  threads or os.cpu_count() or 1)
+    if rc != 0:
+        raise AssertionError("assertion failed: is_power_of_two(n)")
+    return out
+
+
+def poly_at(values, x_mont, threads=0):
+    """p(x) for p given by its values on the n-th roots of unity (inverse NTT + Horner) -> uint64[4] Montgomery"""
+    v, x = _u64(values).reshape(-1, 4), _u64(x_mont).reshape(4)
+    out = np.zeros(4, dtype=np.uint64)
+    rc = lib().oracle_fr_poly_at(v.ctypes.data, v.shape[0], x.ctypes.data, threads or os.cpu_count() or 1,
+                                 out.ctypes.data)
+    assert rc == 0
+    return out
+
+
+def msm_pippenger(points_xyz, scalars, threads=0, window=0):
+    """signed-digit Pippenger on all host cores; points must be normalised (Z = R) or the identity"""
+    p, s = _u64(points_xyz).reshape(-1, 18), _u64(scalars).reshape(-1, 4)
+    out = np.zeros(18, dtype=np.uint64)
+    rc = lib().oracle_msm_pippenger_mt(p.ctypes.data, p.shape[0], s.ctypes.data, s.shape[0],
+                                       threads or os.cpu_count() or 1, window, out.ctypes.data)
+    if rc != 0:
+        raise ValueError("oracle_msm_pippenger_mt: rc %d" % rc)
     return out

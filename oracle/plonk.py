@@ -326,6 +326,37 @@ class OracleBackend:
         return O.msm_naive(self.srs, coeffs)
 
 
+class CRefBackend:
+    """The three hot-path surfaces through the C restatement of the reference's OWN algorithms (oracle/ref_cpu.c):
+    naive O(n^2) i_ntt_381 (utils.rs:106-129), impl Mul by coeffs_evaluate + naive inverse DFT
+    (polynomial.rs:241-273), bucket_msm(256, 4) with complete projective additions (msm.rs:76-118).  This is the
+    reference-algorithm prover whose time bench.py reports as the CPU baseline of the prove metric."""
+
+    def __init__(self, srs_points):
+        import numpy as np
+        self.np = np
+        self.srs = np.array([O.g1_scale_proj(p, 1) for p in srs_points], dtype=np.uint64)
+
+    def _m(self, vals):
+        return self.np.array([O.fr_to_mont(v) for v in vals], dtype=self.np.uint64).reshape(-1, 4)
+
+    def _i(self, arr):
+        return [O.fr_from_mont([int(x) for x in row]) for row in arr]
+
+    def i_ntt(self, values):
+        from oracle import cref
+        return self._i(cref.ntt_381(self._m(values), inverse=True))
+
+    def mul(self, a, b):
+        from oracle import cref
+        return self._i(cref.poly_mul(self._m(a), self._m(b)))
+
+    def commit(self, coeffs):
+        from oracle import cref
+        assert len(coeffs) <= len(self.srs), "SRS too short"
+        return O.g1_proj_limbs_to_affine([int(v) for v in cref.bucket_msm(self.srs, self._m(coeffs), 256, 4)])
+
+
 # --------------------------------------------------------------------------------------------------
 # prover (src/prover.rs) -- SURVEY.md Appendix A
 # --------------------------------------------------------------------------------------------------
@@ -477,13 +508,49 @@ def verify(program: Program, proof: Proof, public_inputs, tau: int, commit) -> b
          tau * (W_zeta + mu W_zeta_omega) == zeta W_zeta + mu zeta omega W_zeta_omega + F - E   in G1,
     which is the pairing equation of verifier.rs:186-190 with the trapdoor known.  `commit` commits the
     eight pre-processed polynomials (verifier.rs:49-79 does that through Setup::commit, i.e. the hot path)."""
-    n = program.n
-    omega = O.root_of_unity(n)
-    G = O.G1_GEN
     ql, qr, qm, qo, qc = program.selectors()
     s1, s2, s3 = program.sigmas()
     inv = lambda v: O.ntt_fast(v, inverse=True)
-    cqm, cql, cqr, cqo, cqc, cs1, cs2, cs3 = (commit(inv(v)) for v in (qm, ql, qr, qo, qc, s1, s2, s3))
+    commitments = [commit(inv(v)) for v in (qm, ql, qr, qo, qc, s1, s2, s3)]
+    return verify_with_commitments(program.n, proof, public_inputs, tau, commitments)
+
+
+def lagrange_public_input_eval(n: int, public_inputs, zeta: int) -> int:
+    """PI(zeta) for PI = sum_i (-pub_i) L_i (verifier.rs:95-104 interpolates the column and evaluates it):
+    L_i(zeta) = w^i (zeta^n - 1) / (n (zeta - w^i)), O(len(public_inputs)) instead of an n-point transform"""
+    omega = O.root_of_unity(n)
+    zh = (pow(zeta, n, Q) - 1) % Q
+    acc, wi = 0, 1
+    for v in public_inputs:
+        acc = (acc - v * wi % Q * zh % Q * pow(n * (zeta - wi) % Q, -1, Q)) % Q
+        wi = wi * omega % Q
+    return acc
+
+
+def verify_columns(n: int, selectors_mont, sigmas_mont, proof: Proof, public_inputs, tau: int, threads: int = 0) -> bool:
+    """verify() for circuits given as pre-processed COLUMNS (uint64[n, 4] Montgomery arrays: [QL, QR, QM, QO, QC],
+    [S1, S2, S3]) at sizes where Python transforms are out of reach (2^20+ gates).  The eight pre-processed
+    commitments are formed on the ORACLE side in closed form, [p(tau)]G with p(tau) from the C inverse transform +
+    Horner (oracle/fast_cpu.c::oracle_fr_poly_at) -- no GPU result enters the check except the proof itself."""
+    import numpy as np
+    from oracle import cref
+    tau_m = np.array(O.fr_to_mont(tau % Q), dtype=np.uint64)
+    ql, qr, qm, qo, qc = selectors_mont
+    s1, s2, s3 = sigmas_mont
+    commitments = []
+    for col in (qm, ql, qr, qo, qc, s1, s2, s3):
+        assert col.shape == (n, 4)
+        e = O.fr_from_mont([int(x) for x in cref.poly_at(col, tau_m, threads)])
+        commitments.append(O.g1_mul(O.G1_GEN, e))
+    return verify_with_commitments(n, proof, public_inputs, tau, commitments, fast_pi=True)
+
+
+def verify_with_commitments(n: int, proof: Proof, public_inputs, tau: int, commitments, fast_pi: bool = False) -> bool:
+    """the verifier equation given the commitments [QM, QL, QR, QO, QC, S1, S2, S3] of the pre-processed polynomials"""
+    omega = O.root_of_unity(n)
+    G = O.G1_GEN
+    inv = lambda v: O.ntt_fast(v, inverse=True)
+    cqm, cql, cqr, cqo, cqc, cs1, cs2, cs3 = commitments
     tr = PlonkTranscript()
     for lab in ("a_1", "b_1", "c_1"):
         tr.append_point(lab.encode(), getattr(proof, lab))
@@ -504,8 +571,11 @@ def verify(program: Program, proof: Proof, public_inputs, tau: int, commit) -> b
 
     zh = (pow(zeta, n, Q) - 1) % Q
     l1 = zh * pow(n * (zeta - 1) % Q, -1, Q) % Q
-    pi_vals = [(-v) % Q for v in public_inputs] + [0] * (n - len(public_inputs))
-    pi_zeta = p_eval(inv(pi_vals), zeta)
+    if fast_pi:
+        pi_zeta = lagrange_public_input_eval(n, public_inputs, zeta)
+    else:
+        pi_vals = [(-v) % Q for v in public_inputs] + [0] * (n - len(public_inputs))
+        pi_zeta = p_eval(inv(pi_vals), zeta)
     ab, bb_, cb, s1b, s2b, zwb = (proof.a_bar, proof.b_bar, proof.c_bar, proof.s1_bar, proof.s2_bar, proof.z_omega_bar)
     r0 = (pi_zeta - l1 * alpha * alpha - alpha * (ab + beta * s1b + gamma) * (bb_ + beta * s2b + gamma) % Q
           * (cb + gamma) % Q * zwb) % Q

@@ -367,6 +367,45 @@ int oracle_ntt_381_rows(const u64* in, u64* out, size_t n, int inverse, size_t r
     return dft_rows(in, out, n, inverse, row_lo, row_hi);
 }
 
+/* ------------------------------------------------------------------ src/polynomial.rs */
+/* roots_of_unity (utils.rs:45-52): [1, w, w^2, ...] by sequential multiplication, w = ROOT^(2^32 / n) by pow */
+static void roots_of_unity_seq(size_t n, fr* out) {
+    u64 by[4] = {((u64)1 << 32) / n, 0, 0, 0};
+    fr w = fr_pow(ROOT_OF_UNITY, by), cur = fr_one();
+    for (size_t i = 0; i < n; i++) {
+        out[i] = cur;
+        cur = fr_mul(cur, w);
+    }
+}
+/* coeffs_evaluate (polynomial.rs:34-45): sum_i c_i * x.pow([i,0,0,0]) -- one 256-bit pow per term */
+static fr coeffs_evaluate(const fr* c, size_t len, fr x) {
+    fr res = {{0, 0, 0, 0}};
+    for (size_t i = 0; i < len; i++) {
+        u64 by[4] = {(u64)i, 0, 0, 0};
+        res = fr_add(res, fr_mul(c[i], fr_pow(x, by)));
+    }
+    return res;
+}
+/* impl Mul for Polynomial, Monomial branch (polynomial.rs:241-273): evaluate both operands on the D-th roots of
+ * unity (D = find_next_power_of_two, utils.rs:54-61), multiply pointwise, i_ntt_381, keep la + lb - 1 coefficients */
+int oracle_poly_mul(const u64* a, size_t la, const u64* b, size_t lb, u64* out) {
+    if (la == 0 || lb == 0) return -1;
+    size_t target = la + lb - 1, D = 1;
+    while (D < target) D <<= 1;
+    fr* roots = (fr*)malloc(sizeof(fr) * D);
+    fr* prod = (fr*)malloc(sizeof(fr) * D);
+    fr* coef = (fr*)malloc(sizeof(fr) * D);
+    roots_of_unity_seq(D, roots);
+    for (size_t i = 0; i < D; i++)
+        prod[i] = fr_mul(coeffs_evaluate((const fr*)a, la, roots[i]), coeffs_evaluate((const fr*)b, lb, roots[i]));
+    int rc = dft_rows((const u64*)prod, (u64*)coef, D, 1, 0, D);
+    memcpy(out, coef, sizeof(fr) * target);
+    free(roots);
+    free(prod);
+    free(coef);
+    return rc;
+}
+
 /* ------------------------------------------------------------------ helpers for the tests */
 void oracle_fp_mul(const u64* a, const u64* b, u64* r) { f_mul(&FP, r, a, b); }
 void oracle_fr_mul(const u64* a, const u64* b, u64* r) { f_mul(&FR, r, a, b); }
@@ -397,5 +436,21 @@ void oracle_g1_iota(size_t n, u64* out_xyz) {
     for (size_t i = 0; i < n; i++) {
         memcpy(out_xyz + 18 * i, &cur, sizeof cur);
         cur = g1_add(&cur, &g);
+    }
+}
+/* P, [k]P, [k^2]P, ... (n points) for a small multiplier k by double-and-add with the complete formulas:
+ * the synthetic SRS [tau^i]G of the benchmark workload (Setup::generate_srs, setup.rs:12-31, multiplies by tau
+ * the same way) for the CPU timing legs, continued from any starting point so that threads can split the range */
+void oracle_g1_powers_small(const u64* start_xyz, u64 k, size_t n, u64* out_xyz) {
+    g1p cur;
+    memcpy(&cur, start_xyz, sizeof cur);
+    for (size_t i = 0; i < n; i++) {
+        memcpy(out_xyz + 18 * i, &cur, sizeof cur);
+        g1p acc = g1_identity();
+        for (int b = 63; b >= 0; b--) {
+            acc = g1_double(&acc);
+            if ((k >> b) & 1) acc = g1_add(&acc, &cur);
+        }
+        cur = acc;
     }
 }

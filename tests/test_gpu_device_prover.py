@@ -264,3 +264,33 @@ def test_device_prove_at_scale_self_verifies(ctx):
     assert P.verify(prog, proof, pub, 101, commit)
     proof.z_omega_bar = (proof.z_omega_bar + 1) % Q
     assert not P.verify(prog, proof, pub, 101, commit)
+
+
+@pytest.mark.parametrize("logn", [20, 22])
+def test_full_size_proofs_verify_against_oracle_commitments(ctx, logn):
+    """BASELINE.json configs[3] (2^20 gates, the circuit family bench.py times) and 2^22: prove on the device, then
+    check the verifier equation (verifier.rs:186-190, trapdoor form) with the eight pre-processed commitments
+    formed on the ORACLE side in closed form [p(tau)]G (C inverse transform + Horner), so that no GPU result but
+    the proof itself enters the check -- prove -> verify as tests/verify_proof_test.rs:13-50, at scale.  A flipped
+    evaluation, a flipped commitment and a different circuit must all be rejected."""
+    prover_mod = importlib.import_module("baby-plonk-rust_b200.prover")
+    synthetic = importlib.import_module("baby-plonk-rust_b200.synthetic")
+    n = 1 << logn
+    circ = synthetic.chain_circuit(n, n - 3, seed=2)
+    setup = bpk.Setup.generate_srs(n + 8, 101, ctx)
+    setup.precompute(0)
+    prover = prover_mod.DeviceProver(setup, n, circ["selectors"], circ["sigmas"])
+    blinding = O.random_fr(42, 11)
+    proof = as_oracle_proof(prover.prove(circ["wires"], circ["public_inputs"], blinding))
+    del prover
+    setup.free()
+    sel, sig, pub = circ["selectors"], circ["sigmas"], circ["public_inputs"]
+    assert P.verify_columns(n, sel, sig, proof, pub, 101)
+    proof.s1_bar = (proof.s1_bar + 1) % Q
+    assert not P.verify_columns(n, sel, sig, proof, pub, 101)
+    proof.s1_bar = (proof.s1_bar - 1) % Q
+    if logn == 20:
+        proof.t_mid_1 = O.g1_add(proof.t_mid_1, O.G1_GEN)
+        assert not P.verify_columns(n, sel, sig, proof, pub, 101)
+        proof.t_mid_1 = O.g1_add(proof.t_mid_1, O.g1_neg(O.G1_GEN))
+        assert not P.verify_columns(n, sel, sig, proof, [pub[0] + 1], 101)
