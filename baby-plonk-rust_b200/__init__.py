@@ -74,6 +74,7 @@ _SIGNATURES = {
     "bpk_srs_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p]),
     "bpk_srs_len": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_size_t)]),
     "bpk_srs_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64]),
+    "bpk_srs_table_bytes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_size_t)]),
     "bpk_bucket_msm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t,
                                       ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p]),
     "bpk_msm_g1": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
@@ -128,6 +129,7 @@ _SIGNATURES = {
                                        ctypes.POINTER(ctypes.c_uint64)]),
     "bpk_launch_count": (ctypes.c_uint64, [ctypes.c_void_p]),
     "bpk_msm_last_plan": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint)]),
+    "bpk_msm_last_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]),
     "bpk_imad_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "bpk_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_long]),
 }
@@ -280,6 +282,14 @@ class Context:
         arr = (ctypes.c_uint * 4)()
         self.check(self.lib.bpk_msm_last_plan(self.handle, arr), "bpk_msm_last_plan")
         return {"window_bits": arr[0], "windows": arr[1], "pairs_per_thread": arr[2], "buckets": arr[3]}
+
+    def msm_last_stats(self) -> dict:
+        """counters of the most recent MSM (synchronises): how its additions split between the batched-affine
+        pairwise tree and the XYZZ tail"""
+        arr = (ctypes.c_uint64 * 6)()
+        self.check(self.lib.bpk_msm_last_stats(self.handle, arr), "bpk_msm_last_stats")
+        return {"entries": int(arr[0]), "affine_adds": int(arr[1]), "xyzz_adds_bound": int(arr[2]),
+                "nonempty_buckets": int(arr[3]), "tree_levels": int(arr[4]), "batch": int(arr[5])}
 
     def synchronize(self):
         self.check(self.lib.bpk_synchronize(self.handle), "bpk_synchronize")
@@ -481,6 +491,13 @@ class Setup:
         self.ctx.check(self.ctx.lib.bpk_srs_precompute(self.ctx.handle, self.handle, int(window_bits)),
                        "bpk_srs_precompute")
         return self
+
+    def table_bytes(self) -> int:
+        """HBM bytes of the point table behind this Setup (W x the SRS after precompute)"""
+        out = ctypes.c_size_t()
+        self.ctx.check(self.ctx.lib.bpk_srs_table_bytes(self.ctx.handle, self.handle, ctypes.byref(out)),
+                       "bpk_srs_table_bytes")
+        return int(out.value)
 
     def powers_of_x(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
         count = self.n - first if count is None else count

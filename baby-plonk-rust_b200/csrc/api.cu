@@ -46,6 +46,11 @@ void StageTimer::end() {
     pe.stop = stop;
     pe.launches = ctx->launches - launches_before;
     ctx->pending.push_back(pe);
+    start = stop = nullptr;  // owned by the context now
+}
+StageTimer::~StageTimer() {
+    if (start) cudaEventDestroy(start);
+    if (stop) cudaEventDestroy(stop);
 }
 int profile_collect(bpk_ctx* ctx) {
     for (auto& pe : ctx->pending) {
@@ -63,6 +68,11 @@ int profile_collect(bpk_ctx* ctx) {
 }
 
 // ---- IMAD throughput probe ---------------------------------------------------------------------
+// (hi:lo) += a * b: the mad.lo.cc / madc.hi pair that ptxas fuses into one IMAD.WIDE.U32 Rd, Ra, Rb, Rd
+__device__ __forceinline__ void probe_mad_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    asm("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+
 // mode 0: 8 independent 32x32+64 multiply-adds per iteration (IMAD.WIDE.U32)
 // mode 1: two independent 12-limb carry chains (IMAD.WIDE.U32.X), the shape the Fp multiplier issues
 __global__ void __launch_bounds__(256) imad_probe_kernel(uint64_t* out, uint32_t iters, uint32_t seed, int mode) {
@@ -92,7 +102,7 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(uint64_t* out, uint32_t
         }
         for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
-            for (int i = 0; i < 14; i++) detail::mad_wide(lo[i], hi[i], m[i], b);
+            for (int i = 0; i < 14; i++) probe_mad_wide(lo[i], hi[i], m[i], b);
         }
         uint64_t s = 0;
 #pragma unroll
@@ -154,6 +164,21 @@ static fr_t fr_from_host(const uint64_t v[4]) {
 }  // namespace bpk
 
 using namespace bpk;
+
+// Calls on one context are serialised inside the library (include/bpk.h, "Threading").
+#define BPK_LOCK(ctx) std::lock_guard<std::recursive_mutex> bpk_guard_((ctx)->mutex)
+
+// Fp / Fr limbs that arrive over the ABI must be canonical (< modulus): the kernels' reduction steps assume it
+template <class F>
+static bool limbs_canonical(const uint64_t* v) {
+    constexpr int N = F::N;
+    for (int i = N - 1; i >= 0; i--) {
+        const uint32_t w = (uint32_t)(v[i / 2] >> (32 * (i & 1)));
+        const uint32_t m = F::params::mod(i);
+        if (w != m) return w < m;
+    }
+    return false;  // equal to the modulus
+}
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -234,6 +259,7 @@ extern "C" const char* bpk_last_error(bpk_ctx* ctx) { return ctx ? ctx->last_err
 
 extern "C" int bpk_set_stream(bpk_ctx* ctx, void* s) {
     if (!ctx) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     BPK_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->stream = (cudaStream_t)s;
     return BPK_OK;
@@ -241,17 +267,30 @@ extern "C" int bpk_set_stream(bpk_ctx* ctx, void* s) {
 
 extern "C" int bpk_synchronize(bpk_ctx* ctx) {
     if (!ctx) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     BPK_CUDA(cudaStreamSynchronize(ctx->stream));
     return BPK_OK;
 }
 
 extern "C" int bpk_set_option(bpk_ctx* ctx, const char* key, long value) {
     if (!ctx || !key) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     std::string k(key);
     if (k == "msm.window") ctx->opt_msm_window = value;
     else if (k == "msm.chunk") ctx->opt_msm_chunk = value;
-    else if (k == "msm.fanin") ctx->opt_msm_fanin = value;
-    else if (k == "msm.reduce") ctx->opt_msm_reduce = value;
+    else if (k == "msm.affine_levels") {
+        if (value < -1 || value > 29) return BPK_ERR_INVALID_ARG;
+        ctx->opt_msm_affine_levels = value;
+    } else if (k == "msm.min_pairs") {
+        if (value < 0) return BPK_ERR_INVALID_ARG;
+        ctx->opt_msm_min_pairs = value;
+    } else if (k == "msm.batch") {
+        if (value < 1 || value > 4096) return BPK_ERR_INVALID_ARG;
+        ctx->opt_msm_batch = value;
+    } else if (k == "msm.level_mib") {
+        if (value < 0) return BPK_ERR_INVALID_ARG;
+        ctx->opt_msm_level_mib = value;
+    } else if (k == "msm.tree_top") ctx->opt_msm_tree_top = value;
     else if (k == "msm.lanes") ctx->opt_msm_lanes = value;
     else if (k == "msm.host_slices") ctx->opt_msm_host_slices = value;
     else if (k == "ntt.tile_log2") {
@@ -287,6 +326,7 @@ static int srs_register(bpk_ctx* ctx, affine_t* pts, size_t n, uint64_t* handle_
 
 extern "C" int bpk_srs_load(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n, uint64_t* handle_out) {
     if (!ctx || !handle_out || (n && !points_xyz)) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     BPK_CUDA(cudaSetDevice(ctx->device));
     affine_t* pts = nullptr;
     BPK_CUDA(cudaMalloc(&pts, (n ? n : 1) * sizeof(affine_t)));
@@ -317,6 +357,8 @@ extern "C" int bpk_srs_generate(bpk_ctx* ctx, const uint64_t tau_mont[4], size_t
 extern "C" int bpk_srs_generate_range(bpk_ctx* ctx, const uint64_t tau_mont[4], size_t first, size_t n,
                                       uint64_t* handle_out) {
     if (!ctx || !handle_out || !tau_mont) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
+    if (!limbs_canonical<fr_t>(tau_mont)) return BPK_ERR_INVALID_ARG;
     BPK_CUDA(cudaSetDevice(ctx->device));
     affine_t* pts = nullptr;
     BPK_CUDA(cudaMalloc(&pts, (n ? n : 1) * sizeof(affine_t)));
@@ -331,6 +373,7 @@ extern "C" int bpk_srs_generate_range(bpk_ctx* ctx, const uint64_t tau_mont[4], 
 
 extern "C" int bpk_srs_len(bpk_ctx* ctx, uint64_t handle, size_t* n_out) {
     if (!ctx || !n_out) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     auto it = ctx->srs.find(handle);
     if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
     *n_out = it->second.n;
@@ -339,6 +382,7 @@ extern "C" int bpk_srs_len(bpk_ctx* ctx, uint64_t handle, size_t* n_out) {
 
 extern "C" int bpk_srs_read(bpk_ctx* ctx, uint64_t handle, size_t first, size_t count, uint64_t* out_xyz) {
     if (!ctx || (count && !out_xyz)) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     auto it = ctx->srs.find(handle);
     if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
     if (first > it->second.n || count > it->second.n - first) return BPK_ERR_INVALID_ARG;
@@ -354,8 +398,10 @@ extern "C" int bpk_srs_read(bpk_ctx* ctx, uint64_t handle, size_t first, size_t 
 
 extern "C" int bpk_srs_free(bpk_ctx* ctx, uint64_t handle) {
     if (!ctx) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     auto it = ctx->srs.find(handle);
     if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
     BPK_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(it->second.points);
     ctx->srs.erase(it);
@@ -367,6 +413,7 @@ extern "C" int bpk_srs_free(bpk_ctx* ctx, uint64_t handle) {
 // 2^(c-1) buckets: fewer windows for the same bucket memory, and no Horner doubling chain at the end.
 extern "C" int bpk_srs_precompute(bpk_ctx* ctx, uint64_t handle, unsigned window_bits) {
     if (!ctx) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     auto it = ctx->srs.find(handle);
     if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
     SrsEntry& e = it->second;
@@ -443,6 +490,7 @@ static int msm_host_scalars(bpk_ctx* ctx, const SrsEntry& srs, const uint64_t* s
 extern "C" int bpk_bucket_msm(bpk_ctx* ctx, uint64_t handle, const uint64_t* scalars_mont, size_t n_scalars,
                               size_t b, size_t c, uint64_t out_xyz[18]) {
     if (!ctx || !out_xyz || (n_scalars && !scalars_mont)) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     unsigned rshift = 0;
     BPK_TRY(window_to_shift(b, c, &rshift));
     auto it = ctx->srs.find(handle);
@@ -459,6 +507,7 @@ extern "C" int bpk_msm_g1(bpk_ctx* ctx, uint64_t handle, const uint64_t* scalars
 extern "C" int bpk_msm_g1_points(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n_points,
                                  const uint64_t* scalars_mont, size_t n_scalars, uint64_t out_xyz[18]) {
     if (!ctx || !out_xyz || (n_points && !points_xyz) || (n_scalars && !scalars_mont)) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     size_t n = n_points < n_scalars ? n_points : n_scalars;
     uint64_t h = 0;
     BPK_TRY(bpk_srs_load(ctx, points_xyz, n, &h));
@@ -470,6 +519,7 @@ extern "C" int bpk_msm_g1_points(bpk_ctx* ctx, const uint64_t* points_xyz, size_
 extern "C" int bpk_msm_g1_dev(bpk_ctx* ctx, uint64_t handle, size_t first, const void* d_scalars_mont, size_t n,
                               int normalise, void* d_out_xyz) {
     if (!ctx || !d_out_xyz || (n && !d_scalars_mont)) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     auto it = ctx->srs.find(handle);
     if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
     if (first > it->second.n || n > it->second.n - first) return BPK_ERR_INVALID_ARG;
@@ -481,6 +531,7 @@ extern "C" int bpk_msm_g1_dev(bpk_ctx* ctx, uint64_t handle, size_t first, const
 extern "C" int bpk_msm_g1_from_host(bpk_ctx* ctx, uint64_t handle, size_t first, const uint64_t* scalars_mont,
                                     size_t n, int normalise, void* d_out_xyz) {
     if (!ctx || !d_out_xyz || (n && !scalars_mont)) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     auto it = ctx->srs.find(handle);
     if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
     if (first > it->second.n || n > it->second.n - first) return BPK_ERR_INVALID_ARG;
@@ -494,6 +545,7 @@ extern "C" int bpk_msm_g1_from_host(bpk_ctx* ctx, uint64_t handle, size_t first,
 extern "C" int bpk_msm_g1_dev_batch(bpk_ctx* ctx, uint64_t handle, size_t count, const void* const* d_scalars_mont,
                                     const size_t* first, const size_t* n, int normalise, void* d_out_xyz) {
     if (!ctx || !d_out_xyz || (count && (!d_scalars_mont || !first || !n))) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     auto it = ctx->srs.find(handle);
     if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
     for (size_t i = 0; i < count; i++) {
@@ -543,6 +595,7 @@ extern "C" int bpk_msm_g1_dev_batch(bpk_ctx* ctx, uint64_t handle, size_t count,
 
 extern "C" int bpk_g1_sum(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n, uint64_t out_xyz[18]) {
     if (!ctx || !out_xyz || (n && !points_xyz) || n > (1u << 20)) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     BPK_CUDA(cudaSetDevice(ctx->device));
     uint64_t* d_in;
     BPK_TRY(ws_reserve(ctx, 8, (n ? n : 1) * 18 * sizeof(uint64_t), (void**)&d_in));
@@ -557,6 +610,7 @@ extern "C" int bpk_g1_sum(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n, ui
 
 extern "C" int bpk_g1_sum_dev(bpk_ctx* ctx, const void* d_points_xyz, size_t n, void* d_out_xyz) {
     if (!ctx || !d_out_xyz || (n && !d_points_xyz) || n > (1u << 20)) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     BPK_CUDA(cudaSetDevice(ctx->device));
     return g1_sum_run(ctx, (const uint64_t*)d_points_xyz, n, (uint64_t*)d_out_xyz);
 }
@@ -567,6 +621,8 @@ extern "C" int bpk_g1_sum_dev(bpk_ctx* ctx, const void* d_points_xyz, size_t n, 
 static int ntt_host(bpk_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, size_t batch, bool inverse,
                     const uint64_t* shift) {
     if (!ctx || !in || !out) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
+    if (shift && !limbs_canonical<fr_t>(shift)) return BPK_ERR_INVALID_ARG;
     if (n == 0 || (n & (n - 1)) != 0) return BPK_ERR_NOT_POW2;
     if (n > ((size_t)1 << NTT_MAX_LOG)) return BPK_ERR_TOO_LARGE;
     if (batch == 0) return BPK_OK;
@@ -603,7 +659,8 @@ extern "C" int bpk_coset_intt_fr(bpk_ctx* ctx, const uint64_t* in, uint64_t* out
 extern "C" int bpk_ntt_fr_dev(bpk_ctx* ctx, const void* d_in, void* d_out, size_t n, size_t batch, int flags,
                               const uint64_t* shift_mont) {
     if (!ctx || !d_in || !d_out) return BPK_ERR_INVALID_ARG;
-    if ((flags & 2) && !shift_mont) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
+    if ((flags & 2) && (!shift_mont || !limbs_canonical<fr_t>(shift_mont))) return BPK_ERR_INVALID_ARG;
     BPK_CUDA(cudaSetDevice(ctx->device));
     fr_t sh;
     if (flags & 2) sh = fr_from_host(shift_mont);
@@ -613,6 +670,7 @@ extern "C" int bpk_ntt_fr_dev(bpk_ctx* ctx, const void* d_in, void* d_out, size_
 extern "C" int bpk_poly_mul_fr(bpk_ctx* ctx, const uint64_t* a, size_t la, const uint64_t* b, size_t lb,
                                uint64_t* out) {
     if (!ctx || !a || !b || !out || la == 0 || lb == 0) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     // D = find_next_power_of_two(deg a, deg b) (utils.rs:54-61): smallest power of two >= la + lb - 1
     size_t target = la + lb - 1;
     size_t D = 1;
@@ -634,6 +692,7 @@ extern "C" int bpk_poly_mul_fr(bpk_ctx* ctx, const uint64_t* a, size_t la, const
 
 extern "C" int bpk_poly_mul_fr_dev(bpk_ctx* ctx, const void* d_a, size_t la, const void* d_b, size_t lb, void* d_out) {
     if (!ctx || !d_a || !d_b || !d_out || la == 0 || lb == 0) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     size_t target = la + lb - 1;
     size_t D = 1;
     while (D < target) D <<= 1;
@@ -657,6 +716,7 @@ extern "C" int bpk_poly_mul_fr_dev(bpk_ctx* ctx, const void* d_a, size_t la, con
 // ------------------------------------------------------------------------------------------------
 extern "C" int bpk_dev_alloc(bpk_ctx* ctx, size_t bytes, void** d_out) {
     if (!ctx || !d_out) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     BPK_CUDA(cudaSetDevice(ctx->device));
     *d_out = nullptr;
     bytes = (bytes + 255) / 256 * 256;
@@ -686,6 +746,7 @@ extern "C" int bpk_dev_alloc(bpk_ctx* ctx, size_t bytes, void** d_out) {
 
 extern "C" int bpk_dev_free(bpk_ctx* ctx, void* d_ptr) {
     if (!ctx) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     if (!d_ptr) return BPK_OK;
     auto it = ctx->dev_live.find(d_ptr);
     if (it == ctx->dev_live.end()) return BPK_ERR_INVALID_ARG;  // not from bpk_dev_alloc (or freed twice)
@@ -696,6 +757,7 @@ extern "C" int bpk_dev_free(bpk_ctx* ctx, void* d_ptr) {
 
 extern "C" int bpk_dev_upload(bpk_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
     if (!ctx || (bytes && (!d_dst || !h_src))) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     BPK_CUDA(cudaSetDevice(ctx->device));
     if (bytes) BPK_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return BPK_OK;
@@ -703,6 +765,7 @@ extern "C" int bpk_dev_upload(bpk_ctx* ctx, void* d_dst, const void* h_src, size
 
 extern "C" int bpk_dev_download(bpk_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
     if (!ctx || (bytes && (!h_dst || !d_src))) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     BPK_CUDA(cudaSetDevice(ctx->device));
     if (bytes) BPK_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     BPK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -711,6 +774,7 @@ extern "C" int bpk_dev_download(bpk_ctx* ctx, void* h_dst, const void* d_src, si
 
 extern "C" int bpk_dev_copy(bpk_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
     if (!ctx || (bytes && (!d_dst || !d_src))) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     BPK_CUDA(cudaSetDevice(ctx->device));
     if (bytes) BPK_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return BPK_OK;
@@ -718,6 +782,7 @@ extern "C" int bpk_dev_copy(bpk_ctx* ctx, void* d_dst, const void* d_src, size_t
 
 extern "C" int bpk_dev_zero(bpk_ctx* ctx, void* d_dst, size_t bytes) {
     if (!ctx || (bytes && !d_dst)) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     BPK_CUDA(cudaSetDevice(ctx->device));
     if (bytes) BPK_CUDA(cudaMemsetAsync(d_dst, 0, bytes, ctx->stream));
     return BPK_OK;
@@ -729,6 +794,7 @@ extern "C" int bpk_dev_zero(bpk_ctx* ctx, void* d_dst, size_t bytes) {
 extern "C" int bpk_fr_vec_op(bpk_ctx* ctx, int op, const void* d_a, const void* d_b, const uint64_t* scalar_mont,
                              void* d_out, size_t n) {
     if (!ctx || op < 0 || op > 6 || (n && (!d_a || !d_out))) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     const bool needs_b = op == 0 || op == 1 || op == 2 || op == 4 || op == 6;
     const bool needs_s = op >= 3;
     if (n && ((needs_b && !d_b) || (needs_s && !scalar_mont))) return BPK_ERR_INVALID_ARG;
@@ -740,6 +806,7 @@ extern "C" int bpk_fr_vec_op(bpk_ctx* ctx, int op, const void* d_a, const void* 
 extern "C" int bpk_fr_scale_powers(bpk_ctx* ctx, const void* d_a, const uint64_t g_mont[4], const uint64_t c0_mont[4],
                                    void* d_out, size_t n) {
     if (!ctx || !g_mont || !c0_mont || (n && (!d_a || !d_out))) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     BPK_CUDA(cudaSetDevice(ctx->device));
     return fr_scale_powers(ctx, (const fr_t*)d_a, fr_from_host(g_mont), fr_from_host(c0_mont), (fr_t*)d_out, n);
 }
@@ -747,6 +814,7 @@ extern "C" int bpk_fr_scale_powers(bpk_ctx* ctx, const void* d_a, const uint64_t
 extern "C" int bpk_fr_poly_eval(bpk_ctx* ctx, const void* d_coeffs, size_t n, const uint64_t x_mont[4],
                                 uint64_t out_mont[4]) {
     if (!ctx || !x_mont || !out_mont || (n && !d_coeffs)) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     BPK_CUDA(cudaSetDevice(ctx->device));
     fr_t* d_out;
     BPK_TRY(ws_reserve(ctx, 10, sizeof(fr_t) * 8, (void**)&d_out));
@@ -759,6 +827,7 @@ extern "C" int bpk_fr_poly_eval(bpk_ctx* ctx, const void* d_coeffs, size_t n, co
 extern "C" int bpk_fr_poly_eval_many(bpk_ctx* ctx, size_t count, const void* const* d_coeffs, const size_t* n,
                                      const uint64_t x_mont[4], uint64_t* out_mont) {
     if (!ctx || !x_mont || (count && (!d_coeffs || !n || !out_mont)) || count > 64) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     for (size_t i = 0; i < count; i++)
         if (n[i] && !d_coeffs[i]) return BPK_ERR_INVALID_ARG;
     if (count == 0) return BPK_OK;
@@ -774,12 +843,14 @@ extern "C" int bpk_fr_poly_eval_many(bpk_ctx* ctx, size_t count, const void* con
 extern "C" int bpk_fr_poly_div_linear(bpk_ctx* ctx, const void* d_coeffs, size_t n, const uint64_t root_mont[4],
                                       void* d_quotient) {
     if (!ctx || !root_mont || (n >= 2 && (!d_coeffs || !d_quotient))) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     BPK_CUDA(cudaSetDevice(ctx->device));
     return fr_poly_div_linear(ctx, (const fr_t*)d_coeffs, n, fr_from_host(root_mont), (fr_t*)d_quotient);
 }
 
 extern "C" int bpk_fr_poly_div_vanishing(bpk_ctx* ctx, const void* d_coeffs, size_t len, size_t n, void* d_quotient) {
     if (!ctx || n == 0 || (len > n && (!d_coeffs || !d_quotient))) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     BPK_CUDA(cudaSetDevice(ctx->device));
     return fr_poly_div_vanishing(ctx, (const fr_t*)d_coeffs, len, n, (fr_t*)d_quotient);
 }
@@ -789,6 +860,7 @@ extern "C" int bpk_plonk_grand_product(bpk_ctx* ctx, const void* d_a, const void
                                        const uint64_t gamma[4], const uint64_t k1[4], const uint64_t k2[4], void* d_z) {
     if (!ctx || !d_a || !d_b || !d_c || !d_s1 || !d_s2 || !d_s3 || !beta || !gamma || !k1 || !k2 || !d_z)
         return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     BPK_CUDA(cudaSetDevice(ctx->device));
     return plonk_grand_product(ctx, (const fr_t*)d_a, (const fr_t*)d_b, (const fr_t*)d_c, (const fr_t*)d_s1,
                                (const fr_t*)d_s2, (const fr_t*)d_s3, n, fr_from_host(beta), fr_from_host(gamma),
@@ -801,6 +873,7 @@ extern "C" int bpk_plonk_quotient_evals(bpk_ctx* ctx, const void* d_witness_eval
                                         const uint64_t k1[4], const uint64_t k2[4], const uint64_t* zh_inv_mont,
                                         void* d_out) {
     if (!ctx || !d_witness_evals || !d_circuit_evals || !beta || !gamma || !alpha || !k1 || !k2 || !zh_inv_mont || !d_out) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     if (n == 0 || domain < n || domain / n > 64) return BPK_ERR_INVALID_ARG;
     BPK_CUDA(cudaSetDevice(ctx->device));
     fr_t zh[64];
@@ -847,12 +920,14 @@ extern "C" void bpk_keccak_f1600(uint64_t s[25]) {
 // ------------------------------------------------------------------------------------------------
 extern "C" int bpk_profile_enable(bpk_ctx* ctx, int on) {
     if (!ctx) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     profile_collect(ctx);
     ctx->profiling = on != 0;
     return BPK_OK;
 }
 extern "C" int bpk_profile_reset(bpk_ctx* ctx) {
     if (!ctx) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     profile_collect(ctx);
     ctx->stats.clear();
     ctx->launches = 0;
@@ -860,6 +935,7 @@ extern "C" int bpk_profile_reset(bpk_ctx* ctx) {
 }
 extern "C" int bpk_profile_get(bpk_ctx* ctx, const char* name, double* ms_out, uint64_t* launches_out) {
     if (!ctx || !name) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     profile_collect(ctx);
     auto it = ctx->stats.find(name);
     double ms = 0;
@@ -876,6 +952,7 @@ extern "C" uint64_t bpk_launch_count(bpk_ctx* ctx) { return ctx ? ctx->launches 
 
 extern "C" int bpk_msm_last_plan(bpk_ctx* ctx, unsigned out[4]) {
     if (!ctx || !out) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     out[0] = ctx->last_c;
     out[1] = ctx->last_W;
     out[2] = ctx->last_chunk;
@@ -883,8 +960,34 @@ extern "C" int bpk_msm_last_plan(bpk_ctx* ctx, unsigned out[4]) {
     return BPK_OK;
 }
 
+extern "C" int bpk_msm_last_stats(bpk_ctx* ctx, uint64_t out[6]) {
+    if (!ctx || !out) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    uint64_t st[4];
+    BPK_TRY(msm_read_stats(ctx, st));
+    out[0] = st[0];                 // (bucket, point) entries of the last bucket fill
+    out[1] = st[0] - st[1];         // additions done in affine coordinates (pairwise tree)
+    out[2] = st[1] - st[2];         // additions left to the XYZZ tail
+    out[3] = st[2];                 // non-empty buckets
+    out[4] = ctx->last_levels;      // tree levels launched
+    out[5] = ctx->last_batch;       // additions per shared inversion (upper bound)
+    return BPK_OK;
+}
+
+extern "C" int bpk_srs_table_bytes(bpk_ctx* ctx, uint64_t handle, size_t* bytes_out) {
+    if (!ctx || !bytes_out) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
+    auto it = ctx->srs.find(handle);
+    if (it == ctx->srs.end()) return BPK_ERR_INVALID_ARG;
+    const SrsEntry& e = it->second;
+    *bytes_out = (e.pre_c ? (size_t)e.pre_W : 1) * e.n * sizeof(affine_t);
+    return BPK_OK;
+}
+
 extern "C" int bpk_imad_peak(bpk_ctx* ctx, double* rate, double* seconds) {
     if (!ctx || !rate || !seconds) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
     BPK_CUDA(cudaSetDevice(ctx->device));
     return imad_peak_run(ctx, rate, seconds);
 }

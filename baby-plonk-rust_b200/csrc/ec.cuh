@@ -142,6 +142,48 @@ BPK_HD void xyzz_add(xyzz_t& p, const xyzz_t& q) {
     p.Y = Y3;
 }
 
+// ------------------------------------------------------------------------------------------
+// affine + affine with the slope's denominator inverted OUTSIDE (batched: Montgomery's trick over many
+// independent additions, msm.cu).  prepare() classifies the pair and yields the denominator that has to be
+// inverted (1 where none is needed, so that a batch product is never poisoned); finish() completes the
+// addition from its inverse: 1 M (slope) + 1 S + 1 M, against 8 M + 2 S of the XYZZ mixed addition.
+// All degenerate cases are explicit, as in xyzz_madd: the reference's tests run on SRS where all points coincide.
+// ------------------------------------------------------------------------------------------
+enum : int { AFF_COPY_P = 0, AFF_COPY_Q = 1, AFF_ADD = 2, AFF_DBL = 3, AFF_INF = 4 };
+
+BPK_HD int affine_add_prepare(const affine_t& p, const affine_t& q, fp_t& den) {
+    den = fp_t::one();
+    if (q.is_inf()) return AFF_COPY_P;
+    if (p.is_inf()) return AFF_COPY_Q;
+    fp_t dx = sub(q.x, p.x);
+    if (!dx.is_zero()) {
+        den = dx;
+        return AFF_ADD;
+    }
+    if (p.y != q.y) return AFF_INF;  // opposite points
+    fp_t dy = dbl(p.y);              // same point: slope 3 x^2 / 2 y
+    if (dy.is_zero()) return AFF_INF;  // y == 0 cannot occur on E(Fp) (odd group order); malformed input stays harmless
+    den = dy;
+    return AFF_DBL;
+}
+
+BPK_HD affine_t affine_add_finish(int kind, const affine_t& p, const affine_t& q, const fp_t& den_inv) {
+    if (kind == AFF_COPY_P) return p;
+    if (kind == AFF_COPY_Q) return q;
+    if (kind == AFF_INF) return affine_t::inf();
+    fp_t lam;
+    if (kind == AFF_ADD) {
+        lam = mul(sub(q.y, p.y), den_inv);
+    } else {
+        fp_t xx = sqr(p.x);
+        lam = mul(add(dbl(xx), xx), den_inv);
+    }
+    affine_t r;
+    r.x = sub(sub(sqr(lam), p.x), q.x);
+    r.y = sub(mul(lam, sub(p.x, r.x)), p.y);
+    return r;
+}
+
 BPK_HD affine_t affine_neg(const affine_t& a) {
     affine_t r;
     r.x = a.x;

@@ -13,7 +13,8 @@
 // limbs are accumulated in two separate arrays so that both carry chains stay pair-aligned.
 //
 // Every primitive also has a plain-C host path (carry flag emulated in a thread_local) so that
-// the very same templates are unit-tested on the CPU in the build container (tests/host_ff_test.cu).
+// the very same templates are unit-tested on the CPU in the build container (tests/host/ff_host_check.cpp,
+// driven by tests/test_host_templates.py).
 #pragma once
 #include <cstdint>
 
@@ -169,14 +170,7 @@ struct FrParams {
                                    0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
         return m[i];
     }
-    // reduced-radix form used inside mul(): 9 limbs of 29 bits (261 bits), operand a pre-shifted by 5
-    static constexpr int RB = 29, NL = 9, PRESHIFT = 5;
-    static constexpr uint32_t M0R = 0x1fffffffu;  // -q^-1 mod 2^29
-    BPK_HD static constexpr uint32_t modr(int i) {
-        constexpr uint32_t m[9] = {0x00000001u, 0x1ffffff8u, 0x1f96ffbfu, 0x1b4805ffu, 0x1d80553bu,
-                                   0x0c0404d0u, 0x1520cce7u, 0x0a6533afu, 0x0073eda7u};
-        return m[i];
-    }
+    static constexpr int BITS = 255;  // bit length of q
 };
 
 // fp.rs:70-77 (MODULUS), :80 (INV), :83-90 (R), :93-100 (R2)
@@ -204,15 +198,7 @@ struct FpParams {
                                     0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
         return m[i];
     }
-    // reduced-radix form used inside mul(): 14 limbs of 28 bits (392 bits), operand a pre-shifted by 8
-    static constexpr int RB = 28, NL = 14, PRESHIFT = 8;
-    static constexpr uint32_t M0R = 0x0ffcfffdu;  // -p^-1 mod 2^28
-    BPK_HD static constexpr uint32_t modr(int i) {
-        constexpr uint32_t m[14] = {0x0fffaaabu, 0x0fefffffu, 0x03ffffb9u, 0x0fffeb15u, 0x06241eabu,
-                                    0x0a0f6b0fu, 0x0f6730d2u, 0x0f38512bu, 0x04774b84u, 0x04bacd76u,
-                                    0x0ba7b643u, 0x0e69a4b1u, 0x01ea397fu, 0x0001a011u};
-        return m[i];
-    }
+    static constexpr int BITS = 381;  // bit length of p
 };
 
 // ------------------------------------------------------------------------------------------
@@ -315,41 +301,9 @@ BPK_HD void madc_n_rshift(uint32_t* odd, const uint32_t* a, uint32_t bi) {
     odd[N - 1] = ptx::madc_hi(a[N - 2], bi, 0);
 }
 
-// "split" forms of madc_n_rshift / cmad_mod: the products are formed without addend on the heavy
-// FMA pipe and folded in by an add-with-carry chain on the ALU pipe (IADD3.X), so that the two
-// pipes share the work of a row instead of the FMA pipe doing all of it at half rate.
-template <int N>
-BPK_HD void madc_n_rshift_split(uint32_t* odd, const uint32_t* a, uint32_t bi) {
-    uint32_t pl[N / 2], ph[N / 2];
-#pragma unroll
-    for (int j = 0; j < N; j += 2) mul_wide(pl[j / 2], ph[j / 2], a[j], bi);
-#pragma unroll
-    for (int j = 0; j < N - 2; j += 2) {
-        odd[j] = ptx::addc_cc(pl[j / 2], odd[j + 2]);
-        odd[j + 1] = ptx::addc_cc(ph[j / 2], odd[j + 3]);
-    }
-    odd[N - 2] = ptx::addc_cc(pl[N / 2 - 1], 0);
-    odd[N - 1] = ptx::addc(ph[N / 2 - 1], 0);
-}
-template <class P, int OFF>
-BPK_HD void cmad_mod_split(uint32_t* acc, uint32_t mi) {
-    constexpr int N = P::N;
-    uint32_t pl[N / 2], ph[N / 2];
-#pragma unroll
-    for (int j = 0; j < N; j += 2) mul_wide(pl[j / 2], ph[j / 2], P::mod(j + OFF), mi);
-    acc[0] = ptx::add_cc(acc[0], pl[0]);
-    acc[1] = ptx::addc_cc(acc[1], ph[0]);
-#pragma unroll
-    for (int j = 2; j < N; j += 2) {
-        acc[j] = ptx::addc_cc(acc[j], pl[j / 2]);
-        acc[j + 1] = ptx::addc_cc(acc[j + 1], ph[j / 2]);
-    }
-}
-
 // one row of the interleaved multiply + Montgomery reduction.
 // value = sum even[j] 2^(32j) + sum odd[j] 2^(32(j+1)); on exit even[0] == 0
-// SPLIT: bit 0 -> odd a*b chain on the ALU pipe, bit 1 -> odd m*p chain, bit 2 -> even m*p chain
-template <class P, bool FIRST, int SPLIT = 0>
+template <class P, bool FIRST>
 BPK_HD void mad_n_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t bi) {
     constexpr int N = P::N;
     if (FIRST) {
@@ -357,10 +311,7 @@ BPK_HD void mad_n_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_
         mul_n<N>(even, a, bi);
     } else {
         even[0] = ptx::add_cc(even[0], odd[1]);
-        if (SPLIT & 1)
-            madc_n_rshift_split<N>(odd, a + 1, bi);
-        else
-            madc_n_rshift<N>(odd, a + 1, bi);
+        madc_n_rshift<N>(odd, a + 1, bi);
         cmad_n<N>(even, a, bi);
         odd[N - 1] = ptx::addc(odd[N - 1], 0);
     }
@@ -395,14 +346,8 @@ BPK_HD void mad_n_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_
         return;
     }
     uint32_t mi = even[0] * P::M0;
-    if (SPLIT & 2)
-        cmad_mod_split<P, 1>(odd, mi);
-    else
-        cmad_mod<P, 1>(odd, mi);
-    if (SPLIT & 4)
-        cmad_mod_split<P, 0>(even, mi);
-    else
-        cmad_mod<P, 0>(even, mi);
+    cmad_mod<P, 1>(odd, mi);
+    cmad_mod<P, 0>(even, mi);
     odd[N - 1] = ptx::addc(odd[N - 1], 0);
 }
 
@@ -421,21 +366,21 @@ BPK_HD void final_sub(uint32_t* r) {
 
 }  // namespace detail
 
-// Montgomery product a*b/R mod p, fully reduced -- carry-chained 32-bit-limb version (v1).
-// Kept as the cross-check of mul(); every IMAD.WIDE.U32.X it issues occupies the heavy FMA pipe for
-// two slots on sm_100 (measured, profiles/r1_v1_msm_accumulate_ncu.md), which is why mul() below
-// does not use carry flags on the multiplier pipe.
-template <class P, int SPLIT = 0>
+// Montgomery product a*b/R mod p, fully reduced; scalar.rs:562-586, fp.rs:565-609.  Two interleaved carry chains of
+// IMAD.WIDE.U32.X (even / odd limb products), one Montgomery row per limb of b.  On sm_100 every form of IMAD.WIDE
+// retires at 32 / clk / SM; a reduced-radix multiplier without carries and variants that moved chains to the ALU
+// pipe were built, verified and measured slower (profiles/r1_imad_forms.md) -- this is the form that stayed.
+template <class P>
 BPK_HD Fe<P> mul_cc(const Fe<P>& a, const Fe<P>& b) {
     constexpr int N = P::N;
     uint32_t even[N], odd[N];
 #pragma unroll
     for (int i = 0; i < N; i += 2) {
         if (i == 0)
-            detail::mad_n_redc<P, true, SPLIT>(even, odd, a.l, b.l[0]);
+            detail::mad_n_redc<P, true>(even, odd, a.l, b.l[0]);
         else
-            detail::mad_n_redc<P, false, SPLIT>(even, odd, a.l, b.l[i]);
-        detail::mad_n_redc<P, false, SPLIT>(odd, even, a.l, b.l[i + 1]);
+            detail::mad_n_redc<P, false>(even, odd, a.l, b.l[i]);
+        detail::mad_n_redc<P, false>(odd, even, a.l, b.l[i + 1]);
     }
     // merge: r[j] = even[j] + odd[j+1]
     Fe<P> r;
@@ -566,120 +511,17 @@ BPK_HD Fe<P> sqr_cc(const Fe<P>& a) {
     return r;
 }
 
-namespace detail {
-// (hi:lo) += a * b, 32 x 32 -> 64 multiply-add on a 64-bit accumulator held in two registers.
-// The mad.lo.cc / madc.hi pair is what ptxas fuses into ONE plain IMAD.WIDE.U32 Rd, Ra, Rb, Rd; a
-// `mad.wide.u32` with a 64-bit addend is instead split by ptxas into IMAD.WIDE(.., RZ) + IADD3 + IADD3.X.
-BPK_HD void mad_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
-#if defined(__CUDA_ARCH__)
-    asm("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
-#else
-    uint64_t t = (((uint64_t)hi << 32) | lo) + (uint64_t)a * b;
-    lo = (uint32_t)t;
-    hi = (uint32_t)(t >> 32);
-#endif
-}
-// limb k (RB bits) of the integer (x << SH), x given as N 32-bit words
-template <class P, int SH>
-BPK_HD uint32_t rr_limb(const uint32_t* x, int k) {
-    constexpr int N = P::N, RB = P::RB;
-    constexpr uint32_t MASK = (1u << RB) - 1;
-    const int s = RB * k - SH;
-    if (s < 0) return (x[0] << (-s)) & MASK;
-    const int w = s >> 5, off = s & 31;
-    if (w >= N) return 0;
-    uint32_t lo = x[w];
-    uint32_t hi = (w + 1 < N) ? x[w + 1] : 0u;
-    uint32_t v = off ? ((lo >> off) | (hi << (32 - off))) : lo;
-    return v & MASK;
-}
-}  // namespace detail
-
-// Montgomery product a*b/R mod p (R = 2^(32 N)), fully reduced; scalar.rs:562-586, fp.rs:565-609.
-//
-// Reduced-radix formulation for the sm_100 multiplier pipe: the operands are re-sliced into NL limbs
-// of RB bits (Fp: 14 x 28, Fr: 9 x 29) and every partial product a_j b_i and m_i p_j is accumulated
-// into a 64-bit column with a plain IMAD.WIDE.U32 -- 2 NL products of < 2^(2 RB) never overflow 64
-// bits, so the multiplier pipe sees no carry flags at all (a carry-in IMAD.WIDE.U32.X costs two pipe
-// slots).  One row retires RB bits: m_i = t0 * (-p^-1) mod 2^RB, t += m_i p, t >>= RB.  NL rows divide by
-// 2^(RB NL); operand a enters pre-shifted by RB NL - 32 N bits, so the result is exactly a b / 2^(32 N):
-// the Montgomery domain is the reference's.  Column carries, re-slicing and the final conditional
-// subtraction run on the ALU pipe, which is otherwise idle.
-template <class P>
-BPK_HD Fe<P> mul_rr(const Fe<P>& a, const Fe<P>& b) {
-    constexpr int N = P::N, NL = P::NL, RB = P::RB;
-    constexpr uint32_t MASK = (1u << RB) - 1;
-    uint32_t A[NL];
-#pragma unroll
-    for (int k = 0; k < NL; k++) A[k] = detail::rr_limb<P, P::PRESHIFT>(a.l, k);
-    uint32_t tl[NL + 1], th[NL + 1];  // 64-bit columns as (lo, hi) register pairs
-#pragma unroll
-    for (int k = 0; k <= NL; k++) tl[k] = th[k] = 0;
-#pragma unroll
-    for (int i = 0; i < NL; i++) {
-        const uint32_t bi = detail::rr_limb<P, 0>(b.l, i);
-#pragma unroll
-        for (int j = 0; j < NL; j++) detail::mad_wide(tl[j], th[j], A[j], bi);
-        const uint32_t m = (tl[0] * P::M0R) & MASK;
-#pragma unroll
-        for (int j = 0; j < NL; j++) detail::mad_wide(tl[j], th[j], m, P::modr(j));
-        // column 0 is now a multiple of 2^RB: retire it, carry into column 1, slide the window
-        const uint32_t cl = (tl[0] >> RB) | (th[0] << (32 - RB));
-        const uint32_t ch = th[0] >> RB;
-        tl[0] = ptx::add_cc(tl[1], cl);
-        th[0] = ptx::addc(th[1], ch);
-#pragma unroll
-        for (int j = 1; j < NL; j++) {
-            tl[j] = tl[j + 1];
-            th[j] = th[j + 1];
-        }
-        tl[NL] = th[NL] = 0;
-    }
-    // carry-normalise the NL columns to RB-bit limbs
-    uint32_t L[NL + 1];
-    uint32_t cl = 0, ch = 0;
-#pragma unroll
-    for (int j = 0; j < NL; j++) {
-        uint32_t vl = ptx::add_cc(tl[j], cl);
-        uint32_t vh = ptx::addc(th[j], ch);
-        L[j] = vl & MASK;
-        cl = (vl >> RB) | (vh << (32 - RB));
-        ch = vh >> RB;
-    }
-    L[NL] = cl;  // 0 for reduced inputs (result < 2p < 2^(RB NL))
-    // re-slice to 32-bit words
-    Fe<P> r;
-#pragma unroll
-    for (int j = 0; j < N; j++) {
-        const int bit = 32 * j;
-        const int k = bit / RB, off = bit % RB;
-        uint32_t v = L[k] >> off;
-        if (k + 1 <= NL) v |= L[k + 1] << (RB - off);
-        if (2 * RB - off < 32 && k + 2 <= NL) v |= L[k + 2] << (2 * RB - off);
-        r.l[j] = v;
-    }
-    detail::final_sub<P>(r.l);
-    return r;
-}
-
-// The product the kernels use.  BPK_MUL_IMPL: 0 = carry chains only (v1), 1 = reduced radix,
-// 2.. = carry chains with SPLIT = BPK_MUL_IMPL - 2 (some chains moved to the ALU pipe).
-#ifndef BPK_MUL_IMPL
-#define BPK_MUL_IMPL 0
-#endif
 #if defined(__CUDACC__) && defined(BPK_FP_MUL_CALL)
 // Out-of-line Fp product: a kernel whose hot loop inlines ten ~450-instruction multiplications (the MSM
 // accumulate loop is ~75 KB of SASS) overflows the instruction caches; calling one shared body keeps the
 // loop resident at the price of a register-passing call per product.
-template <class P, int SPLIT>
-BPK_HD Fe<P> mul_cc(const Fe<P>& a, const Fe<P>& b);
 static __device__ __noinline__ Fe<FpParams> fp_mul_call(Fe<FpParams> a, Fe<FpParams> b) {
-    return mul_cc<FpParams, 0>(a, b);
+    return mul_cc<FpParams>(a, b);
 }
 static __device__ __noinline__ Fe<FpParams> fp_sqr_call(Fe<FpParams> a) { return sqr_cc<FpParams>(a); }
 template <class P>
 struct MulCall {
-    static __device__ __forceinline__ Fe<P> run(const Fe<P>& a, const Fe<P>& b) { return mul_cc<P, 0>(a, b); }
+    static __device__ __forceinline__ Fe<P> run(const Fe<P>& a, const Fe<P>& b) { return mul_cc<P>(a, b); }
 };
 template <>
 struct MulCall<FpParams> {
@@ -693,13 +535,8 @@ template <class P>
 BPK_HD Fe<P> mul(const Fe<P>& a, const Fe<P>& b) {
 #if defined(__CUDA_ARCH__) && defined(BPK_FP_MUL_CALL)
     return MulCall<P>::run(a, b);
-#endif
-#if BPK_MUL_IMPL == 1
-    return mul_rr<P>(a, b);
-#elif BPK_MUL_IMPL >= 2
-    return mul_cc<P, BPK_MUL_IMPL - 2>(a, b);
 #else
-    return mul_cc<P, 0>(a, b);
+    return mul_cc<P>(a, b);
 #endif
 }
 
@@ -777,103 +614,169 @@ BPK_HD Fe<P> to_mont(const Fe<P>& a) {
     return mul(a, Fe<P>::r2());
 }
 
-// a^(p-2): field inversion by Fermat (fp.rs:346-358); 0 -> 0.  Kept as the cross-check of inv().
+// ------------------------------------------------------------------------------------------
+// Field inversion, 0 -> 0 (same VALUE as fp.rs:346-358 / scalar.rs:416-511, which exponentiate).
+//
+// Bernstein-Yang division steps ("safegcd", the delta = 1 form) on signed 30-bit limbs: 30 steps at a time are run
+// on the low words of (f, g) alone and collected in a 2x2 transition matrix, which is then applied to the full
+// (f, g) -- an exact division by 2^30 -- and to (d, e) modulo p.  No multiplications by field elements, no
+// data-dependent branches inside a round: every lane of a warp runs the same instruction stream, which is what
+// lets each MSM thread invert its own batch product (msm.cu, batched-affine additions) -- ~20 k mostly-ALU
+// instructions against ~170 k wide multiply-adds for Fermat's a^(p-2), and the ALU pipe is the idle one there.
+// Termination: floor((49 BITS + 57) / 17) steps suffice for BITS >= 46 (Bernstein-Yang 2019, Thm 11.2); the round
+// loop also leaves as soon as g == 0, and the bound holds for ANY limbs, so malformed input cannot hang a thread.
+// ------------------------------------------------------------------------------------------
+namespace detail {
 template <class P>
-BPK_HD Fe<P> inv_fermat(const Fe<P>& a) {
-    constexpr int N = P::N;
-    Fe<P> r = Fe<P>::one();
-    // exponent p - 2, limb by limb with borrow (Fr's low limb is 1)
-    uint32_t ex[N];
-    uint32_t borrow = 2;
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        uint32_t m = P::mod(i);
-        ex[i] = m - borrow;
-        borrow = (m < borrow) ? 1u : 0u;
+struct SafeGcd {
+    static constexpr int N = P::N;
+    static constexpr int NL = (P::BITS + 2 + 29) / 30;                       // values stay in (-2p, p)
+    static constexpr int ROUNDS = ((49 * P::BITS + 57) / 17 + 29) / 30;      // Fp: 37 x 30 >= 1101, Fr: 25 x 30 >= 738
+    static constexpr int32_t M30 = (int32_t)0x3fffffff;
+    // bits [30 i, 30 i + 30) of an N-word integer
+    BPK_HD static constexpr uint32_t limb30(const uint32_t* x, int i) {
+        const int bit = 30 * i, w = bit >> 5, off = bit & 31;
+        if (w >= N) return 0;
+        uint32_t v = x[w] >> off;
+        if (off > 2 && w + 1 < N) v |= x[w + 1] << (32 - off);
+        return v & 0x3fffffffu;
     }
-#pragma unroll 1
-    for (int i = N - 1; i >= 0; i--) {
-        uint32_t e = ex[i];
-#pragma unroll 1
-        for (int b = 31; b >= 0; b--) {
-            r = sqr(r);
-            if ((e >> b) & 1u) r = mul(r, a);
-        }
+    BPK_HD static constexpr uint32_t mod30(int i) {
+        const int bit = 30 * i, w = bit >> 5, off = bit & 31;
+        if (w >= N) return 0;
+        uint32_t v = P::mod(w) >> off;
+        if (off > 2 && w + 1 < N) v |= P::mod(w + 1) << (32 - off);
+        return v & 0x3fffffffu;
     }
-    return r;
-}
+    // p^-1 mod 2^30 by Newton iteration (p odd)
+    BPK_HD static constexpr uint32_t mod_inv30() {
+        uint32_t p0 = P::mod(0), x = p0;  // correct to 3 bits
+        for (int i = 0; i < 5; i++) x *= 2u - p0 * x;
+        return x & 0x3fffffffu;
+    }
+};
+}  // namespace detail
 
-// Field inversion, 0 -> 0 (same value as fp.rs:346-358 / scalar.rs:416-511, which exponentiate).
-// Binary extended Euclid on the raw limbs: ~2 * bits iterations of shifts and add/sub chains, no
-// multiplications -- about 6x shorter than the 570 dependent Montgomery multiplications of Fermat's
-// method when a single thread has to normalise an MSM result (msm_finalize_kernel).
 template <class P>
 BPK_HD Fe<P> inv(const Fe<P>& a) {
-    constexpr int N = P::N;
-    if (a.is_zero()) return a;
-    uint32_t u[N], v[N];
-    Fe<P> x1 = Fe<P>::zero(), x2 = Fe<P>::zero();
-    x1.l[0] = 1;
+    typedef detail::SafeGcd<P> S;
+    constexpr int N = P::N, NL = S::NL;
+    constexpr int32_t M30 = S::M30;
+    int32_t f[NL], g[NL], d[NL], e[NL];
 #pragma unroll
-    for (int i = 0; i < N; i++) {
-        u[i] = a.l[i];
-        v[i] = P::mod(i);
+    for (int i = 0; i < NL; i++) {
+        f[i] = (int32_t)S::mod30(i);
+        g[i] = (int32_t)S::limb30(a.l, i);
+        d[i] = 0;
+        e[i] = 0;
     }
-    // x <- x / 2 mod p
-    auto halve = [](Fe<P>& x) {
-        uint32_t c = 0;
-        if (x.l[0] & 1u) {
-            x.l[0] = ptx::add_cc(x.l[0], P::mod(0));
+    e[0] = 1;
+    int32_t eta = -1;  // eta = -delta
+#pragma unroll 1
+    for (int round = 0; round < S::ROUNDS; round++) {
+        int32_t nz = 0;
 #pragma unroll
-            for (int i = 1; i < N; i++) x.l[i] = ptx::addc_cc(x.l[i], P::mod(i));
-            c = ptx::addc(0u, 0u);
+        for (int i = 0; i < NL; i++) nz |= g[i];
+        if (nz == 0) break;
+        // 30 division steps on the low words; 2^30 [f', g'] = [[u, v], [q, r]] [f, g]
+        uint32_t u = 1, v = 0, q = 0, r = 1;
+        uint32_t fl = (uint32_t)f[0], gl = (uint32_t)g[0];
+#pragma unroll 2
+        for (int i = 0; i < 30; i++) {
+            uint32_t c1 = (uint32_t)(eta >> 31);  // delta > 0
+            const uint32_t c2 = 0u - (gl & 1u);   // g odd
+            const uint32_t x = (fl ^ c1) - c1, y = (u ^ c1) - c1, z = (v ^ c1) - c1;  // -(f, u, v) if delta > 0
+            gl += x & c2;
+            q += y & c2;
+            r += z & c2;
+            c1 &= c2;                                   // swap case: delta > 0 and g odd
+            eta = (int32_t)(((uint32_t)eta ^ c1) - (c1 + 1u));  // -eta - 1 there, eta - 1 otherwise
+            fl += gl & c1;
+            u += q & c1;
+            v += r & c1;
+            gl >>= 1;
+            u <<= 1;
+            v <<= 1;
+        }
+        // 32 x 32 -> 64 signed products (mul.wide.s32): both factors are sign-extended 32-bit values
+        const int32_t iu = (int32_t)u, iv = (int32_t)v, iq = (int32_t)q, ir = (int32_t)r;
+#define BPK_MW(a, b) ((int64_t)(a) * (int64_t)(b))
+        {   // (d, e) <- [[u, v], [q, r]] (d, e) / 2^30 mod p, values kept in (-2p, p)
+            const int32_t sd = d[NL - 1] >> 31, se = e[NL - 1] >> 31;
+            int32_t md = ((int32_t)u & sd) + ((int32_t)v & se);
+            int32_t me = ((int32_t)q & sd) + ((int32_t)r & se);
+            int64_t cd = BPK_MW(iu, d[0]) + BPK_MW(iv, e[0]);
+            int64_t ce = BPK_MW(iq, d[0]) + BPK_MW(ir, e[0]);
+            md -= (int32_t)((S::mod_inv30() * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+            me -= (int32_t)((S::mod_inv30() * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+            cd += BPK_MW((int32_t)S::mod30(0), md);
+            ce += BPK_MW((int32_t)S::mod30(0), me);
+            cd >>= 30;
+            ce >>= 30;
+#pragma unroll
+            for (int i = 1; i < NL; i++) {
+                cd += BPK_MW(iu, d[i]) + BPK_MW(iv, e[i]) + BPK_MW((int32_t)S::mod30(i), md);
+                ce += BPK_MW(iq, d[i]) + BPK_MW(ir, e[i]) + BPK_MW((int32_t)S::mod30(i), me);
+                d[i - 1] = (int32_t)cd & M30;
+                e[i - 1] = (int32_t)ce & M30;
+                cd >>= 30;
+                ce >>= 30;
+            }
+            d[NL - 1] = (int32_t)cd;
+            e[NL - 1] = (int32_t)ce;
+        }
+        {   // (f, g) <- [[u, v], [q, r]] (f, g) / 2^30 (exact)
+            int64_t cf = BPK_MW(iu, f[0]) + BPK_MW(iv, g[0]);
+            int64_t cg = BPK_MW(iq, f[0]) + BPK_MW(ir, g[0]);
+            cf >>= 30;
+            cg >>= 30;
+#pragma unroll
+            for (int i = 1; i < NL; i++) {
+                cf += BPK_MW(iu, f[i]) + BPK_MW(iv, g[i]);
+                cg += BPK_MW(iq, f[i]) + BPK_MW(ir, g[i]);
+                f[i - 1] = (int32_t)cf & M30;
+                g[i - 1] = (int32_t)cg & M30;
+                cf >>= 30;
+                cg >>= 30;
+            }
+            f[NL - 1] = (int32_t)cf;
+            g[NL - 1] = (int32_t)cg;
+        }
+#undef BPK_MW
+    }
+    // f = +-1 (gcd of p and a non-zero a); a^-1 = sign(f) d, brought from (-2p, p) to [0, p)
+    {
+        int32_t add = d[NL - 1] >> 31;
+        const int32_t negate = f[NL - 1] >> 31;
+#pragma unroll
+        for (int i = 0; i < NL; i++) {
+            d[i] += (int32_t)S::mod30(i) & add;
+            d[i] = (d[i] ^ negate) - negate;
         }
 #pragma unroll
-        for (int i = 0; i < N - 1; i++) x.l[i] = (x.l[i] >> 1) | (x.l[i + 1] << 31);
-        x.l[N - 1] = (x.l[N - 1] >> 1) | (c << 31);
-    };
-    auto shr1 = [](uint32_t* w) {
-#pragma unroll
-        for (int i = 0; i < N - 1; i++) w[i] = (w[i] >> 1) | (w[i + 1] << 31);
-        w[N - 1] >>= 1;
-    };
-    auto is_one = [](const uint32_t* w) {
-        uint32_t acc = w[0] ^ 1u;
-#pragma unroll
-        for (int i = 1; i < N; i++) acc |= w[i];
-        return acc == 0;
-    };
-#pragma unroll 1
-    while (!is_one(u) && !is_one(v)) {
-#pragma unroll 1
-        while ((u[0] & 1u) == 0) {
-            shr1(u);
-            halve(x1);
+        for (int i = 0; i < NL - 1; i++) {
+            d[i + 1] += d[i] >> 30;
+            d[i] &= M30;
         }
-#pragma unroll 1
-        while ((v[0] & 1u) == 0) {
-            shr1(v);
-            halve(x2);
-        }
-        uint32_t t[N];
-        t[0] = ptx::sub_cc(u[0], v[0]);
+        add = d[NL - 1] >> 31;
 #pragma unroll
-        for (int i = 1; i < N; i++) t[i] = ptx::subc_cc(u[i], v[i]);
-        uint32_t borrow = ptx::subc(0u, 0u);
-        if (borrow == 0) {  // u >= v
+        for (int i = 0; i < NL; i++) d[i] += (int32_t)S::mod30(i) & add;
 #pragma unroll
-            for (int i = 0; i < N; i++) u[i] = t[i];
-            x1 = sub(x1, x2);
-        } else {
-            v[0] = ptx::sub_cc(v[0], u[0]);
-#pragma unroll
-            for (int i = 1; i < N - 1; i++) v[i] = ptx::subc_cc(v[i], u[i]);
-            v[N - 1] = ptx::subc(v[N - 1], u[N - 1]);
-            x2 = sub(x2, x1);
+        for (int i = 0; i < NL - 1; i++) {
+            d[i + 1] += d[i] >> 30;
+            d[i] &= M30;
         }
     }
-    Fe<P> t = is_one(u) ? x1 : x2;  // (a as a plain integer)^-1 = (value R)^-1
-    // value^-1 R = t R^2: two Montgomery multiplications by R^2
+    Fe<P> t;  // re-slice the 30-bit limbs into 32-bit words
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const int bit = 32 * j, k = bit / 30, off = bit % 30;
+        uint32_t w = (uint32_t)d[k] >> off;
+        if (k + 1 < NL) w |= (uint32_t)d[k + 1] << (30 - off);
+        if (60 - off < 32 && k + 2 < NL) w |= (uint32_t)d[k + 2] << (60 - off);
+        t.l[j] = w;
+    }
+    // t = (a as a plain integer)^-1 = (value R)^-1; value^-1 R = t R^2: two Montgomery multiplications by R^2
     return mul(mul(t, Fe<P>::r2()), Fe<P>::r2());
 }
 

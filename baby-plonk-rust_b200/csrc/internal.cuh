@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -17,7 +18,7 @@ constexpr int NTT_MAX_LOG = 28;   // largest transform: 2^28 elements (8 GiB)
 constexpr int TW_LO_BITS = 13;    // two-level twiddle table split
 constexpr int TW_HI_BITS = NTT_MAX_LOG - TW_LO_BITS;
 constexpr int MSM_LANES = 3;      // concurrent MSMs of bpk_msm_g1_dev_batch (one stream + one workspace bank each)
-constexpr int WS_SLOTS = 16;      // workspace slots per bank
+constexpr int WS_SLOTS = 24;      // workspace slots per bank
 
 struct DeviceBuffer {
     void* ptr = nullptr;
@@ -54,6 +55,9 @@ struct PendingEvent {
 }  // namespace bpk
 
 struct bpk_ctx {
+    // every extern "C" entry point holds this for its whole duration: calls on one context from several threads
+    // (cargo test runs the reference's tests in parallel) are serialised here, not by the caller
+    std::recursive_mutex mutex;
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
@@ -94,10 +98,13 @@ struct bpk_ctx {
     // options
     long opt_msm_window = 0;
     long opt_msm_chunk = 0;
-    long opt_msm_fanin = 8;
     long opt_msm_lanes = bpk::MSM_LANES;  // 1: bpk_msm_g1_dev_batch runs its MSMs one after the other
     long opt_msm_host_slices = 1;  // 0: upload all scalars before the MSM starts
-    long opt_msm_reduce = 0;  // 0: bit-plane reduction, 1: fan-in running-sum tree (kept for A/B runs)
+    long opt_msm_affine_levels = -1;  // levels of the batched-affine pairwise tree (-1: from the expected bucket load, 0: XYZZ only)
+    long opt_msm_min_pairs = 1 << 16;  // a tree level expected to hold fewer pairs is left to the XYZZ tail
+    long opt_msm_batch = 256;          // additions that share one inversion (per thread)
+    long opt_msm_level_mib = 48 << 10; // budget of the tree's level buffers
+    long opt_msm_tree_top = 1;         // narrow top of the bucket-reduction tree in one block
     long opt_ntt_tile_log2 = 10;  // R x C elements per CTA tile (32 KiB): best of the sweep in profiles/
     long opt_ntt_max_radix_log2 = 0;  // 0 = auto
     long opt_ntt_threads = 0;
@@ -106,7 +113,8 @@ struct bpk_ctx {
     long opt_imad_mode = 0;
 
     // plan of the most recent MSM (window bits, windows, pairs per accumulate thread, buckets)
-    unsigned last_c = 0, last_W = 0, last_chunk = 0, last_buckets = 0;
+    unsigned last_c = 0, last_W = 0, last_chunk = 0, last_buckets = 0, last_levels = 0, last_batch = 0;
+    unsigned long long* last_stats_dev = nullptr;  // counters of the most recent bucket fill (device)
 
     // instrumentation
     bool profiling = false;
@@ -134,13 +142,17 @@ int cuda_fail(bpk_ctx* ctx, cudaError_t e, const char* what, const char* file, i
 // grow-only device workspace slot
 int ws_reserve(bpk_ctx* ctx, int slot, size_t bytes, void** out);
 
-// stage instrumentation: RAII-less begin/end because kernels are launched in between
+// stage instrumentation: end() hands the event pair to the context; a timer that goes out of scope without end()
+// (an error return between the two) destroys its events
 struct StageTimer {
     bpk_ctx* ctx;
     const char* name;
     uint64_t launches_before;
     cudaEvent_t start = nullptr, stop = nullptr;
     StageTimer(bpk_ctx* c, const char* n);
+    ~StageTimer();
+    StageTimer(const StageTimer&) = delete;
+    StageTimer& operator=(const StageTimer&) = delete;
     void end();
 };
 int profile_collect(bpk_ctx* ctx);
@@ -174,6 +186,7 @@ int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n,
 int msm_run_from_host(bpk_ctx* ctx, const MsmPoints& pts, const uint64_t* h_scalars, fr_t* d_stage, size_t n,
                       unsigned rshift, bool normalise, uint64_t* d_out_xyz);
 int g1_sum_run(bpk_ctx* ctx, const uint64_t* d_points_xyz, size_t n, uint64_t* d_out_xyz);
+int msm_read_stats(bpk_ctx* ctx, uint64_t out[4]);
 
 // ---- srs.cu ----
 int srs_from_projective(bpk_ctx* ctx, const uint64_t* d_xyz, size_t n, affine_t* d_out);

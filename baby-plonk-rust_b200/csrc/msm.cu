@@ -4,30 +4,37 @@
 // affine image of the result (G1Affine::from, g1.rs:49-63).  The reference walks 64 4-bit windows
 // serially with complete projective additions; nothing of that structure is kept:
 //
-//   K1 recode      scalar: Montgomery -> canonical (scalar.rs:292-304 semantics), signed c-bit digits;
-//                  one (bucket key, point index | sign) pair per (scalar, window)
-//   K2 sort        radix sort of the pairs by bucket key  (replaces the serial scatter, msm.rs:29-35)
-//   K3 accumulate  equal-size chunks of the sorted pair list, one thread per chunk, XYZZ += affine;
-//                  a bucket whose run lies inside one chunk is written directly, runs that cross chunk
-//                  borders leave partial sums that K3b merges -> load balance is independent of the
-//                  scalar distribution
-//   K4 reduce      sum_b (b+1) B_b per window by a tree of running sums (msm.rs:42-46 is the serial form)
-//   K5 finalize    Horner over windows (msm.rs:107-115), affine normalisation, G1Projective limbs out
+//   K1 count       scalar: Montgomery -> canonical (scalar.rs:292-304 semantics), signed c-bit digits; histogram
+//                  of the bucket keys (warp-aggregated reductions in L2)
+//   K2 layout      one scan over the buckets lays out EVERY level of the pairwise tree below: bucket b holds
+//                  ceil(c_b / 2^l) entries at level l, padded to an even count
+//   K3 scatter     the digits again, each (bucket, point | sign) pair placed at its bucket's cursor: a counting
+//                  sort fused with the recoding (replaces the serial scatter, msm.rs:29-35)
+//   K4 affine tree level l adds the entries 2j, 2j+1 of every bucket in AFFINE coordinates -- all additions of a
+//                  level are independent, so each thread shares ONE field inversion over a batch of them
+//                  (Montgomery's trick; per-thread division-step inversion, ff.cuh): 5 M + 1 S per addition instead
+//                  of the 8 M + 2 S of XYZZ += affine.  A bucket that is down to one entry is written out.
+//   K5 tail        whatever the affine levels leave (heavy buckets of skewed scalars, or everything for tiny inputs)
+//                  goes through equal-size chunks of the sorted list in XYZZ coordinates, one thread per chunk;
+//                  runs that cross chunk borders leave partial sums that three merge kernels fold -> load balance
+//                  is independent of the scalar distribution
+//   K6 reduce      sum_b (b+1) B_b by bit planes over one pairwise tree (msm.rs:42-46 is the serial form)
+//   K7 finalize    Horner over planes / windows (msm.rs:107-115), affine normalisation, G1Projective limbs out
 //
-// Roofline: integer multiply pipe.  Algorithmic work per accumulated pair: one mixed addition
-// = 8 M + 2 S in Fp, each 300 32x32->64 products; HBM traffic per pair is 8 B of
-// sorted pair + 96 B point gather -- two orders of magnitude below the arithmetic time.
-#include <cub/device/device_radix_sort.cuh>
+// Roofline: integer multiply pipe.  Algorithmic work per accumulated pair (SURVEY.md 8d): one mixed addition
+// = 8 M + 2 S in Fp, each 300 32x32->64 products; executed: 5 M + 1 S.  HBM: 8 B of sorted pair + 96 B point gather
+// per pair and pass at level 0, 192 B in + 96 B out per addition above, 96 B of prefix-product scratch.
 
-// One shared out-of-line body for the Fp product: the accumulate loop otherwise inlines ten ~450-instruction
-// multiplications (~75 KB of SASS) and stalls on instruction fetch (14 % "no_instructions" samples in
-// profiles/r1_final_msm_accumulate_ncu.md); measured 79.9 -> 77.3 ms at 2^24.
+// One shared out-of-line body for the Fp product: the addition loops otherwise inline ~450-instruction
+// multiplications many times over and stall on instruction fetch (14 % "no_instructions" samples in
+// profiles/r1_final_msm_accumulate_ncu.md); measured 79.9 -> 77.3 ms at 2^24 in round 1.
 #define BPK_FP_MUL_CALL 1
 #include "internal.cuh"
 
 namespace bpk {
 
 static constexpr uint32_t INVALID_KEY = 0xffffffffu;
+static constexpr int MSM_MAX_LEVELS = 29;  // affine levels the layout tables can describe (2^29 entries per bucket)
 
 __device__ __forceinline__ fp_t ld_fp(const fp_t* p) {
     const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -49,6 +56,10 @@ __device__ __forceinline__ affine_t ld_affine(const affine_t* p) {
     r.x = ld_fp(&p->x);
     r.y = ld_fp(&p->y);
     return r;
+}
+__device__ __forceinline__ void st_affine(affine_t* p, const affine_t& v) {
+    st_fp(&p->x, v.x);
+    st_fp(&p->y, v.y);
 }
 __device__ __forceinline__ xyzz_t ld_xyzz(const xyzz_t* p) {
     xyzz_t r;
@@ -74,24 +85,24 @@ __device__ __forceinline__ fr_t ld_fr_g(const fr_t* p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: signed-digit recoding
+// K1 / K3: signed-digit recoding, shared by the counting and the scattering pass
 // ------------------------------------------------------------------------------------------
 // key_stride: buckets per window (2^(c-1)) for per-window bucket sets, 0 when every window shares one
 // bucket set (precomputed SRS levels); val_stride: distance between precomputed levels in points, else 0.
-__global__ void __launch_bounds__(256) msm_recode_kernel(const fr_t* __restrict__ scalars, uint32_t n, uint32_t c,
-                                                          uint32_t W, uint32_t rshift, uint32_t key_stride,
-                                                          uint32_t val_stride, uint32_t* __restrict__ keys,
-                                                          uint32_t* __restrict__ vals) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    fr_t s = from_mont(ld_fr_g(scalars + i));  // canonical integer < q
-    uint32_t l[10];
+struct RecodeArgs {
+    const fr_t* scalars;
+    uint32_t n, c, W, rshift, key_stride, val_stride;
+};
+
+// canonical integer (value >> rshift) of scalar i as 10 limbs (two of padding for the window reads)
+__device__ __forceinline__ void recode_limbs(const RecodeArgs& a, uint32_t i, uint32_t l[10]) {
+    fr_t s = from_mont(ld_fr_g(a.scalars + i));  // canonical integer < q
 #pragma unroll
     for (int k = 0; k < 8; k++) l[k] = s.l[k];
     l[8] = 0;
     l[9] = 0;
-    if (rshift) {  // value >> rshift (the c-does-not-divide-256 quirk of msm.rs:119-139)
-        uint32_t ws = rshift >> 5, bs = rshift & 31;
+    if (a.rshift) {  // value >> rshift (the c-does-not-divide-256 quirk of msm.rs:119-139)
+        uint32_t ws = a.rshift >> 5, bs = a.rshift & 31;
         uint32_t t[10];
 #pragma unroll
         for (int k = 0; k < 10; k++) {
@@ -102,103 +113,409 @@ __global__ void __launch_bounds__(256) msm_recode_kernel(const fr_t* __restrict_
 #pragma unroll
         for (int k = 0; k < 10; k++) l[k] = t[k];
     }
-    const uint32_t half = 1u << (c - 1);
-    const uint32_t mask = (1u << c) - 1;
+}
+
+// window w of the signed recoding: key = bucket (INVALID_KEY for a zero digit), val = point index | sign << 31
+__device__ __forceinline__ void recode_window(const RecodeArgs& a, const uint32_t l[10], uint32_t i, uint32_t w,
+                                              uint32_t& carry, uint32_t& key, uint32_t& val) {
+    const uint32_t half = 1u << (a.c - 1), mask = (1u << a.c) - 1;
+    const uint32_t bit = w * a.c, limb = bit >> 5, off = bit & 31;
+    uint64_t two = 0;
+    if (limb < 9) two = (uint64_t)l[limb] | ((uint64_t)l[limb + 1] << 32);
+    const uint32_t raw = ((uint32_t)(two >> off) & mask) + carry;
+    uint32_t d, neg;
+    if (raw > half) {
+        d = (1u << a.c) - raw;
+        neg = 1;
+        carry = 1;
+    } else {
+        d = raw;
+        neg = 0;
+        carry = 0;
+    }
+    key = d ? (w * a.key_stride + d - 1) : INVALID_KEY;
+    val = (w * a.val_stride + i) | (neg << 31);
+}
+
+// Histogram of the bucket keys.  Lanes of a warp that hit the same bucket are combined before the L2 reduction
+// (match.any): with uniform digits that changes nothing, with skewed scalars (a witness full of zeros and ones, all
+// scalars equal) it keeps one hot bucket from serialising 32 reductions per warp.
+__global__ void __launch_bounds__(256) msm_count_kernel(RecodeArgs a, uint32_t* __restrict__ cnt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const bool active = i < a.n;
+    uint32_t l[10];
+    if (active) recode_limbs(a, i, l);
     uint32_t carry = 0;
-    for (uint32_t w = 0; w < W; w++) {
-        uint32_t bit = w * c;
-        uint32_t limb = bit >> 5, off = bit & 31;
-        uint64_t two = 0;
-        if (limb < 9) two = (uint64_t)l[limb] | ((uint64_t)l[limb + 1] << 32);
-        uint32_t raw = ((uint32_t)(two >> off) & mask) + carry;
-        uint32_t d, neg;
-        if (raw > half) {
-            d = (1u << c) - raw;
-            neg = 1;
-            carry = 1;
-        } else {
-            d = raw;
-            neg = 0;
-            carry = 0;
-        }
-        size_t o = (size_t)w * n + i;
-        keys[o] = d ? (w * key_stride + d - 1) : INVALID_KEY;
-        vals[o] = (w * val_stride + i) | (neg << 31);
+    for (uint32_t w = 0; w < a.W; w++) {
+        uint32_t key = INVALID_KEY, val = 0;
+        if (active) recode_window(a, l, i, w, carry, key, val);
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        if (key != INVALID_KEY && (peers & ((1u << lane) - 1)) == 0) atomicAdd(cnt + key, (uint32_t)__popc(peers));
+    }
+}
+
+// Counting-sort scatter: cursor[b] starts at the first level-0 slot of bucket b (K2).  The order of the entries inside a
+// bucket depends on the order in which warps arrive; the bucket SUM (a group element, output in affine form) does not.
+__global__ void __launch_bounds__(256) msm_scatter_kernel(RecodeArgs a, uint32_t* __restrict__ cursor,
+                                                           uint2* __restrict__ kv0) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const bool active = i < a.n;
+    uint32_t l[10];
+    if (active) recode_limbs(a, i, l);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < a.W; w++) {
+        uint32_t key = INVALID_KEY, val = 0;
+        if (active) recode_window(a, l, i, w, carry, key, val);
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        const uint32_t leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (key != INVALID_KEY && lane == leader) base = atomicAdd(cursor + key, (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (key != INVALID_KEY) kv0[base + __popc(peers & ((1u << lane) - 1))] = make_uint2(key, val);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// K3: chunked bucket accumulation
+// K2: layout of all tree levels from the histogram.  Bucket b with c0 entries holds c_l = ceil(c0 / 2^l) entries at
+// level l; a bucket that is down to one entry (l >= 1) has left the tree (its sum sits in the bucket array).  Every
+// level but the last pads a bucket to an even number of slots, so that the pair (2j, 2j + 1) never straddles two
+// buckets; level L (the input of the XYZZ tail) is dense.  off[l][b] = first slot of bucket b at level l.
 // ------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t level_entries(uint32_t c0, int l) { return (c0 + ((1u << l) - 1u)) >> l; }
+__device__ __forceinline__ uint32_t level_slots(uint32_t c0, int l, int L) {
+    if (c0 == 0) return 0;
+    const uint32_t c = level_entries(c0, l);
+    if (l > 0 && c < 2) return 0;
+    return l == L ? c : (c + 1u) & ~1u;
+}
+
+// block-wide exclusive scan of one value per thread (SCAN_THREADS threads); returns the exclusive prefix, total to all
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& total, uint32_t* smem /* 9 words */) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += t;
+    }
+    __syncthreads();  // smem may still be read from a previous call
+    if (lane == 31) smem[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < SCAN_THREADS / 32 ? smem[lane] : 0, wi = w;
+#pragma unroll
+        for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= (uint32_t)d) wi += t;
+        }
+        if (lane < SCAN_THREADS / 32) smem[lane] = wi - w;  // exclusive warp bases
+        if (lane == SCAN_THREADS / 32 - 1) smem[8] = wi;
+    }
+    __syncthreads();
+    total = smem[8];
+    return incl - v + smem[warp];
+}
+
+// stats: [0] entries at level 0, [1] entries at level L (finished buckets count 1), [2] non-empty buckets
+__global__ void __launch_bounds__(SCAN_THREADS) msm_level_sums_kernel(const uint32_t* __restrict__ cnt, uint32_t nb, int L,
+                                                                       uint32_t nblk, uint32_t* __restrict__ blocksums,
+                                                                       unsigned long long* __restrict__ stats) {
+    __shared__ uint32_t smem[9];
+    uint32_t c0[SCAN_ITEMS];
+    const uint32_t first = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) c0[k] = first + k < nb ? cnt[first + k] : 0;
+    for (int l = 0; l <= L; l++) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) s += level_slots(c0[k], l, L);
+        uint32_t total;
+        block_exclusive_scan(s, total, smem);
+        if (threadIdx.x == 0) blocksums[(size_t)l * nblk + blockIdx.x] = total;
+    }
+    uint32_t e0 = 0, eL = 0, ne = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        e0 += c0[k];
+        eL += c0[k] ? level_entries(c0[k], L) : 0;
+        ne += c0[k] != 0;
+    }
+    uint32_t t0, tL, tn;
+    block_exclusive_scan(e0, t0, smem);
+    block_exclusive_scan(eL, tL, smem);
+    block_exclusive_scan(ne, tn, smem);
+    if (threadIdx.x == 0) {
+        atomicAdd(stats + 0, (unsigned long long)t0);
+        atomicAdd(stats + 1, (unsigned long long)tL);
+        atomicAdd(stats + 2, (unsigned long long)tn);
+    }
+}
+
+// one block per level: exclusive scan of the per-block sums in place, level total out
+__global__ void __launch_bounds__(1024) msm_level_scan_kernel(uint32_t* __restrict__ blocksums, uint32_t nblk,
+                                                               uint32_t* __restrict__ totals) {
+    __shared__ uint32_t part[1024];
+    uint32_t* row = blocksums + (size_t)blockIdx.x * nblk;
+    const uint32_t per = (nblk + 1023) / 1024;
+    const uint32_t lo = threadIdx.x * per, hi = lo + per < nblk ? lo + per : nblk;
+    uint32_t s = 0;
+    for (uint32_t i = lo; i < hi; i++) s += row[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {  // Hillis-Steele on 1024 partial sums
+        uint32_t t = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint32_t run = part[threadIdx.x] - s;
+    for (uint32_t i = lo; i < hi; i++) {
+        uint32_t v = row[i];
+        row[i] = run;
+        run += v;
+    }
+    if (threadIdx.x == 1023) totals[blockIdx.x] = part[1023];
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) msm_level_offsets_kernel(const uint32_t* __restrict__ cnt, uint32_t nb, int L,
+                                                                          uint32_t nblk, const uint32_t* __restrict__ blockbase,
+                                                                          uint32_t* __restrict__ off /* [(L+1)][nb] */,
+                                                                          uint32_t* __restrict__ cursor,
+                                                                          uint2* __restrict__ kv0) {
+    __shared__ uint32_t smem[9];
+    uint32_t c0[SCAN_ITEMS];
+    const uint32_t first = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) c0[k] = first + k < nb ? cnt[first + k] : 0;
+    for (int l = 0; l <= L; l++) {
+        uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            v[k] = level_slots(c0[k], l, L);
+            s += v[k];
+        }
+        uint32_t total;
+        uint32_t run = block_exclusive_scan(s, total, smem) + blockbase[(size_t)l * nblk + blockIdx.x];
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (first + k < nb) {
+                off[(size_t)l * nb + first + k] = run;
+                if (l == 0) {
+                    cursor[first + k] = run;
+                    if (L > 0 && (c0[k] & 1u)) kv0[run + c0[k]] = make_uint2(INVALID_KEY, 0);  // the pad slot
+                }
+            }
+            run += v[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: one level of the pairwise tree in affine coordinates
+// ------------------------------------------------------------------------------------------
+struct AffLevelArgs {
+    const uint2* kv0;          // level 0: (bucket, point | sign) per slot
+    const uint32_t* keys_in;   // level >= 1: bucket per slot
+    const affine_t* pts_in;    // level 0: the SRS (all precomputed levels); level >= 1: this level's points
+    uint32_t* keys_out;
+    affine_t* pts_out;         // level + 1
+    const uint32_t* cnt0;
+    const uint32_t* off_in;    // off[level]
+    const uint32_t* off_out;   // off[level + 1]
+    const uint32_t* totals;    // slots per level
+    xyzz_t* buckets;           // finished buckets, as XYZZ (x, y, 1, 1)
+    uint4* scratch;            // prefix products: [bmax][3][threads of the launch]
+    uint32_t level, bmax, out_is_tail;
+};
+
+#ifndef BPK_AFF_MINBLOCKS
+#define BPK_AFF_MINBLOCKS 4
+#endif
+template <bool LEVEL0>
+__global__ void __launch_bounds__(128, BPK_AFF_MINBLOCKS) msm_affine_level_kernel(AffLevelArgs a) {
+    const uint32_t S = a.totals[a.level] >> 1;  // pairs of this level
+    if (S == 0) return;
+    const uint32_t T = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    // every thread takes batches of B pairs, interleaved with the other threads (pair = base + j T + tid): the lanes of a
+    // warp read neighbouring pairs and prefix slots; B is the smallest batch that covers the level in whole rounds
+    const uint64_t per_round = (uint64_t)T * a.bmax;
+    const uint32_t rounds = (uint32_t)((S + per_round - 1) / per_round);
+    const uint32_t B = (uint32_t)((S + (uint64_t)T * rounds - 1) / ((uint64_t)T * rounds));
+    uint4* const sc = a.scratch + tid;
+
+    auto load_pair = [&](uint32_t p, affine_t& P, affine_t& Q, uint32_t& key) {
+        if (LEVEL0) {
+            const uint4 e = reinterpret_cast<const uint4*>(a.kv0)[p];  // (key, val) of slots 2p and 2p + 1
+            key = e.x;
+            P = ld_affine(a.pts_in + (e.y & 0x7fffffffu));
+            if (e.y >> 31) P.y = neg(P.y);
+            if (e.z == INVALID_KEY) {
+                Q = affine_t::inf();
+            } else {
+                Q = ld_affine(a.pts_in + (e.w & 0x7fffffffu));
+                if (e.w >> 31) Q.y = neg(Q.y);
+            }
+        } else {
+            const uint2 kk = reinterpret_cast<const uint2*>(a.keys_in)[p];
+            key = kk.x;
+            P = ld_affine(a.pts_in + 2 * (size_t)p);
+            Q = kk.y == INVALID_KEY ? affine_t::inf() : ld_affine(a.pts_in + 2 * (size_t)p + 1);
+        }
+    };
+
+    for (uint32_t r = 0; r < rounds; r++) {
+        const uint64_t base = (uint64_t)r * T * B + tid;
+        if (base >= S) break;
+        const uint64_t left = (S - base + T - 1) / T;
+        const uint32_t nj = left < B ? (uint32_t)left : B;
+
+        // forward: denominators and their running product.  Only the x coordinates are needed unless the pair is
+        // degenerate (pad, identity operand, equal x), which is re-examined with the full points.
+        fp_t prod = fp_t::one();
+        for (uint32_t j = 0; j < nj; j++) {
+            const uint32_t p = (uint32_t)(base + (uint64_t)j * T);
+            fp_t den;
+            bool slow;
+            if (LEVEL0) {
+                const uint4 e = reinterpret_cast<const uint4*>(a.kv0)[p];
+                slow = e.z == INVALID_KEY;
+                const fp_t x1 = ld_fp(&a.pts_in[e.y & 0x7fffffffu].x);
+                const fp_t x2 = slow ? x1 : ld_fp(&a.pts_in[e.w & 0x7fffffffu].x);
+                den = sub(x2, x1);
+                slow = slow || den.is_zero() || x1.is_zero() || x2.is_zero();
+            } else {
+                const uint2 kk = reinterpret_cast<const uint2*>(a.keys_in)[p];
+                slow = kk.y == INVALID_KEY;
+                const fp_t x1 = ld_fp(&a.pts_in[2 * (size_t)p].x);
+                const fp_t x2 = slow ? x1 : ld_fp(&a.pts_in[2 * (size_t)p + 1].x);
+                den = sub(x2, x1);
+                slow = slow || den.is_zero() || x1.is_zero() || x2.is_zero();
+            }
+            if (slow) {
+                affine_t P, Q;
+                uint32_t key;
+                load_pair(p, P, Q, key);
+                affine_add_prepare(P, Q, den);
+            }
+            prod = j == 0 ? den : mul(prod, den);
+            uint4* s = sc + (size_t)j * 3 * T;
+            s[0] = make_uint4(prod.l[0], prod.l[1], prod.l[2], prod.l[3]);
+            s[T] = make_uint4(prod.l[4], prod.l[5], prod.l[6], prod.l[7]);
+            s[2 * (size_t)T] = make_uint4(prod.l[8], prod.l[9], prod.l[10], prod.l[11]);
+        }
+
+        fp_t acc = inv(prod);  // 1 / (den_0 ... den_{nj-1})
+
+        // backward: peel the inverses off, finish the additions, place the results
+        for (uint32_t j = nj; j-- > 0;) {
+            const uint32_t p = (uint32_t)(base + (uint64_t)j * T);
+            affine_t P, Q;
+            uint32_t key;
+            load_pair(p, P, Q, key);
+            fp_t den;
+            const int kind = affine_add_prepare(P, Q, den);
+            fp_t dinv = acc;
+            if (j > 0) {
+                const uint4* s = sc + (size_t)(j - 1) * 3 * T;
+                const uint4 u0 = s[0], u1 = s[T], u2 = s[2 * (size_t)T];
+                fp_t pre;
+                pre.l[0] = u0.x; pre.l[1] = u0.y; pre.l[2] = u0.z; pre.l[3] = u0.w;
+                pre.l[4] = u1.x; pre.l[5] = u1.y; pre.l[6] = u1.z; pre.l[7] = u1.w;
+                pre.l[8] = u2.x; pre.l[9] = u2.y; pre.l[10] = u2.z; pre.l[11] = u2.w;
+                dinv = mul(acc, pre);
+                acc = mul(acc, den);
+            }
+            const affine_t R = affine_add_finish(kind, P, Q, dinv);
+            const uint32_t c0 = a.cnt0[key];
+            const uint32_t cn = (c0 + ((2u << a.level) - 1u)) >> (a.level + 1);  // entries of the bucket at level + 1
+            if (cn <= 1) {
+                st_xyzz(a.buckets + key, xyzz_t::from_affine(R));
+            } else {
+                const uint32_t rel = p - (a.off_in[key] >> 1);
+                const uint32_t slot = a.off_out[key] + rel;
+                st_affine(a.pts_out + slot, R);
+                a.keys_out[slot] = key;
+                if (!a.out_is_tail && (cn & 1u) && rel == cn - 1) a.keys_out[slot + 1] = INVALID_KEY;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: chunked bucket accumulation in XYZZ coordinates (the tail of the affine tree, or the whole accumulation when no
+// affine level runs).  The list is sorted by bucket and dense; its length comes from the layout scan.
+// ------------------------------------------------------------------------------------------
+struct TailSrc {
+    const uint2* kv0;         // level 0 list (points gathered through val), or null
+    const uint32_t* keys;     // level >= 1 list (point e of pts)
+    const affine_t* pts;
+    const uint32_t* total;    // number of entries (device)
+};
+template <bool LEVEL0>
+__device__ __forceinline__ uint32_t tail_key(const TailSrc& s, size_t e) {
+    return LEVEL0 ? s.kv0[e].x : s.keys[e];
+}
+template <bool LEVEL0>
+__device__ __forceinline__ affine_t tail_point(const TailSrc& s, size_t e) {
+    if (LEVEL0) {
+        const uint32_t v = s.kv0[e].y;
+        affine_t p = ld_affine(s.pts + (v & 0x7fffffffu));
+        if (v >> 31) p.y = neg(p.y);
+        return p;
+    }
+    return ld_affine(s.pts + e);
+}
+
 #ifndef BPK_ACC_MINBLOCKS
 #define BPK_ACC_MINBLOCKS 4  // 4 x 128 threads / SM = 128 registers per thread: ~0.5 KB of spills, but 16 warps hide the
                              // dependent-issue waits better than 12 (2^24: 74.6 -> 73.2 ms; 2 CTAs: 77.0, 5 CTAs: 77.4)
 #endif
-__global__ void __launch_bounds__(128, BPK_ACC_MINBLOCKS) msm_accumulate_kernel(const uint32_t* __restrict__ keys,
-                                                              const uint32_t* __restrict__ vals, size_t M,
-                                                              uint32_t chunk, size_t num_chunks,
-                                                              const affine_t* __restrict__ points, uint32_t nb_total,
+template <bool LEVEL0>
+__global__ void __launch_bounds__(128, BPK_ACC_MINBLOCKS) msm_accumulate_kernel(TailSrc src, uint32_t chunk, size_t num_chunks,
                                                               xyzz_t* __restrict__ buckets,
                                                               uint32_t* __restrict__ pkeys,
                                                               xyzz_t* __restrict__ pvals) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= num_chunks) return;
+    const size_t M = *src.total;
     const size_t a = t * chunk;
-    const size_t b = (a + chunk < M) ? a + chunk : M;
     uint32_t pk0 = INVALID_KEY, pk1 = INVALID_KEY;
-
-    uint32_t cur = INVALID_KEY;
-    bool left_open = false;
-    xyzz_t acc = xyzz_t::inf();
-
-    // software pipeline: the point of entry e+1 is fetched while entry e is added, and the (key, value) pair of
-    // entry e+2 is already in registers, so the gather never waits behind the two strided index loads
-    uint32_t k_next = keys[a], v_next = vals[a];
-    uint32_t k_next2 = INVALID_KEY, v_next2 = 0;
-    if (a + 1 < b) {
-        k_next2 = keys[a + 1];
-        v_next2 = vals[a + 1];
-    }
-    affine_t p_next = affine_t::inf();
-    if (k_next < nb_total) {
-        p_next = ld_affine(points + (v_next & 0x7fffffffu));
-        if (v_next >> 31) p_next.y = neg(p_next.y);
-    }
-    size_t e = a;
-    for (; e < b; e++) {
-        uint32_t k = k_next;
-        if (k >= nb_total) break;
-        affine_t p = p_next;
-        k_next = k_next2;
-        v_next = v_next2;
-        if (e + 2 < b) {
-            k_next2 = keys[e + 2];
-            v_next2 = vals[e + 2];
-        } else {
-            k_next2 = INVALID_KEY;
-        }
-        if (e + 1 < b && k_next < nb_total) {
-            p_next = ld_affine(points + (v_next & 0x7fffffffu));
-            if (v_next >> 31) p_next.y = neg(p_next.y);
-        }
-        if (k != cur) {
-            if (cur != INVALID_KEY) {  // close the previous run (cannot be right-open)
-                if (left_open) {
-                    pk0 = cur;
-                    st_xyzz(pvals + 2 * t, acc);
-                } else {
-                    st_xyzz(buckets + cur, acc);
-                }
+    if (a < M) {
+        const size_t b = (a + chunk < M) ? a + chunk : M;
+        uint32_t cur = INVALID_KEY;
+        bool left_open = false;
+        xyzz_t acc = xyzz_t::inf();
+        // software pipeline: the point of entry e + 1 is fetched while entry e is added
+        uint32_t k_next = tail_key<LEVEL0>(src, a);
+        affine_t p_next = tail_point<LEVEL0>(src, a);
+        for (size_t e = a; e < b; e++) {
+            const uint32_t k = k_next;
+            const affine_t p = p_next;
+            if (e + 1 < b) {
+                k_next = tail_key<LEVEL0>(src, e + 1);
+                p_next = tail_point<LEVEL0>(src, e + 1);
             }
-            cur = k;
-            left_open = (e == a) && (a > 0) && (keys[a - 1] == k);
-            acc = xyzz_t::from_affine(p);
-        } else {
-            xyzz_madd(acc, p);
+            if (k != cur) {
+                if (cur != INVALID_KEY) {  // close the previous run (cannot be right-open)
+                    if (left_open) {
+                        pk0 = cur;
+                        st_xyzz(pvals + 2 * t, acc);
+                    } else {
+                        st_xyzz(buckets + cur, acc);
+                    }
+                }
+                cur = k;
+                left_open = (e == a) && (a > 0) && (tail_key<LEVEL0>(src, a - 1) == k);
+                acc = xyzz_t::from_affine(p);
+            } else {
+                xyzz_madd(acc, p);
+            }
         }
-    }
-    if (cur != INVALID_KEY) {
-        bool right_open = (e == b) && (b < M) && (keys[b] == cur);
+        const bool right_open = (b < M) && (tail_key<LEVEL0>(src, b) == cur);
         if (left_open) {
             pk0 = cur;
             st_xyzz(pvals + 2 * t, acc);
@@ -213,10 +530,10 @@ __global__ void __launch_bounds__(128, BPK_ACC_MINBLOCKS) msm_accumulate_kernel(
     pkeys[2 * t + 1] = pk1;
 }
 
-// K3b: a run that crosses chunk borders starts as slot 1 of some chunk t0 (the head) and continues as slot 0
-// of the chunks t0+1 .. t1 whose first pair has the same key.  The thread that owns the head finds t1 by a
+// K5b: a run that crosses chunk borders starts as slot 1 of some chunk t0 (the head) and continues as slot 0
+// of the chunks t0+1 .. t1 whose first entry has the same key.  The thread that owns the head finds t1 by a
 // binary search over the first keys of the chunks (sorted), adds short runs itself and queues long runs
-// (heavy buckets: skewed scalars, narrow top windows) for a block-wide tree reduction, so that no scalar
+// (heavy buckets: skewed scalars, narrow top windows) for a warp- or block-wide tree reduction, so that no scalar
 // distribution can serialise the merge.
 constexpr uint32_t MERGE_SERIAL_MAX = 8;    // runs up to this many partials: added by the head's thread
 constexpr uint32_t MERGE_WARP_MAX = 256;    // up to this many: one warp per run; longer: one block per run
@@ -224,10 +541,11 @@ struct LongRun {
     uint32_t key, t0, t1, pad;
 };
 
+template <bool LEVEL0>
 __global__ void __launch_bounds__(128, 3) msm_merge_partials_kernel(const uint32_t* __restrict__ pkeys,
                                                                   const xyzz_t* __restrict__ pvals,
                                                                   size_t num_chunks, xyzz_t* __restrict__ buckets,
-                                                                  const uint32_t* __restrict__ keys, uint32_t chunk,
+                                                                  TailSrc src, uint32_t chunk,
                                                                   LongRun* __restrict__ long_runs,
                                                                   uint32_t* __restrict__ long_count,
                                                                   LongRun* __restrict__ warp_runs,
@@ -237,10 +555,12 @@ __global__ void __launch_bounds__(128, 3) msm_merge_partials_kernel(const uint32
     uint32_t k = pkeys[2 * t + 1];
     if (k == INVALID_KEY) return;
     // chunk t+1 starts with key k (the head is right-open); find the last chunk that does
-    size_t lo = t + 1, hi = num_chunks;
+    const size_t M = *src.total;
+    const size_t live = (M + chunk - 1) / chunk;  // chunks that hold entries
+    size_t lo = t + 1, hi = live;
     while (lo + 1 < hi) {
         size_t mid = lo + (hi - lo) / 2;
-        if (keys[mid * chunk] <= k)
+        if (tail_key<LEVEL0>(src, mid * chunk) <= k)
             lo = mid;
         else
             hi = mid;
@@ -272,6 +592,14 @@ __device__ __forceinline__ fp_t shfl_down_fp(const fp_t& v, int delta) {
     for (int i = 0; i < 12; i++) r.l[i] = __shfl_down_sync(0xffffffffu, v.l[i], delta);
     return r;
 }
+__device__ __forceinline__ xyzz_t shfl_down_xyzz(const xyzz_t& v, int delta) {
+    xyzz_t o;
+    o.X = shfl_down_fp(v.X, delta);
+    o.Y = shfl_down_fp(v.Y, delta);
+    o.ZZ = shfl_down_fp(v.ZZ, delta);
+    o.ZZZ = shfl_down_fp(v.ZZZ, delta);
+    return o;
+}
 
 // one warp per medium run: lane-strided partial sums, then a shuffle tree
 __global__ void __launch_bounds__(128) msm_merge_warp_runs_kernel(const LongRun* __restrict__ runs,
@@ -293,11 +621,7 @@ __global__ void __launch_bounds__(128) msm_merge_warp_runs_kernel(const LongRun*
         __syncwarp();
 #pragma unroll 1
         for (int delta = 16; delta >= 1; delta >>= 1) {
-            xyzz_t o;
-            o.X = shfl_down_fp(acc.X, delta);
-            o.Y = shfl_down_fp(acc.Y, delta);
-            o.ZZ = shfl_down_fp(acc.ZZ, delta);
-            o.ZZZ = shfl_down_fp(acc.ZZZ, delta);
+            xyzz_t o = shfl_down_xyzz(acc, delta);
             xyzz_add(acc, o);
             __syncwarp();
         }
@@ -339,43 +663,7 @@ __global__ void __launch_bounds__(MERGE_BLOCK) msm_merge_long_runs_kernel(const 
 }
 
 // ------------------------------------------------------------------------------------------
-// K4: bucket reduction tree.  Level input: per window `items` points A (and carried sums V);
-// each thread folds S consecutive items:  A' = sum A_r,  V' = 2^dbls * sum_r r A_r + sum_r V_r.
-// Invariant: sum_b b A0_b = S^level * sum_k k A'_k + sum_k V'_k.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) msm_reduce_level_kernel(const xyzz_t* __restrict__ A,
-                                                                const xyzz_t* __restrict__ V,
-                                                                xyzz_t* __restrict__ A2, xyzz_t* __restrict__ V2,
-                                                                uint32_t items, uint32_t S, uint32_t W,
-                                                                uint32_t dbls) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t groups = items / S;
-    if (t >= groups * W) return;
-    uint32_t w = t / groups, k = t % groups;
-    size_t base = (size_t)w * items + (size_t)k * S;
-    xyzz_t run = xyzz_t::inf(), acc = xyzz_t::inf();
-    for (uint32_t r = S - 1; r >= 1; r--) {
-        xyzz_t q = ld_xyzz(A + base + r);
-        xyzz_add(run, q);
-        xyzz_add(acc, run);
-    }
-    {
-        xyzz_t q = ld_xyzz(A + base);
-        xyzz_add(run, q);
-    }
-    for (uint32_t i = 0; i < dbls; i++) xyzz_dbl(acc);
-    if (V) {
-        for (uint32_t r = 0; r < S; r++) {
-            xyzz_t q = ld_xyzz(V + base + r);
-            xyzz_add(acc, q);
-        }
-    }
-    st_xyzz(A2 + (size_t)w * groups + k, run);
-    st_xyzz(V2 + (size_t)w * groups + k, acc);
-}
-
-// ------------------------------------------------------------------------------------------
-// K4 (default): bucket reduction by bit planes.  With B_k the bucket of digit k + 1 (k < half = 2^L),
+// K6: bucket reduction by bit planes.  With B_k the bucket of digit k + 1 (k < half = 2^L),
 //     sum_k (k + 1) B_k = sum_k B_k + sum_{p < L} 2^p T_p,      T_p = sum_{k : bit p of k set} B_k.
 // One pairwise tree carries the plane sums along: a level-k node covers 2^k consecutive buckets and holds
 // k + 1 points [S, T_0 .. T_{k-1}] restricted to its range.  Merging the children (c0, c1) of a node:
@@ -408,8 +696,42 @@ __global__ void __launch_bounds__(128, BPK_TREE_MINBLOCKS) msm_plane_tree_level_
     st_xyzz(out + t, a);
 }
 
+// The narrow top of the same tree in ONE block: from level k_first on, a level has at most 512 (node, slot) additions, so
+// a launch per level is all latency (launch gap + one addition each).  The block keeps the levels in its ping-pong
+// buffers and synchronises between them.
+constexpr int TREE_TOP_THREADS = 512;
+__global__ void __launch_bounds__(TREE_TOP_THREADS) msm_plane_tree_top_kernel(const xyzz_t* __restrict__ in, xyzz_t* __restrict__ buf_a,
+                                                                               xyzz_t* __restrict__ buf_b, uint32_t k_first,
+                                                                               uint32_t k_last, size_t nodes_first) {
+    const uint32_t t = threadIdx.x;
+    const xyzz_t* src = in;
+    size_t nodes = nodes_first;
+    for (uint32_t k = k_first; k <= k_last; k++) {
+        xyzz_t* dst = (k & 1) ? buf_a : buf_b;
+        const uint32_t slots = k + 1;
+        if (t < nodes * slots) {
+            const size_t node = t / slots;
+            const uint32_t s = (uint32_t)(t - node * slots);
+            const xyzz_t* c0 = src + 2 * node * k;
+            const xyzz_t* c1 = c0 + k;
+            if (s == k) {
+                st_xyzz(dst + t, ld_xyzz(c1));
+            } else {
+                xyzz_t a = ld_xyzz(c0 + s);
+                xyzz_t b = ld_xyzz(c1 + s);
+                xyzz_add(a, b);
+                st_xyzz(dst + t, a);
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+        src = dst;
+        nodes >>= 1;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
-// K5: window Horner + output
+// K7: plane / window Horner + output
 // ------------------------------------------------------------------------------------------
 __device__ void write_projective(uint64_t* out, const xyzz_t& p, bool normalise) {
     fp_t X, Y, Z;
@@ -435,23 +757,13 @@ __device__ void write_projective(uint64_t* out, const xyzz_t& p, bool normalise)
     }
 }
 
-__global__ void msm_finalize_kernel(const xyzz_t* A, const xyzz_t* V, uint32_t W, uint32_t c, int normalise,
-                                    uint64_t* out) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    xyzz_t acc = xyzz_t::inf();
-    for (int w = (int)W - 1; w >= 0; w--) {
-        for (uint32_t i = 0; i < c; i++) xyzz_dbl(acc);
-        xyzz_t tw = ld_xyzz(V + w);  // sum_b b B_b
-        xyzz_t g = ld_xyzz(A + w);   // sum_b B_b
-        xyzz_add(tw, g);
-        xyzz_add(acc, tw);
-    }
-    write_projective(out, acc, normalise != 0);
+__global__ void msm_write_identity_kernel(uint64_t* out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) write_projective(out, xyzz_t::inf(), true);
 }
 
-// plane form: the L plane sums of a window are folded by Horner in 2.  With few windows (precomputed levels:
-// one) the planes are split into groups of GROUP consecutive planes, one thread per group, and the group values
-// are folded in 2^GROUP -- the same doublings, but a third of the additions on the serial path.
+// The L plane sums of a window are folded by Horner in 2.  With few windows (precomputed levels: one) the planes are
+// split into groups of GROUP consecutive planes, one thread per group, and the group values are folded in 2^GROUP --
+// the same doublings, but a third of the additions on the serial path.
 constexpr uint32_t FIN_GROUP = 4;
 __global__ void __launch_bounds__(128) msm_finalize_planes_kernel(const xyzz_t* __restrict__ roots, uint32_t W,
                                                                    uint32_t L, uint32_t c, uint32_t groups,
@@ -499,11 +811,12 @@ __global__ void __launch_bounds__(128) msm_finalize_planes_kernel(const xyzz_t* 
     write_projective(out, acc, normalise != 0);
 }
 
-// sum of n homogeneous projective points (X:Y:Z), normalised output
-__global__ void g1_sum_kernel(const uint64_t* pts, uint32_t n, uint64_t* out) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// sum of n homogeneous projective points (X:Y:Z), normalised output: one warp, lane-strided partial sums and a
+// shuffle tree (the post-gather step of the sharded MSM adds one partial per rank)
+__global__ void __launch_bounds__(32) g1_sum_kernel(const uint64_t* pts, uint32_t n, uint64_t* out) {
+    const uint32_t lane = threadIdx.x;
     xyzz_t acc = xyzz_t::inf();
-    for (uint32_t i = 0; i < n; i++) {
+    for (uint32_t i = lane; i < n; i += 32) {
         const fp_t* p = reinterpret_cast<const fp_t*>(pts + 18 * (size_t)i);
         fp_t X = ld_fp(p), Y = ld_fp(p + 1), Z = ld_fp(p + 2);
         if (Z.is_zero()) continue;
@@ -514,7 +827,16 @@ __global__ void g1_sum_kernel(const uint64_t* pts, uint32_t n, uint64_t* out) {
         q.Y = mul(Y, q.ZZ);
         xyzz_add(acc, q);
     }
-    write_projective(out, acc, true);
+    __syncwarp();
+#pragma unroll 1
+    for (int delta = 16; delta >= 1; delta >>= 1) {
+        if ((uint32_t)delta < n) {  // uniform across the warp
+            xyzz_t o = shfl_down_xyzz(acc, delta);
+            xyzz_add(acc, o);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) write_projective(out, acc, true);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -526,9 +848,9 @@ static uint32_t pick_window(bpk_ctx* ctx, size_t n) {
     uint32_t best_c = 4;
     for (uint32_t c = 3; c <= 16; c++) {
         uint32_t W = (256 + c - 1) / c;
-        // pair additions + bucket-tree additions (full adds ~1.5x a mixed add, 3 per bucket) + a latency
+        // pair additions + bucket-tree additions (full adds ~2.3x a batched-affine add, 2 per bucket) + a latency
         // term for the serial depth of the tree / Horner tail expressed in pair-addition equivalents
-        double cost = (double)W * ((double)n + 4.5 * (double)(1u << (c - 1))) + 2000.0 * c;
+        double cost = (double)W * ((double)n + 5.0 * (double)(1u << (c - 1))) + 2000.0 * c;
         if (cost < best) {
             best = cost;
             best_c = c;
@@ -541,7 +863,29 @@ static uint32_t pick_window(bpk_ctx* ctx, size_t n) {
 struct MsmPlan {
     bool pre;        // all windows share one bucket set (precomputed SRS levels)
     uint32_t c, W, half, WB, nb_total;
+    int L;           // affine tree levels
 };
+
+static size_t level_ub(size_t M, uint32_t nb, int l) {  // slots of level l: entries + one pad per unfinished bucket
+    const size_t e = M >> l;
+    return e + 2 * (e < nb ? e : (size_t)nb) + 2;
+}
+
+// number of affine tree levels for M entries in nb buckets
+static int msm_pick_levels(bpk_ctx* ctx, size_t M, uint32_t nb) {
+    if (ctx->opt_msm_affine_levels >= 0)
+        return (int)(ctx->opt_msm_affine_levels > MSM_MAX_LEVELS ? MSM_MAX_LEVELS : ctx->opt_msm_affine_levels);
+    if (M < (size_t)ctx->opt_msm_min_pairs) return 0;
+    // uniform digits: the fullest bucket holds about avg + 6 sqrt(avg) entries; one more level than its depth costs an
+    // empty launch, one fewer leaves work to the (slower) XYZZ tail
+    const double avg = (double)M / (double)nb;
+    const double top = avg + 6.0 * sqrt(avg) + 1.0;
+    int L = 0;
+    while (L < MSM_MAX_LEVELS && (double)((size_t)1 << L) < top) L++;
+    // a level with few pairs is all latency (one inversion per thread): leave those to the tail
+    while (L > 0 && (M >> L) < (size_t)ctx->opt_msm_min_pairs) L--;
+    return L;
+}
 
 static int msm_make_plan(bpk_ctx* ctx, const MsmPoints& pts, size_t n, MsmPlan* plan) {
     if (n >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
@@ -551,27 +895,31 @@ static int msm_make_plan(bpk_ctx* ctx, const MsmPoints& pts, size_t n, MsmPlan* 
     plan->half = 1u << (plan->c - 1);
     plan->WB = plan->pre ? 1 : plan->W;
     plan->nb_total = plan->WB * plan->half;
-    if ((size_t)plan->W * n >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
+    if ((size_t)plan->W * n + plan->nb_total >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
     if (plan->pre && (size_t)plan->W * pts.level_stride >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
+    plan->L = msm_pick_levels(ctx, (size_t)plan->W * n, plan->nb_total);
+    // the tree's level buffers (96 B per slot at levels 1 and 2) must fit the budget; beyond it (2^26-point inputs next
+    // to a precomputed SRS) everything goes through the XYZZ chunks, which need no per-entry storage
+    if (plan->L >= 1) {
+        const size_t M = (size_t)plan->W * n;
+        const size_t bytes = (level_ub(M, plan->nb_total, 1) + (plan->L >= 2 ? level_ub(M, plan->nb_total, 2) : 0)) * 100;
+        if (bytes > (size_t)ctx->opt_msm_level_mib << 20) plan->L = 0;
+    }
     return BPK_OK;
 }
 
 static int msm_empty_result(bpk_ctx* ctx, uint64_t* d_out) {  // empty sum: identity (0, R, 0)
-    xyzz_t* zero;
-    BPK_TRY(ws_reserve(ctx, 5, 2 * sizeof(xyzz_t), (void**)&zero));
-    BPK_CUDA(cudaMemsetAsync(zero, 0, 2 * sizeof(xyzz_t), ctx->stream));
-    msm_finalize_kernel<<<1, 1, 0, ctx->stream>>>(zero, zero + 1, 1, 1, 1, d_out);
+    msm_write_identity_kernel<<<1, 1, 0, ctx->stream>>>(d_out);
     count_launch(ctx);
     BPK_CUDA(cudaGetLastError());
     return BPK_OK;
 }
 
-static uint32_t msm_chunk(bpk_ctx* ctx, size_t M) {  // sorted pairs per accumulate thread
+static uint32_t msm_chunk(bpk_ctx* ctx, size_t M) {  // sorted entries per accumulate thread
     uint32_t chunk = (uint32_t)ctx->opt_msm_chunk;
     if (chunk == 0) {
-        // about 2048 threads per SM, at most 256 pairs each; then shrink the chunk so that the grid is a whole
-        // number of waves of resident threads (threads take equal time, a nearly empty last wave costs a full one:
-        // 2^20: 44 -> 36..45 pairs 7.41 -> 7.25 ms, 2^24: 256 -> 242 pairs 84.2 -> 83.6 ms)
+        // about 2048 threads per SM, at most 256 entries each; then shrink the chunk so that the grid is a whole
+        // number of waves of resident threads (threads take equal time, a nearly empty last wave costs a full one)
         size_t target = M / ((size_t)ctx->sm_count * 2048);
         target = target < 16 ? 16 : (target > 256 ? 256 : target);
         const size_t resident = (size_t)ctx->sm_count * BPK_ACC_MINBLOCKS * 128;
@@ -582,115 +930,190 @@ static uint32_t msm_chunk(bpk_ctx* ctx, size_t M) {  // sorted pairs per accumul
     return chunk;
 }
 
-// grow the per-MSM workspaces for `n` pairs up front (growing later would synchronise the stream)
-static int msm_reserve(bpk_ctx* ctx, const MsmPlan& pl, size_t n) {
-    const size_t M = (size_t)pl.W * n;
-    void* p;
-    BPK_TRY(ws_reserve(ctx, 2, 4 * M * sizeof(uint32_t), &p));
-    int end_bit = 1;
-    while (((uint64_t)1 << end_bit) <= pl.nb_total) end_bit++;
-    size_t sort_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint32_t*)p, (uint32_t*)p, (uint32_t*)p, (uint32_t*)p, (int)M, 0,
-                                    end_bit, ctx->stream);
-    BPK_TRY(ws_reserve(ctx, 3, sort_bytes, &p));
-    const uint32_t chunk = msm_chunk(ctx, M);
-    const size_t num_chunks = (M + chunk - 1) / chunk;
-    BPK_TRY(ws_reserve(ctx, 5, 2 * num_chunks * (sizeof(xyzz_t) + sizeof(uint32_t)), &p));
-    BPK_TRY(ws_reserve(ctx, 11, 2 * (num_chunks / MERGE_SERIAL_MAX + 2) * sizeof(LongRun) + 16, &p));
+// ---- workspace of one bucket fill ----
+struct MsmWork {
+    size_t M;                 // upper bound of the entries (W n)
+    uint32_t nb, nblk;
+    int L;
+    uint32_t *cnt0, *cursor, *off, *blocksums, *totals;
+    unsigned long long* stats;
+    uint2* kv0;
+    uint32_t* keys_lvl[2];    // [odd levels, even levels >= 2]
+    affine_t* pts_lvl[2];
+    uint4* scratch;
+    uint32_t aff_threads, bmax;
+    size_t tail_ub;           // upper bound of the tail list
+    uint32_t chunk;
+    size_t num_chunks;
+    uint32_t* pkeys;
+    xyzz_t* pvals;
+    LongRun *long_runs, *warp_runs;
+    uint32_t *long_count, *warp_count;
+};
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+// reserves (grow-only) and carves the buffers; growing later would synchronise the stream, so callers that run
+// several fills back to back reserve for the largest first
+static int msm_workspace(bpk_ctx* ctx, const MsmPlan& pl, size_t n, MsmWork* w) {
+    w->M = (size_t)pl.W * n;
+    w->nb = pl.nb_total;
+    w->nblk = (w->nb + SCAN_TILE - 1) / SCAN_TILE;
+    w->L = pl.L;
+    const int L = pl.L;
+    {   // tables
+        const size_t b_cnt = align256((size_t)w->nb * 4), b_off = align256((size_t)(L + 1) * w->nb * 4);
+        const size_t b_sums = align256((size_t)(L + 1) * w->nblk * 4), b_tot = 256, b_stats = 256;
+        char* base;
+        BPK_TRY(ws_reserve(ctx, 3, 2 * b_cnt + b_off + b_sums + b_tot + b_stats, (void**)&base));
+        w->cnt0 = (uint32_t*)base;
+        w->cursor = (uint32_t*)(base + b_cnt);
+        w->off = (uint32_t*)(base + 2 * b_cnt);
+        w->blocksums = (uint32_t*)(base + 2 * b_cnt + b_off);
+        w->totals = (uint32_t*)(base + 2 * b_cnt + b_off + b_sums);
+        w->stats = (unsigned long long*)(base + 2 * b_cnt + b_off + b_sums + b_tot);
+    }
+    BPK_TRY(ws_reserve(ctx, 2, (level_ub(w->M, w->nb, 0) + 2) * sizeof(uint2), (void**)&w->kv0));
+    w->keys_lvl[0] = w->keys_lvl[1] = nullptr;
+    w->pts_lvl[0] = w->pts_lvl[1] = nullptr;
+    w->scratch = nullptr;
+    w->aff_threads = (uint32_t)ctx->sm_count * BPK_AFF_MINBLOCKS * 128;
+    w->bmax = (uint32_t)(ctx->opt_msm_batch < 1 ? 1 : ctx->opt_msm_batch);
+    if (L >= 1) {
+        const size_t u1 = level_ub(w->M, w->nb, 1) + 2, u2 = L >= 2 ? level_ub(w->M, w->nb, 2) + 2 : 0;
+        char* base;
+        BPK_TRY(ws_reserve(ctx, 16, align256(u1 * 4) + align256(u2 * 4), (void**)&base));
+        w->keys_lvl[0] = (uint32_t*)base;
+        w->keys_lvl[1] = (uint32_t*)(base + align256(u1 * 4));
+        BPK_TRY(ws_reserve(ctx, 17, u1 * sizeof(affine_t), (void**)&w->pts_lvl[0]));
+        if (u2) BPK_TRY(ws_reserve(ctx, 18, u2 * sizeof(affine_t), (void**)&w->pts_lvl[1]));
+        // batches never exceed what one round over the largest level needs
+        const size_t pairs0 = level_ub(w->M, w->nb, 0) / 2;
+        size_t need = (pairs0 + w->aff_threads - 1) / w->aff_threads;
+        if (need < w->bmax) w->bmax = (uint32_t)(need < 1 ? 1 : need);
+        BPK_TRY(ws_reserve(ctx, 19, (size_t)w->bmax * 3 * w->aff_threads * sizeof(uint4), (void**)&w->scratch));
+    }
+    w->tail_ub = L == 0 ? w->M : level_ub(w->M, w->nb, L);
+    w->chunk = msm_chunk(ctx, w->tail_ub);
+    w->num_chunks = (w->tail_ub + w->chunk - 1) / w->chunk;
+    {
+        char* base;
+        const size_t pv_bytes = 2 * w->num_chunks * sizeof(xyzz_t);
+        BPK_TRY(ws_reserve(ctx, 5, pv_bytes + 2 * w->num_chunks * sizeof(uint32_t), (void**)&base));
+        w->pvals = (xyzz_t*)base;
+        w->pkeys = (uint32_t*)(base + pv_bytes);
+    }
+    {
+        char* base;
+        const size_t cap = w->num_chunks / MERGE_SERIAL_MAX + 2;  // a queued run covers > MERGE_SERIAL_MAX chunks
+        BPK_TRY(ws_reserve(ctx, 11, 2 * cap * sizeof(LongRun) + 16, (void**)&base));
+        w->long_count = (uint32_t*)base;
+        w->warp_count = w->long_count + 1;
+        w->long_runs = (LongRun*)(base + 16);
+        w->warp_runs = w->long_runs + cap;
+    }
     return BPK_OK;
 }
 
-// phase 1: recode, sort, accumulate, merge: `buckets` (nb_total entries) receives the bucket sums of the n pairs
+template <bool LEVEL0>
+static int msm_launch_tail(bpk_ctx* ctx, const MsmWork& w, const TailSrc& src, xyzz_t* buckets) {
+    const unsigned grid = (unsigned)((w.num_chunks + 127) / 128);
+    msm_accumulate_kernel<LEVEL0><<<grid, 128, 0, ctx->stream>>>(src, w.chunk, w.num_chunks, buckets, w.pkeys, w.pvals);
+    msm_merge_partials_kernel<LEVEL0><<<grid, 128, 0, ctx->stream>>>(w.pkeys, w.pvals, w.num_chunks, buckets, src, w.chunk,
+                                                                    w.long_runs, w.long_count, w.warp_runs, w.warp_count);
+    msm_merge_warp_runs_kernel<<<(unsigned)ctx->sm_count * 4, 128, 0, ctx->stream>>>(w.warp_runs, w.warp_count, w.pvals,
+                                                                                     buckets);
+    msm_merge_long_runs_kernel<<<(unsigned)ctx->sm_count * 2, MERGE_BLOCK, 0, ctx->stream>>>(w.long_runs, w.long_count,
+                                                                                          w.pvals, buckets);
+    count_launch(ctx, 4);
+    BPK_CUDA(cudaGetLastError());
+    return BPK_OK;
+}
+
+// phase 1: count, layout, scatter, affine tree, tail: `buckets` (nb_total entries) receives the bucket sums of the n pairs
 static int msm_fill_buckets(bpk_ctx* ctx, const MsmPlan& pl, const MsmPoints& pts, const fr_t* d_scalars, size_t n,
                             unsigned rshift, xyzz_t* buckets) {
-    const affine_t* d_points = pts.base;
-    const bool pre = pl.pre;
-    const uint32_t c = pl.c, W = pl.W, half = pl.half, nb_total = pl.nb_total;
-    const size_t M = (size_t)W * n;
+    MsmWork w;
+    BPK_TRY(msm_workspace(ctx, pl, n, &w));
+    const int L = pl.L;
+    ctx->last_c = pl.c;
+    ctx->last_W = pl.W;
+    ctx->last_chunk = w.chunk;
+    ctx->last_buckets = pl.nb_total;
+    ctx->last_levels = (unsigned)L;
+    ctx->last_batch = w.bmax;
+    ctx->last_stats_dev = w.stats;
 
-    // workspace carve-up
-    uint32_t *keys_in, *vals_in, *keys_out, *vals_out;
+    RecodeArgs ra;
+    ra.scalars = d_scalars;
+    ra.n = (uint32_t)n;
+    ra.c = pl.c;
+    ra.W = pl.W;
+    ra.rshift = rshift;
+    ra.key_stride = pl.pre ? 0u : pl.half;
+    ra.val_stride = pl.pre ? (uint32_t)pts.level_stride : 0u;
+    const unsigned rgrid = (unsigned)((n + 255) / 256);
     {
-        void* base;
-        BPK_TRY(ws_reserve(ctx, 2, 4 * M * sizeof(uint32_t), &base));
-        keys_in = (uint32_t*)base;
-        vals_in = keys_in + M;
-        keys_out = vals_in + M;
-        vals_out = keys_out + M;
-    }
-    int end_bit = 1;
-    while (((uint64_t)1 << end_bit) <= nb_total) end_bit++;  // INVALID keys only need to sort last
-    // INVALID_KEY = 0xffffffff has all low bits set, so within end_bit bits it is >= every valid key
-    size_t sort_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_in, keys_out, vals_in, vals_out, (int)M, 0, end_bit,
-                                    ctx->stream);
-    void* sort_tmp;
-    BPK_TRY(ws_reserve(ctx, 3, sort_bytes, &sort_tmp));
-
-    const uint32_t chunk = msm_chunk(ctx, M);
-    const size_t num_chunks = (M + chunk - 1) / chunk;
-    ctx->last_c = c;
-    ctx->last_W = W;
-    ctx->last_chunk = chunk;
-    ctx->last_buckets = nb_total;
-
-    uint32_t* pkeys;
-    xyzz_t* pvals;
-    {
-        void* base;
-        size_t pv_bytes = 2 * num_chunks * sizeof(xyzz_t);
-        BPK_TRY(ws_reserve(ctx, 5, pv_bytes + 2 * num_chunks * sizeof(uint32_t), &base));
-        pvals = (xyzz_t*)base;
-        pkeys = (uint32_t*)((char*)base + pv_bytes);
-    }
-
-    {
-        StageTimer t(ctx, "msm.recode");
-        msm_recode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
-            d_scalars, (uint32_t)n, c, W, rshift, pre ? 0u : half, pre ? (uint32_t)pts.level_stride : 0u, keys_in, vals_in);
+        StageTimer t(ctx, "msm.recode");  // digits + histogram
+        BPK_CUDA(cudaMemsetAsync(w.cnt0, 0, (size_t)w.nb * 4, ctx->stream));
+        BPK_CUDA(cudaMemsetAsync(w.stats, 0, 32, ctx->stream));
+        msm_count_kernel<<<rgrid, 256, 0, ctx->stream>>>(ra, w.cnt0);
         count_launch(ctx);
         BPK_CUDA(cudaGetLastError());
         t.end();
     }
     {
-        StageTimer t(ctx, "msm.sort");
-        cudaError_t e = cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys_in, keys_out, vals_in, vals_out,
-                                                        (int)M, 0, end_bit, ctx->stream);
-        BPK_CUDA(e);
-        count_launch(ctx, 1 + (uint64_t)((end_bit + 7) / 8));
+        StageTimer t(ctx, "msm.sort");  // layout scan + scatter
+        msm_level_sums_kernel<<<w.nblk, SCAN_THREADS, 0, ctx->stream>>>(w.cnt0, w.nb, L, w.nblk, w.blocksums, w.stats);
+        msm_level_scan_kernel<<<L + 1, 1024, 0, ctx->stream>>>(w.blocksums, w.nblk, w.totals);
+        msm_level_offsets_kernel<<<w.nblk, SCAN_THREADS, 0, ctx->stream>>>(w.cnt0, w.nb, L, w.nblk, w.blocksums, w.off,
+                                                                        w.cursor, w.kv0);
+        msm_scatter_kernel<<<rgrid, 256, 0, ctx->stream>>>(ra, w.cursor, w.kv0);
+        count_launch(ctx, 4);
+        BPK_CUDA(cudaGetLastError());
         t.end();
     }
     {
         StageTimer t(ctx, "msm.accumulate");
-        BPK_CUDA(cudaMemsetAsync(buckets, 0, (size_t)nb_total * sizeof(xyzz_t), ctx->stream));
-        msm_accumulate_kernel<<<(unsigned)((num_chunks + 127) / 128), 128, 0, ctx->stream>>>(
-            keys_out, vals_out, M, chunk, num_chunks, d_points, nb_total, buckets, pkeys, pvals);
-        count_launch(ctx);
+        BPK_CUDA(cudaMemsetAsync(buckets, 0, (size_t)w.nb * sizeof(xyzz_t), ctx->stream));
+        for (int l = 0; l < L; l++) {
+            AffLevelArgs a;
+            a.kv0 = w.kv0;
+            a.keys_in = l == 0 ? nullptr : w.keys_lvl[(l & 1) ? 0 : 1];
+            a.pts_in = l == 0 ? pts.base : w.pts_lvl[(l & 1) ? 0 : 1];
+            a.keys_out = w.keys_lvl[((l + 1) & 1) ? 0 : 1];
+            a.pts_out = w.pts_lvl[((l + 1) & 1) ? 0 : 1];
+            a.cnt0 = w.cnt0;
+            a.off_in = w.off + (size_t)l * w.nb;
+            a.off_out = w.off + (size_t)(l + 1) * w.nb;
+            a.totals = w.totals;
+            a.buckets = buckets;
+            a.scratch = w.scratch;
+            a.level = (uint32_t)l;
+            a.bmax = w.bmax;
+            a.out_is_tail = l + 1 == L ? 1u : 0u;
+            const unsigned grid = w.aff_threads / 128;
+            if (l == 0)
+                msm_affine_level_kernel<true><<<grid, 128, 0, ctx->stream>>>(a);
+            else
+                msm_affine_level_kernel<false><<<grid, 128, 0, ctx->stream>>>(a);
+            count_launch(ctx);
+        }
         BPK_CUDA(cudaGetLastError());
         t.end();
     }
     {
-        StageTimer t(ctx, "msm.merge");
-        LongRun *long_runs, *warp_runs;
-        uint32_t *long_count, *warp_count;
-        {
-            void* base;
-            const size_t cap = num_chunks / MERGE_SERIAL_MAX + 2;  // a queued run covers > MERGE_SERIAL_MAX chunks
-            BPK_TRY(ws_reserve(ctx, 11, 2 * cap * sizeof(LongRun) + 16, &base));
-            long_count = (uint32_t*)base;
-            warp_count = long_count + 1;
-            long_runs = (LongRun*)((char*)base + 16);
-            warp_runs = long_runs + cap;
-        }
-        BPK_CUDA(cudaMemsetAsync(long_count, 0, 2 * sizeof(uint32_t), ctx->stream));
-        msm_merge_partials_kernel<<<(unsigned)((num_chunks + 127) / 128), 128, 0, ctx->stream>>>(
-            pkeys, pvals, num_chunks, buckets, keys_out, chunk, long_runs, long_count, warp_runs, warp_count);
-        msm_merge_warp_runs_kernel<<<(unsigned)ctx->sm_count * 4, 128, 0, ctx->stream>>>(warp_runs, warp_count, pvals,
-                                                                                         buckets);
-        msm_merge_long_runs_kernel<<<(unsigned)ctx->sm_count * 2, MERGE_BLOCK, 0, ctx->stream>>>(long_runs, long_count,
-                                                                                              pvals, buckets);
-        count_launch(ctx, 3);
-        BPK_CUDA(cudaGetLastError());
+        StageTimer t(ctx, "msm.merge");  // XYZZ tail of the tree + merge of the chunk partials
+        BPK_CUDA(cudaMemsetAsync(w.long_count, 0, 2 * sizeof(uint32_t), ctx->stream));
+        TailSrc src;
+        src.kv0 = L == 0 ? w.kv0 : nullptr;
+        src.keys = L == 0 ? nullptr : w.keys_lvl[(L & 1) ? 0 : 1];
+        src.pts = L == 0 ? pts.base : w.pts_lvl[(L & 1) ? 0 : 1];
+        src.total = w.totals + L;
+        if (L == 0)
+            BPK_TRY(msm_launch_tail<true>(ctx, w, src, buckets));
+        else
+            BPK_TRY(msm_launch_tail<false>(ctx, w, src, buckets));
         t.end();
     }
     return BPK_OK;
@@ -710,85 +1133,44 @@ __global__ void __launch_bounds__(128, 3) msm_add_buckets_kernel(xyzz_t* __restr
 
 // phase 2: bucket reduction + window Horner + output
 static int msm_reduce_buckets(bpk_ctx* ctx, const MsmPlan& pl, xyzz_t* buckets, bool normalise, uint64_t* d_out) {
-    const uint32_t c = pl.c, W = pl.W, half = pl.half, WB = pl.WB;
-    if (ctx->opt_msm_reduce == 0) {
-        // bit-plane reduction (see K4): one tree whose nodes carry the plane sums, then Horner over the planes
-        const uint32_t L = c - 1;  // half == 1 << L
-        // ping-pong level buffers: level k holds WB * (half >> k) * (k + 1) points, largest at k = 1 and k = 2
-        const size_t buf_a = (size_t)WB * half;                    // odd levels  (k = 1: WB * half points)
-        const size_t buf_b = (size_t)WB * (half / 4 + 1) * 3;      // even levels (k = 2: 3/4 WB * half points)
-        xyzz_t* lvl;
-        BPK_TRY(ws_reserve(ctx, 6, (buf_a + buf_b + 1) * sizeof(xyzz_t), (void**)&lvl));
-        const xyzz_t* roots = buckets;  // L == 0: the single bucket of each window is its own root
-        {
-            StageTimer t(ctx, "msm.reduce");
-            const xyzz_t* in = buckets;
-            for (uint32_t k = 1; k <= L; k++) {
-                xyzz_t* out = (k & 1) ? lvl : lvl + buf_a;
-                const size_t nodes = (size_t)WB * (half >> k);
-                const size_t threads = nodes * (k + 1);
-                msm_plane_tree_level_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(in, out, k, nodes);
-                count_launch(ctx);
-                in = out;
-            }
-            roots = in;
-            BPK_CUDA(cudaGetLastError());
-            t.end();
-        }
-        {
-            StageTimer t(ctx, "msm.finalize");
-            uint32_t groups = (L + FIN_GROUP - 1) / FIN_GROUP;
-            if (groups == 0 || WB * groups > 128) groups = 1;
-            msm_finalize_planes_kernel<<<1, 128, 0, ctx->stream>>>(roots, WB, L, c, groups, normalise ? 1 : 0, d_out);
-            count_launch(ctx);
-            BPK_CUDA(cudaGetLastError());
-            t.end();
-        }
-        return BPK_OK;
-    }
-    // reduction tree: fold `fanin` items per thread per level (serial depth 3 x fanin additions per level)
-    const uint32_t W_h = W;  // (window count of the Horner pass is WB below)
-    (void)W_h;
-    uint32_t fanin = (uint32_t)ctx->opt_msm_fanin;
-    if (fanin < 2 || fanin > 32 || (fanin & (fanin - 1))) fanin = 8;
-    const xyzz_t* A = buckets;
-    const xyzz_t* V = nullptr;
+    const uint32_t c = pl.c, half = pl.half, WB = pl.WB;
+    // bit-plane reduction (see K6): one tree whose nodes carry the plane sums, then Horner over the planes
+    const uint32_t L = c - 1;  // half == 1 << L
+    // ping-pong level buffers: level k holds WB * (half >> k) * (k + 1) points, largest at k = 1 and k = 2
+    const size_t buf_a = (size_t)WB * half + TREE_TOP_THREADS;                    // odd levels  (k = 1: WB * half points)
+    const size_t buf_b = (size_t)WB * (half / 4 + 1) * 3 + TREE_TOP_THREADS;      // even levels (k = 2: 3/4 WB * half points)
+    xyzz_t* lvl;
+    BPK_TRY(ws_reserve(ctx, 6, (buf_a + buf_b + 1) * sizeof(xyzz_t), (void**)&lvl));
+    const xyzz_t* roots = buckets;  // L == 0: the single bucket of each window is its own root
     {
         StageTimer t(ctx, "msm.reduce");
-        xyzz_t* lvl;
-        // level outputs: items/32 (+ /1024 + ...) per window, A and V each; 2 * nb_total/16 is ample
-        size_t lvl_elems = (size_t)WB * (half + 64);
-        BPK_TRY(ws_reserve(ctx, 6, 2 * lvl_elems * sizeof(xyzz_t), (void**)&lvl));
-        uint32_t items = half;
-        uint32_t dbls = 0;
-        size_t off = 0;
-        while (items > 1) {
-            uint32_t S = items >= fanin ? fanin : items;
-            uint32_t groups = items / S;
-            xyzz_t* A2 = lvl + off;
-            xyzz_t* V2 = lvl + off + (size_t)WB * groups;
-            off += 2 * (size_t)WB * groups;
-            uint32_t threads = WB * groups;
-            msm_reduce_level_kernel<<<(threads + 127) / 128, 128, 0, ctx->stream>>>(A, V, A2, V2, items, S, WB, dbls);
+        const xyzz_t* in = buckets;
+        uint32_t k = 1;
+        for (; k <= L; k++) {
+            const size_t nodes = (size_t)WB * (half >> k);
+            const size_t threads = nodes * (k + 1);
+            // every later level is narrower still (nodes halve, slots grow by one): finish in one block
+            if (ctx->opt_msm_tree_top && threads <= TREE_TOP_THREADS) break;
+            xyzz_t* out = (k & 1) ? lvl : lvl + buf_a;
+            msm_plane_tree_level_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(in, out, k, nodes);
             count_launch(ctx);
-            BPK_CUDA(cudaGetLastError());
-            A = A2;
-            V = V2;
-            uint32_t logS = 0;
-            while ((1u << logS) < S) logS++;
-            dbls += logS;
-            items = groups;
+            in = out;
         }
-        if (V == nullptr) {  // c == 1: a single bucket per window, weight 1, no tree level ran
-            xyzz_t* z = lvl + off;
-            BPK_CUDA(cudaMemsetAsync(z, 0, (size_t)WB * sizeof(xyzz_t), ctx->stream));
-            V = z;
+        if (k <= L) {
+            msm_plane_tree_top_kernel<<<1, TREE_TOP_THREADS, 0, ctx->stream>>>(in, lvl, lvl + buf_a, k, L,
+                                                                                (size_t)WB * (half >> k));
+            count_launch(ctx);
+            in = (L & 1) ? lvl : lvl + buf_a;
         }
+        roots = in;
+        BPK_CUDA(cudaGetLastError());
         t.end();
     }
     {
         StageTimer t(ctx, "msm.finalize");
-        msm_finalize_kernel<<<1, 1, 0, ctx->stream>>>(A, V, WB, c, normalise ? 1 : 0, d_out);
+        uint32_t groups = (L + FIN_GROUP - 1) / FIN_GROUP;
+        if (groups == 0 || WB * groups > 128) groups = 1;
+        msm_finalize_planes_kernel<<<1, 128, 0, ctx->stream>>>(roots, WB, L, c, groups, normalise ? 1 : 0, d_out);
         count_launch(ctx);
         BPK_CUDA(cudaGetLastError());
         t.end();
@@ -820,12 +1202,16 @@ int msm_run_from_host(bpk_ctx* ctx, const MsmPoints& pts, const uint64_t* h_scal
         if (n) BPK_CUDA(cudaMemcpyAsync(d_stage, h_scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
         return msm_run(ctx, pts, d_stage, n, rshift, normalise, d_out);
     }
+    // both slices use the geometry (window, tree depth) of the larger one, and its workspace
     MsmPlan pl;
-    BPK_TRY(msm_make_plan(ctx, pts, n, &pl));
+    BPK_TRY(msm_make_plan(ctx, pts, n - head, &pl));
     xyzz_t *buckets, *buckets_b;
     BPK_TRY(ws_reserve(ctx, 4, (size_t)pl.nb_total * sizeof(xyzz_t), (void**)&buckets));
     BPK_TRY(ws_reserve(ctx, 15, (size_t)pl.nb_total * sizeof(xyzz_t), (void**)&buckets_b));
-    BPK_TRY(msm_reserve(ctx, pl, n - head));
+    {
+        MsmWork w;
+        BPK_TRY(msm_workspace(ctx, pl, n - head, &w));
+    }
     if (!ctx->copy_stream) BPK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (!ctx->copy_done) BPK_CUDA(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
     if (!ctx->lane_fork) BPK_CUDA(cudaEventCreateWithFlags(&ctx->lane_fork, cudaEventDisableTiming));
@@ -854,10 +1240,19 @@ int msm_run_from_host(bpk_ctx* ctx, const MsmPoints& pts, const uint64_t* h_scal
 
 int g1_sum_run(bpk_ctx* ctx, const uint64_t* d_points_xyz, size_t n, uint64_t* d_out_xyz) {
     StageTimer t(ctx, "g1.sum");
-    g1_sum_kernel<<<1, 1, 0, ctx->stream>>>(d_points_xyz, (uint32_t)n, d_out_xyz);
+    g1_sum_kernel<<<1, 32, 0, ctx->stream>>>(d_points_xyz, (uint32_t)n, d_out_xyz);
     count_launch(ctx);
     BPK_CUDA(cudaGetLastError());
     t.end();
+    return BPK_OK;
+}
+
+// counters of the most recent bucket fill: {entries, entries left to the XYZZ tail, non-empty buckets, 0}
+int msm_read_stats(bpk_ctx* ctx, uint64_t out[4]) {
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (!ctx->last_stats_dev) return BPK_OK;
+    BPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    BPK_CUDA(cudaMemcpy(out, ctx->last_stats_dev, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return BPK_OK;
 }
 

@@ -57,19 +57,26 @@ def sharded_msm(partial, sum_points: Callable, group=None):
 class ShardedCommitter:
     """Per-rank state of a sharded KZG commitment: SRS slice on this GPU + reusable device buffers."""
 
-    def __init__(self, pkg, ctx, n_total: int, tau: int, rank: int, world_size: int, group=None, precompute=0):
+    def __init__(self, pkg, ctx, n_total: int, tau: int, rank: int, world_size: int, group=None, precompute=0,
+                 n_global=None):
         import torch
 
         self.pkg, self.ctx, self.group = pkg, ctx, group
         self.rank, self.world = rank, world_size
+        self.n_total = n_total
         self.lo, self.hi = shard_bounds(n_total, world_size, rank)
         self.setup = pkg.Setup.generate_srs(self.hi - self.lo, tau, ctx, first=self.lo)
         if precompute is not None:  # window bits, 0 = auto
-            self.setup.precompute(precompute)
+            self.precompute(precompute)
         self.device = torch.device("cuda", ctx.device)
         self.d_partial = torch.zeros(18, dtype=torch.int64, device=self.device)
         self.d_out = torch.zeros(18, dtype=torch.int64, device=self.device)
         self.d_gather = torch.zeros((world_size, 18), dtype=torch.int64, device=self.device)
+
+    def precompute(self, window_bits: int = 0):
+        """window levels next to this rank's SRS slice (Setup.precompute); 0 = the library's choice for the slice"""
+        self.setup.precompute(window_bits)
+        return self
 
     def commit_device(self, d_scalars) -> "torch.Tensor":
         """d_scalars: int64 tensor holding this rank's (hi - lo) x 4 u64 Montgomery limbs in HBM.

@@ -16,7 +16,11 @@
  * (g1.rs:479-496), so Rust-side `==`, the transcript bytes and the verifier see no difference.
  *
  * Ownership: the caller owns every buffer; the library never keeps a host pointer after return.
- * Threading: calls on one context are serialised by the caller (the reference is single-threaded).
+ * Threading: every entry point takes the context's own lock for its whole duration, so calls on one context from
+ * several threads (e.g. `cargo test`, which runs the reference's tests in parallel) are serialised by the library;
+ * distinct contexts may be used concurrently.  bpk_destroy must not race with other calls on the same context.
+ * Field elements handed over as scalars (tau, coset shifts, evaluation points) must be canonical (< modulus),
+ * otherwise BPK_ERR_INVALID_ARG; coordinates of points are not validated (garbage in, garbage out, but no call hangs).
  * Errors: every function returns 0 on success or a negative bpk_status; nothing throws or aborts.
  * The Rust shim turns a non-zero status into `panic!`, preserving the reference's error behaviour.
  * There is no CPU fallback: without a CUDA device bpk_init fails with BPK_ERR_NO_DEVICE.
@@ -71,6 +75,8 @@ int bpk_srs_precompute(bpk_ctx* ctx, uint64_t handle, unsigned window_bits);
 /* Read points [first, first+count) back as normalised G1Projective limbs. */
 int bpk_srs_read(bpk_ctx* ctx, uint64_t handle, size_t first, size_t count, uint64_t* out_xyz);
 int bpk_srs_len(bpk_ctx* ctx, uint64_t handle, size_t* n_out);
+/* HBM bytes the handle's point table occupies (the SRS, or W x that after bpk_srs_precompute). */
+int bpk_srs_table_bytes(bpk_ctx* ctx, uint64_t handle, size_t* bytes_out);
 int bpk_srs_free(bpk_ctx* ctx, uint64_t handle);
 
 /* ---- MSM ------------------------------------------------------------------------------------ */
@@ -206,11 +212,18 @@ int bpk_profile_get(bpk_ctx* ctx, const char* name, double* ms_out, uint64_t* la
 uint64_t bpk_launch_count(bpk_ctx* ctx);
 /* Plan of the most recent MSM: {window bits c, windows W, pairs per accumulate thread, buckets}. */
 int bpk_msm_last_plan(bpk_ctx* ctx, unsigned out[4]);
+/* Counters of the most recent MSM (synchronises the stream): {entries = non-zero digits, additions done in affine
+ * coordinates by the pairwise tree, additions left to the XYZZ tail, non-empty buckets, tree levels launched,
+ * additions per shared inversion}. */
+int bpk_msm_last_stats(bpk_ctx* ctx, uint64_t out[6]);
 /* Register-only IMAD.WIDE throughput probe: returns 32x32+64 multiply-adds per second. */
 int bpk_imad_peak(bpk_ctx* ctx, double* wide_imad_per_s_out, double* seconds_out);
 /* Tunables (A/B measurements and tests; the defaults are the measured optima):
  *   "msm.window" window bits of the non-precomputed MSM (0 = auto), "msm.chunk" pairs per accumulate thread (0 = auto),
- *   "msm.reduce" 0 = bit-plane bucket reduction, 1 = fan-in running-sum tree ("msm.fanin" 2..32),
+ *   "msm.affine_levels" levels of the batched-affine pairwise tree (-1 = from the expected bucket load, 0 = XYZZ chunks only),
+ *   "msm.min_pairs" a tree level expected to hold fewer pairs is left to the XYZZ tail, "msm.batch" additions per shared
+ *   inversion, "msm.level_mib" memory budget of the tree's level buffers, "msm.tree_top" 0 = one launch per level of the
+ *   bucket-reduction tree,
  *   "msm.lanes" 1..3 concurrent MSMs of bpk_msm_g1_dev_batch, "msm.host_slices" 0 = no upload / compute overlap,
  *   "ntt.tile_log2" log2 of the R x C tile per CTA (default 10), "ntt.max_radix_log2" (0 = auto), "ntt.threads",
  *   "ntt.kernel" 0 = auto, 1 = one radix-2 stage per barrier, 2 = register-blocked radix-8 steps, 3 = 4 rows per

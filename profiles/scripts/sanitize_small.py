@@ -29,9 +29,9 @@ n = 3000
 setup = bpk.Setup.generate_srs(n, 101, ctx)
 sc = scalars(n)
 ref = setup.commit_scalars(sc)
-ctx.set_option("msm.reduce", 1)
+ctx.set_option("msm.affine_levels", 3)
 assert np.array_equal(setup.commit_scalars(sc), ref)
-ctx.set_option("msm.reduce", 0)
+ctx.set_option("msm.affine_levels", -1)
 setup.precompute(0)
 assert np.array_equal(setup.commit_scalars(sc), ref)
 import ctypes

@@ -32,16 +32,11 @@ template <class F> static int run_field(const std::string& op, std::istringstrea
     F r;
     if (op == "mul") r = mul(a, b);
     else if (op == "mulcc") r = mul_cc(a, b);
-    else if (op == "mulrr") r = mul_rr(a, b);
-    else if (op == "mulsplit1") r = mul_cc<typename std::remove_reference<decltype(a)>::type::params, 1>(a, b);
-    else if (op == "mulsplit3") r = mul_cc<typename std::remove_reference<decltype(a)>::type::params, 3>(a, b);
-    else if (op == "mulsplit7") r = mul_cc<typename std::remove_reference<decltype(a)>::type::params, 7>(a, b);
     else if (op == "sqr") r = sqr(a);
     else if (op == "add") r = add(a, b);
     else if (op == "sub") r = sub(a, b);
     else if (op == "neg") r = neg(a);
     else if (op == "inv") r = inv(a);
-    else if (op == "invf") r = inv_fermat(a);
     else if (op == "from_mont") r = from_mont(a);
     else if (op == "to_mont") r = to_mont(a);
     else return 1;
@@ -78,6 +73,13 @@ int main() {
             } else if (op == "to_affine") {
                 xyzz_t p = parse_xyzz(ss); affine_t q = xyzz_to_affine(p);
                 show(q.x); printf(" "); show(q.y); printf("\n");
+            } else if (op == "aff_add") {    // batched-affine addition of one pair: prepare, invert, finish
+                std::string a, b, c, d; ss >> a >> b >> c >> d;
+                affine_t p, q; p.x = parse<fp_t>(a); p.y = parse<fp_t>(b); q.x = parse<fp_t>(c); q.y = parse<fp_t>(d);
+                fp_t den;
+                int kind = affine_add_prepare(p, q, den);
+                affine_t r = affine_add_finish(kind, p, q, inv(den));
+                printf("%d ", kind); show(r.x); printf(" "); show(r.y); printf("\n");
             } else if (op == "proj_to_affine") {
                 std::string a, b, c; ss >> a >> b >> c;
                 affine_t q = proj_to_affine(parse<fp_t>(a), parse<fp_t>(b), parse<fp_t>(c));

@@ -444,22 +444,86 @@ def test_msm_precomputed_degenerate_points(ctx):
     s.free()
 
 
-@pytest.mark.parametrize("fanin", [2, 4, 8, 32])
-def test_msm_reduce_fanin(ctx, fanin):
-    n = 2000
+class options:
+    """set library tunables for a block, restore the defaults afterwards"""
+    DEFAULTS = {"msm.affine_levels": -1, "msm.batch": 256, "msm.min_pairs": 1 << 16, "msm.window": 0, "msm.chunk": 0,
+                "msm.tree_top": 1, "msm.level_mib": 48 << 10}
+
+    def __init__(self, ctx, **kw):
+        self.ctx, self.kw = ctx, {k.replace("_", ".", 1): v for k, v in kw.items()}
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            self.ctx.set_option(k, v)
+
+    def __exit__(self, *exc):
+        for k in self.kw:
+            self.ctx.set_option(k, self.DEFAULTS[k])
+
+
+@pytest.mark.parametrize("levels", [0, 1, 2, 3, 5, 9, 14, 29])
+@pytest.mark.parametrize("batch", [1, 3, 256])
+def test_msm_affine_tree_levels_and_batches(ctx, levels, batch):
+    """the batched-affine pairwise tree with every depth (0 = XYZZ chunks only; 1..: buckets finish inside the tree or
+    leave a tail of every length; more levels than any bucket needs), batches of 1 / 3 / many additions per inversion,
+    own windows and precomputed levels (few buckets, long runs)"""
+    n = 3000
     setup = bpk.Setup.generate_srs(n, 101, ctx)
-    sc = O.random_fr(fanin, n)
-    ctx.set_option("msm.fanin", fanin)
-    ctx.set_option("msm.reduce", 1)       # the running-sum tree kept for A/B runs
-    try:
-        for w in (0, 7, 12):
-            ctx.set_option("msm.window", w)
-            assert bpk.point_to_affine(setup.commit_scalars(S(sc))) == horner_expected(sc, 101)
-    finally:
-        ctx.set_option("msm.fanin", 8)
-        ctx.set_option("msm.reduce", 0)
-        ctx.set_option("msm.window", 0)
-        setup.free()
+    sc = O.random_fr(1000 + levels * 10 + batch, n)
+    want = horner_expected(sc, 101)
+    with options(ctx, msm_affine_levels=levels, msm_batch=batch):
+        for window in (0, 5, 13):
+            with options(ctx, msm_window=window):
+                assert bpk.point_to_affine(setup.commit_scalars(S(sc))) == want, window
+        stats = ctx.msm_last_stats()
+        assert stats["tree_levels"] == levels and stats["entries"] > 0
+        assert stats["affine_adds"] + stats["xyzz_adds_bound"] + stats["nonempty_buckets"] == stats["entries"]
+        if levels == 0:
+            assert stats["affine_adds"] == 0
+        setup.precompute(8)
+        assert bpk.point_to_affine(setup.commit_scalars(S(sc))) == want
+        assert bpk.point_to_affine(setup.commit_scalars(S(sc[:1]))) == O.g1_mul(O.G1_GEN, sc[0])
+        if levels >= 12:   # 128 buckets x ~750 entries: the tree finishes every bucket, nothing is left to the tail
+            setup.commit_scalars(S(sc))
+            assert ctx.msm_last_stats()["xyzz_adds_bound"] == 0
+    setup.free()
+
+
+@pytest.mark.parametrize("levels", [1, 4, 20])
+def test_msm_affine_tree_degenerate_points(ctx, levels):
+    """every degenerate addition inside the batched-affine levels: all points equal (tau = 1: each pair is a doubling at
+    every level, src/prover.rs:684), tau = 0 (identity operands), P + (-P) pairs, opposite scalars on equal points"""
+    n = 2048
+    with options(ctx, msm_affine_levels=levels, msm_batch=5):
+        for tau in (1, 0, 2):
+            setup = bpk.Setup.generate_srs(n, tau, ctx)
+            for sc in (O.random_fr(levels + tau, n), [7] * n, [(1 if i % 2 else O.Q - 1) for i in range(n)]):
+                assert bpk.point_to_affine(setup.commit_scalars(S(sc))) == horner_expected(sc, tau), (tau, sc[:2])
+            setup.precompute(6)
+            sc = O.random_fr(77, n)
+            assert bpk.point_to_affine(setup.commit_scalars(S(sc))) == horner_expected(sc, tau)
+            setup.free()
+        G = O.G1_GEN
+        pts = ([G] * 20 + [None, O.g1_neg(G), G, None]) * 30
+        sc = O.random_fr(3, len(pts))
+        s = bpk.Setup.from_points(bpk.points_from_affine(pts), ctx)
+        assert bpk.point_to_affine(s.commit_scalars(S(sc))) == O.msm_naive(pts, sc)
+        sc = [5] * len(pts)    # one bucket holds 630 copies of G, 30 of -G and 60 identities
+        assert bpk.point_to_affine(s.commit_scalars(S(sc))) == O.msm_naive(pts, sc)
+        s.precompute(6)
+        assert bpk.point_to_affine(s.commit_scalars(S(sc))) == O.msm_naive(pts, sc)
+        s.free()
+
+
+def test_msm_tree_top_and_per_level_reduction_agree(ctx):
+    n = 5000
+    setup = bpk.Setup.generate_srs(n, 101, ctx).precompute(13)
+    sc = O.random_fr(5, n)
+    a = setup.commit_scalars(S(sc))
+    with options(ctx, msm_tree_top=0):
+        b = setup.commit_scalars(S(sc))
+    setup.free()
+    assert np.array_equal(a, b) and bpk.point_to_affine(a) == horner_expected(sc, 101)
 
 
 @pytest.mark.parametrize("window", [2, 3, 5, 11, 12, 13, 16])
@@ -498,8 +562,12 @@ def test_msm_skewed_distributions(ctx, dist):
         sc = [rng.choice([12345, O.Q - 12345]) for _ in range(n)]
     setup = bpk.Setup.generate_srs(n, 101, ctx)
     got = setup.commit_scalars(S(sc))
+    want = horner_expected(sc, 101)
+    assert bpk.point_to_affine(got) == want
+    for levels in (3, 16):     # heavy buckets inside the batched-affine tree, with and without a tail
+        with options(ctx, msm_affine_levels=levels):
+            assert bpk.point_to_affine(setup.commit_scalars(S(sc))) == want
     setup.free()
-    assert bpk.point_to_affine(got) == horner_expected(sc, 101)
 
 
 @pytest.mark.parametrize("pre", [None, 0, 21])

@@ -48,20 +48,18 @@ def test_field_ops(exe):
         for a in vals:
             for b in rng.sample(vals, 6) + [a, mod - 1 - a if a != mod - 1 else 0]:
                 lines.append(f"{name} mul {hx(a)} {hx(b)}"); exp.append(a * b * Rinv % mod)
-                for variant in ("mulcc", "mulrr", "mulsplit1", "mulsplit3", "mulsplit7"):
-                    lines.append(f"{name} {variant} {hx(a)} {hx(b)}"); exp.append(a * b * Rinv % mod)
+                lines.append(f"{name} mulcc {hx(a)} {hx(b)}"); exp.append(a * b * Rinv % mod)
                 lines.append(f"{name} add {hx(a)} {hx(b)}"); exp.append((a + b) % mod)
                 lines.append(f"{name} sub {hx(a)} {hx(b)}"); exp.append((a - b) % mod)
             lines.append(f"{name} sqr {hx(a)}"); exp.append(a * a * Rinv % mod)
             lines.append(f"{name} neg {hx(a)}"); exp.append((-a) % mod)
             lines.append(f"{name} from_mont {hx(a)}"); exp.append(a * Rinv % mod)
             lines.append(f"{name} to_mont {hx(a)}"); exp.append(a * R % mod)
-        for a in vals[:30]:
-            # Montgomery inverse: inv(aR) = a^-1 R  ->  on raw value v: v^-1 R^2
+        # Montgomery inverse: inv(aR) = a^-1 R  ->  on raw value v: v^-1 R^2  (division-step inversion)
+        inv_vals = vals + [rng.randrange(mod) for _ in range(400)] + [1 << k for k in range(0, mod.bit_length() - 1, 7)] \
+            + [mod - (1 << k) for k in range(0, mod.bit_length() - 1, 11)] + [(mod + 1) // 2, (mod - 1) // 2, 3, mod - 3]
+        for a in inv_vals:
             lines.append(f"{name} inv {hx(a)}")
-            exp.append(pow(a, -1, mod) * R * R % mod if a else 0)
-        for a in vals[:10]:
-            lines.append(f"{name} invf {hx(a)}")
             exp.append(pow(a, -1, mod) * R * R % mod if a else 0)
     got = run(exe, lines)
     assert len(got) == len(exp)
@@ -133,6 +131,37 @@ def test_curve_ops(exe):
     for l, g, e in zip(lines, got, exp):
         x, y = (int(t, 16) * O.FP_RINV % O.P for t in g.split())
         assert ((x, y) if (x, y) != (0, 0) else None) == e, l
+
+
+def test_batched_affine_pair_addition(exe):
+    """affine_add_prepare / affine_add_finish (the per-pair halves of the batched-affine bucket additions) on every
+    case: generic, doubling, opposite points, identity operands"""
+    G = O.G1_GEN
+    pts = [None] + [O.g1_mul(G, k) for k in (1, 2, 3, 7, 1000, O.Q - 1, O.Q - 2, O.Q - 7, 98765432109876543210)]
+    kinds = {"copy_p": 0, "copy_q": 1, "add": 2, "dbl": 3, "inf": 4}
+    lines, exp = [], []
+    for a in pts:
+        for b in pts:
+            ax, ay = a if a is not None else (0, 0)
+            bx, by = b if b is not None else (0, 0)
+            lines.append(f"g1 aff_add {M(ax)} {M(ay)} {M(bx)} {M(by)}")
+            kind = "copy_p" if b is None else "copy_q" if a is None else "add" if a[0] != b[0] else \
+                "dbl" if a[1] == b[1] else "inf"
+            exp.append((kinds[kind], O.g1_add(a, b)))
+    got = run(exe, lines)
+    for l, g, (k, e) in zip(lines, got, exp):
+        t = g.split()
+        x, y = (int(v, 16) * O.FP_RINV % O.P for v in t[1:])
+        assert int(t[0]) == k, l
+        assert ((x, y) if (x, y) != (0, 0) else None) == e, l
+
+
+def test_inversion_terminates_on_non_canonical_limbs(exe):
+    """limbs >= the modulus (p, 2p, all ones) must not hang the division-step loop (the binary Euclid did)"""
+    lines = [f"fp inv {hx(O.P)}", f"fp inv {hx(2 * O.P)}", f"fp inv {hx((1 << 384) - 1)}",
+             f"fr inv {hx(O.Q)}", f"fr inv {hx(2 * O.Q)}", f"fr inv {hx((1 << 256) - 1)}"]
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, timeout=20)
+    assert out.returncode == 0 and len(out.stdout.strip().split("\n")) == len(lines)
 
 
 def test_dedicated_fp_squaring(exe):
