@@ -335,111 +335,235 @@ struct AffLevelArgs {
 #ifndef BPK_AFF_MINBLOCKS
 #define BPK_AFF_MINBLOCKS 4
 #endif
+constexpr int AFF_THREADS = 128;
+// Operand staging.  What bounds a kernel in which every lane loads its own 96-byte points is not HBM and not the
+// multiplier but the SM's single L1TEX queue: a warp-wide 16-byte load whose lanes touch 32 different lines costs 32
+// wavefronts, 6 such loads per point (profiles/r2_affine_ab.md: 64-74 % multiplier duty, and prefetching made it
+// worse).  So the warp gathers COOPERATIVELY: 6 (3 for x only) neighbouring lanes copy the 16-byte pieces of one
+// point, five (ten) points per cp.async instruction, a handful of lines each, straight into shared memory; every
+// lane then reads its own pair from there.  The copies for pair j + 1 are issued while pair j is being added.
+// Per warp: 64 points x 96 B + 32 prefix products x 48 B.
+#ifndef BPK_AFF_STAGE
+#define BPK_AFF_STAGE 1   // 0: plain per-lane loads at the point of use (A/B)
+#endif
+constexpr int AFF_WARP_SMEM = 64 * 96 + 32 * 48;                       // bytes per warp
+constexpr size_t AFF_SMEM_BYTES = BPK_AFF_STAGE ? (size_t)(AFF_THREADS / 32) * AFF_WARP_SMEM : 0;  // 30 KB per CTA
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ fp_t lds_fp(const uint4* q) {  // 48 contiguous bytes of shared memory
+    const uint4 a = q[0], b = q[1], c = q[2];
+    fp_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    r.l[8] = c.x; r.l[9] = c.y; r.l[10] = c.z; r.l[11] = c.w;
+    return r;
+}
+
 template <bool LEVEL0>
-__global__ void __launch_bounds__(128, BPK_AFF_MINBLOCKS) msm_affine_level_kernel(AffLevelArgs a) {
+__global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_level_kernel(AffLevelArgs a) {
+    extern __shared__ uint4 aff_smem[];
     const uint32_t S = a.totals[a.level] >> 1;  // pairs of this level
     if (S == 0) return;
     const uint32_t T = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
     // every thread takes batches of B pairs, interleaved with the other threads (pair = base + j T + tid): the lanes of a
-    // warp read neighbouring pairs and prefix slots; B is the smallest batch that covers the level in whole rounds
+    // warp work on 32 neighbouring pairs at every step; B is the smallest batch that covers the level in whole rounds
     const uint64_t per_round = (uint64_t)T * a.bmax;
     const uint32_t rounds = (uint32_t)((S + per_round - 1) / per_round);
     const uint32_t B = (uint32_t)((S + (uint64_t)T * rounds - 1) / ((uint64_t)T * rounds));
     uint4* const sc = a.scratch + tid;
+    // this warp's stage: 64 points of 96 bytes (pair of lane l at 192 l: P.x P.y Q.x Q.y), then [3][32] prefix pieces
+    uint4* const wstage = aff_smem + (threadIdx.x >> 5) * (AFF_WARP_SMEM / 16);
+    const uint32_t wstage_addr = (uint32_t)__cvta_generic_to_shared(wstage);
+    const uint4* const my_pair = wstage + lane * 12;
+    uint4* const pre_stage = wstage + 64 * 6 + lane;
+    const uint32_t pre_addr = wstage_addr + 64 * 96 + lane * 16;
 
-    auto load_pair = [&](uint32_t p, affine_t& P, affine_t& Q, uint32_t& key) {
-        if (LEVEL0) {
-            const uint4 e = reinterpret_cast<const uint4*>(a.kv0)[p];  // (key, val) of slots 2p and 2p + 1
-            key = e.x;
-            P = ld_affine(a.pts_in + (e.y & 0x7fffffffu));
-            if (e.y >> 31) P.y = neg(P.y);
-            if (e.z == INVALID_KEY) {
-                Q = affine_t::inf();
-            } else {
-                Q = ld_affine(a.pts_in + (e.w & 0x7fffffffu));
-                if (e.w >> 31) Q.y = neg(Q.y);
-            }
-        } else {
-            const uint2 kk = reinterpret_cast<const uint2*>(a.keys_in)[p];
-            key = kk.x;
-            P = ld_affine(a.pts_in + 2 * (size_t)p);
-            Q = kk.y == INVALID_KEY ? affine_t::inf() : ld_affine(a.pts_in + 2 * (size_t)p + 1);
-        }
+    // meta word of pair p: level 0 (key, val) of both slots; above: the two keys.  A lane without a pair at this step
+    // gets a harmless one (point 0, padded) so that it can take part in the warp's copies.
+    auto load_meta = [&](uint64_t p) -> uint4 {
+        if (p >= S) return make_uint4(0, 0, INVALID_KEY, 0);
+        if (LEVEL0) return reinterpret_cast<const uint4*>(a.kv0)[p];
+        const uint2 kk = reinterpret_cast<const uint2*>(a.keys_in)[p];
+        return make_uint4(kk.x, 0, kk.y, 0);
     };
+    auto point_of = [&](uint64_t p, const uint4& m, int which) -> const affine_t* {
+        if (LEVEL0) return a.pts_in + ((which ? m.w : m.y) & 0x7fffffffu);
+        return a.pts_in + 2 * (size_t)p + which;
+    };
+    // Cooperative copy of the operands of the warp's 32 pairs (first pair p0) into the stage.  PIECES = 3: x coordinates
+    // only; 6: whole points.  Point q of the warp (q = 2 lane' + which) goes to byte 96 q.
+    auto stage_points = [&](uint64_t p0, const uint4& m, const int PIECES) {
+        const int per = 30 / PIECES;                       // points per instruction
+        const uint32_t sub = lane / PIECES, piece = lane - sub * PIECES;
+        const uint32_t iP = m.y & 0x7fffffffu, iQ = (m.z == INVALID_KEY ? m.y : m.w) & 0x7fffffffu;
+        for (int i = 0; i * per < 64; i++) {
+            const uint32_t q = i * per + sub;
+            const bool on = lane < 30 && q < 64;
+            const affine_t* src;
+            if (LEVEL0) {
+                const uint32_t from = (q < 64 ? q : 63) >> 1;
+                const uint32_t vP = __shfl_sync(0xffffffffu, iP, from), vQ = __shfl_sync(0xffffffffu, iQ, from);
+                src = a.pts_in + ((q & 1) ? vQ : vP);
+            } else {
+                src = a.pts_in + 2 * (size_t)p0 + q;
+            }
+            if (on) cp_async16(wstage_addr + q * 96 + piece * 16, reinterpret_cast<const uint4*>(src) + piece);
+        }
+        cp_async_commit();
+    };
+    // the running product after pair jj of this thread's batch: scratch (written by the forward pass) -> stage
+    auto stage_prefix = [&](uint32_t jj) {
+        const uint4* src = sc + (size_t)jj * 3 * T;
+        cp_async16(pre_addr, src);
+        cp_async16(pre_addr + 32 * 16, src + T);
+        cp_async16(pre_addr + 64 * 16, src + 2 * (size_t)T);
+        cp_async_commit();
+    };
+    // everything this thread read from the stage has arrived in its registers (volatile asm statements keep their order)
+    auto consumed = [](const fp_t& v) { asm volatile("" ::"r"(v.l[0]), "r"(v.l[4]), "r"(v.l[8]) : "memory"); };
 
     for (uint32_t r = 0; r < rounds; r++) {
         const uint64_t base = (uint64_t)r * T * B + tid;
-        if (base >= S) break;
-        const uint64_t left = (S - base + T - 1) / T;
-        const uint32_t nj = left < B ? (uint32_t)left : B;
+        const uint64_t base0 = base - lane;               // the warp's first pair of this round
+        if (base0 >= S) break;                            // warp-uniform
+        uint32_t nj = 0;
+        if (base < S) {
+            const uint64_t left = (S - base + T - 1) / T;
+            nj = left < B ? (uint32_t)left : B;
+        }
+        const uint32_t njw = __shfl_sync(0xffffffffu, nj, 0);   // lane 0 has the most
+        auto pair_at = [&](uint32_t j) { return base + (uint64_t)j * T; };
 
-        // forward: denominators and their running product.  Only the x coordinates are needed unless the pair is
+        // ---- forward: denominators and their running product.  Only the x coordinates are needed unless the pair is
         // degenerate (pad, identity operand, equal x), which is re-examined with the full points.
         fp_t prod = fp_t::one();
-        for (uint32_t j = 0; j < nj; j++) {
-            const uint32_t p = (uint32_t)(base + (uint64_t)j * T);
-            fp_t den;
-            bool slow;
-            if (LEVEL0) {
-                const uint4 e = reinterpret_cast<const uint4*>(a.kv0)[p];
-                slow = e.z == INVALID_KEY;
-                const fp_t x1 = ld_fp(&a.pts_in[e.y & 0x7fffffffu].x);
-                const fp_t x2 = slow ? x1 : ld_fp(&a.pts_in[e.w & 0x7fffffffu].x);
-                den = sub(x2, x1);
-                slow = slow || den.is_zero() || x1.is_zero() || x2.is_zero();
-            } else {
-                const uint2 kk = reinterpret_cast<const uint2*>(a.keys_in)[p];
-                slow = kk.y == INVALID_KEY;
-                const fp_t x1 = ld_fp(&a.pts_in[2 * (size_t)p].x);
-                const fp_t x2 = slow ? x1 : ld_fp(&a.pts_in[2 * (size_t)p + 1].x);
-                den = sub(x2, x1);
-                slow = slow || den.is_zero() || x1.is_zero() || x2.is_zero();
+        {
+            uint4 m_next = load_meta(pair_at(0)), m_next2 = m_next;
+            if (BPK_AFF_STAGE) stage_points(base0, m_next, 3);
+            if (njw > 1) m_next2 = load_meta(pair_at(1));
+            for (uint32_t j = 0; j < njw; j++) {
+                const uint64_t p = pair_at(j);
+                const uint4 m = m_next;
+                m_next = m_next2;
+                const bool pad = m.z == INVALID_KEY;
+                fp_t x1, x2;
+                if (BPK_AFF_STAGE) {
+                    cp_async_wait_all();
+                    __syncwarp();
+                    x1 = lds_fp(my_pair);
+                    x2 = pad ? x1 : lds_fp(my_pair + 6);
+                    consumed(x1);
+                    consumed(x2);
+                    __syncwarp();
+                    if (j + 1 < njw) stage_points(base0 + (uint64_t)(j + 1) * T, m_next, 3);
+                } else if (j < nj) {
+                    x1 = ld_fp(&point_of(p, m, 0)->x);
+                    x2 = pad ? x1 : ld_fp(&point_of(p, m, 1)->x);
+                }
+                if (j + 2 < njw) m_next2 = load_meta(pair_at(j + 2));
+                if (j < nj) {
+                    fp_t den = sub(x2, x1);
+                    if (pad || den.is_zero() || x1.is_zero() || x2.is_zero()) {
+                        affine_t P = ld_affine(point_of(p, m, 0)), Q = affine_t::inf();
+                        if (LEVEL0 && (m.y >> 31)) P.y = neg(P.y);
+                        if (!pad) {
+                            Q = ld_affine(point_of(p, m, 1));
+                            if (LEVEL0 && (m.w >> 31)) Q.y = neg(Q.y);
+                        }
+                        affine_add_prepare(P, Q, den);
+                    }
+                    prod = j == 0 ? den : mul(prod, den);
+                    uint4* s = sc + (size_t)j * 3 * T;
+                    s[0] = make_uint4(prod.l[0], prod.l[1], prod.l[2], prod.l[3]);
+                    s[T] = make_uint4(prod.l[4], prod.l[5], prod.l[6], prod.l[7]);
+                    s[2 * (size_t)T] = make_uint4(prod.l[8], prod.l[9], prod.l[10], prod.l[11]);
+                }
             }
-            if (slow) {
-                affine_t P, Q;
-                uint32_t key;
-                load_pair(p, P, Q, key);
-                affine_add_prepare(P, Q, den);
-            }
-            prod = j == 0 ? den : mul(prod, den);
-            uint4* s = sc + (size_t)j * 3 * T;
-            s[0] = make_uint4(prod.l[0], prod.l[1], prod.l[2], prod.l[3]);
-            s[T] = make_uint4(prod.l[4], prod.l[5], prod.l[6], prod.l[7]);
-            s[2 * (size_t)T] = make_uint4(prod.l[8], prod.l[9], prod.l[10], prod.l[11]);
         }
 
         fp_t acc = inv(prod);  // 1 / (den_0 ... den_{nj-1})
 
-        // backward: peel the inverses off, finish the additions, place the results
-        for (uint32_t j = nj; j-- > 0;) {
-            const uint32_t p = (uint32_t)(base + (uint64_t)j * T);
-            affine_t P, Q;
-            uint32_t key;
-            load_pair(p, P, Q, key);
-            fp_t den;
-            const int kind = affine_add_prepare(P, Q, den);
-            fp_t dinv = acc;
-            if (j > 0) {
-                const uint4* s = sc + (size_t)(j - 1) * 3 * T;
-                const uint4 u0 = s[0], u1 = s[T], u2 = s[2 * (size_t)T];
-                fp_t pre;
-                pre.l[0] = u0.x; pre.l[1] = u0.y; pre.l[2] = u0.z; pre.l[3] = u0.w;
-                pre.l[4] = u1.x; pre.l[5] = u1.y; pre.l[6] = u1.z; pre.l[7] = u1.w;
-                pre.l[8] = u2.x; pre.l[9] = u2.y; pre.l[10] = u2.z; pre.l[11] = u2.w;
-                dinv = mul(acc, pre);
-                acc = mul(acc, den);
+        // ---- backward: peel the inverses off, finish the additions, place the results
+        {
+            uint4 m_next = load_meta(pair_at(njw - 1)), m_next2 = m_next;
+            if (BPK_AFF_STAGE) {
+                stage_points(base0 + (uint64_t)(njw - 1) * T, m_next, 6);
+                if (njw > 1 && nj == njw) stage_prefix(njw - 2);   // needed at the first step if this lane takes part in it
             }
-            const affine_t R = affine_add_finish(kind, P, Q, dinv);
-            const uint32_t c0 = a.cnt0[key];
-            const uint32_t cn = (c0 + ((2u << a.level) - 1u)) >> (a.level + 1);  // entries of the bucket at level + 1
-            if (cn <= 1) {
-                st_xyzz(a.buckets + key, xyzz_t::from_affine(R));
-            } else {
-                const uint32_t rel = p - (a.off_in[key] >> 1);
-                const uint32_t slot = a.off_out[key] + rel;
-                st_affine(a.pts_out + slot, R);
-                a.keys_out[slot] = key;
-                if (!a.out_is_tail && (cn & 1u) && rel == cn - 1) a.keys_out[slot + 1] = INVALID_KEY;
+            if (njw > 1) m_next2 = load_meta(pair_at(njw - 2));
+            for (uint32_t j = njw; j-- > 0;) {
+                const uint64_t p = pair_at(j);
+                const uint4 m = m_next;
+                m_next = m_next2;
+                const bool active = j < nj;
+                affine_t P, Q = affine_t::inf();
+                fp_t pre;
+                if (BPK_AFF_STAGE) {
+                    cp_async_wait_all();
+                    __syncwarp();
+                    P.x = lds_fp(my_pair);
+                    P.y = lds_fp(my_pair + 3);
+                    if (m.z != INVALID_KEY) {
+                        Q.x = lds_fp(my_pair + 6);
+                        Q.y = lds_fp(my_pair + 9);
+                    }
+                    if (active && j > 0) {
+                        const uint4 u0 = pre_stage[0], u1 = pre_stage[32], u2 = pre_stage[64];
+                        pre.l[0] = u0.x; pre.l[1] = u0.y; pre.l[2] = u0.z; pre.l[3] = u0.w;
+                        pre.l[4] = u1.x; pre.l[5] = u1.y; pre.l[6] = u1.z; pre.l[7] = u1.w;
+                        pre.l[8] = u2.x; pre.l[9] = u2.y; pre.l[10] = u2.z; pre.l[11] = u2.w;
+                        consumed(pre);
+                    }
+                    consumed(P.x);
+                    consumed(P.y);
+                    consumed(Q.x);
+                    consumed(Q.y);
+                    __syncwarp();
+                    if (j > 0) stage_points(base0 + (uint64_t)(j - 1) * T, m_next, 6);
+                    // the prefix needed at step j - 1 is the product after pair j - 2 (own slots: no other lane reads them)
+                    if (j > 1 && j - 1 < nj) stage_prefix(j - 2);
+                } else if (active) {
+                    P = ld_affine(point_of(p, m, 0));
+                    if (m.z != INVALID_KEY) Q = ld_affine(point_of(p, m, 1));
+                    if (j > 0) {
+                        const uint4* s = sc + (size_t)(j - 1) * 3 * T;
+                        const uint4 u0 = s[0], u1 = s[T], u2 = s[2 * (size_t)T];
+                        pre.l[0] = u0.x; pre.l[1] = u0.y; pre.l[2] = u0.z; pre.l[3] = u0.w;
+                        pre.l[4] = u1.x; pre.l[5] = u1.y; pre.l[6] = u1.z; pre.l[7] = u1.w;
+                        pre.l[8] = u2.x; pre.l[9] = u2.y; pre.l[10] = u2.z; pre.l[11] = u2.w;
+                    }
+                }
+                if (j > 1) m_next2 = load_meta(pair_at(j - 2));
+                if (!active) continue;
+                if (LEVEL0) {
+                    if (m.y >> 31) P.y = neg(P.y);
+                    if (m.z != INVALID_KEY && (m.w >> 31)) Q.y = neg(Q.y);
+                }
+                fp_t den;
+                const int kind = affine_add_prepare(P, Q, den);
+                fp_t dinv = acc;
+                if (j > 0) {
+                    dinv = mul(acc, pre);
+                    acc = mul(acc, den);
+                }
+                const affine_t R = affine_add_finish(kind, P, Q, dinv);
+                const uint32_t key = m.x;
+                const uint32_t c0 = a.cnt0[key];
+                const uint32_t cn = (c0 + ((2u << a.level) - 1u)) >> (a.level + 1);  // entries of the bucket at level + 1
+                if (cn <= 1) {
+                    st_xyzz(a.buckets + key, xyzz_t::from_affine(R));
+                } else {
+                    const uint32_t rel = (uint32_t)p - (a.off_in[key] >> 1);
+                    const uint32_t slot = a.off_out[key] + rel;
+                    st_affine(a.pts_out + slot, R);
+                    a.keys_out[slot] = key;
+                    if (!a.out_is_tail && (cn & 1u) && rel == cn - 1) a.keys_out[slot + 1] = INVALID_KEY;
+                }
             }
         }
     }
@@ -977,10 +1101,11 @@ static int msm_workspace(bpk_ctx* ctx, const MsmPlan& pl, size_t n, MsmWork* w) 
     w->keys_lvl[0] = w->keys_lvl[1] = nullptr;
     w->pts_lvl[0] = w->pts_lvl[1] = nullptr;
     w->scratch = nullptr;
-    w->aff_threads = (uint32_t)ctx->sm_count * BPK_AFF_MINBLOCKS * 128;
+    w->aff_threads = (uint32_t)ctx->sm_count * BPK_AFF_MINBLOCKS * AFF_THREADS;
     w->bmax = (uint32_t)(ctx->opt_msm_batch < 1 ? 1 : ctx->opt_msm_batch);
     if (L >= 1) {
-        const size_t u1 = level_ub(w->M, w->nb, 1) + 2, u2 = L >= 2 ? level_ub(w->M, w->nb, 2) + 2 : 0;
+        // + 66: the cooperative copies of the last warp of a level read up to 31 pairs past its end
+        const size_t u1 = level_ub(w->M, w->nb, 1) + 66, u2 = L >= 2 ? level_ub(w->M, w->nb, 2) + 66 : 0;
         char* base;
         BPK_TRY(ws_reserve(ctx, 16, align256(u1 * 4) + align256(u2 * 4), (void**)&base));
         w->keys_lvl[0] = (uint32_t*)base;
@@ -1030,11 +1155,21 @@ static int msm_launch_tail(bpk_ctx* ctx, const MsmWork& w, const TailSrc& src, x
     return BPK_OK;
 }
 
+static int msm_configure_kernels(bpk_ctx* ctx) {  // opt in to > 48 KB of dynamic shared memory, once per process
+    static bool done = false;
+    if (done || AFF_SMEM_BYTES <= 48 * 1024) return BPK_OK;
+    BPK_CUDA(cudaFuncSetAttribute(msm_affine_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AFF_SMEM_BYTES));
+    BPK_CUDA(cudaFuncSetAttribute(msm_affine_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AFF_SMEM_BYTES));
+    done = true;
+    return BPK_OK;
+}
+
 // phase 1: count, layout, scatter, affine tree, tail: `buckets` (nb_total entries) receives the bucket sums of the n pairs
 static int msm_fill_buckets(bpk_ctx* ctx, const MsmPlan& pl, const MsmPoints& pts, const fr_t* d_scalars, size_t n,
                             unsigned rshift, xyzz_t* buckets) {
     MsmWork w;
     BPK_TRY(msm_workspace(ctx, pl, n, &w));
+    BPK_TRY(msm_configure_kernels(ctx));
     const int L = pl.L;
     ctx->last_c = pl.c;
     ctx->last_W = pl.W;
@@ -1092,11 +1227,11 @@ static int msm_fill_buckets(bpk_ctx* ctx, const MsmPlan& pl, const MsmPoints& pt
             a.level = (uint32_t)l;
             a.bmax = w.bmax;
             a.out_is_tail = l + 1 == L ? 1u : 0u;
-            const unsigned grid = w.aff_threads / 128;
+            const unsigned grid = w.aff_threads / AFF_THREADS;
             if (l == 0)
-                msm_affine_level_kernel<true><<<grid, 128, 0, ctx->stream>>>(a);
+                msm_affine_level_kernel<true><<<grid, AFF_THREADS, AFF_SMEM_BYTES, ctx->stream>>>(a);
             else
-                msm_affine_level_kernel<false><<<grid, 128, 0, ctx->stream>>>(a);
+                msm_affine_level_kernel<false><<<grid, AFF_THREADS, AFF_SMEM_BYTES, ctx->stream>>>(a);
             count_launch(ctx);
         }
         BPK_CUDA(cudaGetLastError());
