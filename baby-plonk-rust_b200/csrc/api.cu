@@ -290,6 +290,9 @@ extern "C" int bpk_set_option(bpk_ctx* ctx, const char* key, long value) {
     } else if (k == "msm.level_mib") {
         if (value < 0) return BPK_ERR_INVALID_ARG;
         ctx->opt_msm_level_mib = value;
+    } else if (k == "msm.scatter_l2_mib") {
+        if (value < 0) return BPK_ERR_INVALID_ARG;
+        ctx->opt_msm_scatter_l2_mib = value;
     } else if (k == "msm.tree_top") ctx->opt_msm_tree_top = value;
     else if (k == "msm.lanes") ctx->opt_msm_lanes = value;
     else if (k == "msm.host_slices") ctx->opt_msm_host_slices = value;
@@ -421,12 +424,12 @@ extern "C" int bpk_srs_precompute(bpk_ctx* ctx, uint64_t handle, unsigned window
     if (e.n == 0) return BPK_OK;
     unsigned c = window_bits;
     if (c == 0) {
-        // measured optimum of the sweep in profiles/r1_precompute_window_sweep.md (c = 7..22 at 2^16..2^22, c = 21..23
-        // at 2^24): larger windows trade W n pair additions against 2^(c-1) bucket additions and tree depth
+        // measured optimum of the sweep in profiles/r2_msm_plan_sweep.md (c = 8..21 at 2^16..2^22, c = 21..23 at 2^24):
+        // larger windows trade W n pair additions against 2^(c-1) bucket additions and tree depth
         unsigned lg = 0;
         while (((size_t)2 << lg) <= e.n) lg++;          // floor(log2 n)
         if (e.n - ((size_t)1 << lg) >= ((size_t)1 << lg) / 2) lg++;  // nearest power of two
-        c = lg <= 16 ? 8 : lg == 17 ? 16 : lg <= 19 ? 19 : lg <= 22 ? 20 : lg == 23 ? 21 : 22;
+        c = lg <= 16 ? (lg < 9 ? 6 : lg - 3) : lg == 17 ? 15 : lg == 18 ? 16 : lg == 19 ? 18 : lg <= 22 ? 20 : lg == 23 ? 21 : 22;
     }
     if (c < 2 || c > 24) return BPK_ERR_INVALID_ARG;
     const unsigned W = (256 + c - 1) / c;

@@ -101,10 +101,11 @@ struct bpk_ctx {
     long opt_msm_lanes = bpk::MSM_LANES;  // 1: bpk_msm_g1_dev_batch runs its MSMs one after the other
     long opt_msm_host_slices = 1;  // 0: upload all scalars before the MSM starts
     long opt_msm_affine_levels = -1;  // levels of the batched-affine pairwise tree (-1: from the expected bucket load, 0: XYZZ only)
-    long opt_msm_min_pairs = 1 << 16;  // a tree level expected to hold fewer pairs is left to the XYZZ tail
+    long opt_msm_min_pairs = 1 << 19;  // a tree level expected to hold fewer pairs is left to the XYZZ tail (r2_msm_plan_sweep.md)
     long opt_msm_batch = 256;          // additions that share one inversion (per thread)
     long opt_msm_level_mib = 48 << 10; // budget of the tree's level buffers
     long opt_msm_tree_top = 1;         // narrow top of the bucket-reduction tree in one block
+    long opt_msm_scatter_l2_mib = 400; // the level-0 list is scattered in phases over bucket ranges of at most this size
     long opt_ntt_tile_log2 = 10;  // R x C elements per CTA tile (32 KiB): best of the sweep in profiles/
     long opt_ntt_max_radix_log2 = 0;  // 0 = auto
     long opt_ntt_threads = 0;

@@ -90,13 +90,13 @@ __device__ __forceinline__ fr_t ld_fr_g(const fr_t* p) {
 // key_stride: buckets per window (2^(c-1)) for per-window bucket sets, 0 when every window shares one
 // bucket set (precomputed SRS levels); val_stride: distance between precomputed levels in points, else 0.
 struct RecodeArgs {
-    const fr_t* scalars;
+    const fr_t* scalars;   // Montgomery form (the caller's)
+    uint32_t* digits;      // optional [W][n] cache of the recoded windows (bucket | sign << 31), written by the counting pass
     uint32_t n, c, W, rshift, key_stride, val_stride;
 };
 
-// canonical integer (value >> rshift) of scalar i as 10 limbs (two of padding for the window reads)
-__device__ __forceinline__ void recode_limbs(const RecodeArgs& a, uint32_t i, uint32_t l[10]) {
-    fr_t s = from_mont(ld_fr_g(a.scalars + i));  // canonical integer < q
+// canonical integer s -> (s >> rshift) as 10 limbs (two of padding for the window reads)
+__device__ __forceinline__ void recode_shift(const RecodeArgs& a, const fr_t& s, uint32_t l[10]) {
 #pragma unroll
     for (int k = 0; k < 8; k++) l[k] = s.l[k];
     l[8] = 0;
@@ -113,6 +113,12 @@ __device__ __forceinline__ void recode_limbs(const RecodeArgs& a, uint32_t i, ui
 #pragma unroll
         for (int k = 0; k < 10; k++) l[k] = t[k];
     }
+}
+
+// scalar i: Montgomery -> canonical (scalar.rs:292-304 semantics) -> shifted limbs
+__device__ __forceinline__ void recode_limbs(const RecodeArgs& a, uint32_t i, uint32_t l[10]) {
+    const fr_t s = from_mont(ld_fr_g(a.scalars + i));  // canonical integer < q
+    recode_shift(a, s, l);
 }
 
 // window w of the signed recoding: key = bucket (INVALID_KEY for a zero digit), val = point index | sign << 31
@@ -137,10 +143,13 @@ __device__ __forceinline__ void recode_window(const RecodeArgs& a, const uint32_
     val = (w * a.val_stride + i) | (neg << 31);
 }
 
-// Histogram of the bucket keys.  Lanes of a warp that hit the same bucket are combined before the L2 reduction
-// (match.any): with uniform digits that changes nothing, with skewed scalars (a witness full of zeros and ones, all
-// scalars equal) it keeps one hot bucket from serialising 32 reductions per warp.
+// Histogram of the bucket keys.  AGG: lanes of a warp that hit the same bucket are combined before the L2 reduction
+// (match.any, ~300 cycles per warp instruction) -- worth it when there are few buckets; with many buckets and uniform
+// digits it only costs, so the large path takes plain reductions plus the one vote that catches a warp whose lanes
+// all hit the same bucket (equal scalars).
+template <bool AGG>
 __global__ void __launch_bounds__(256) msm_count_kernel(RecodeArgs a, uint32_t* __restrict__ cnt) {
+    // a.digits != null: keep the recoded windows for the phases of the large scatter
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     const bool active = i < a.n;
@@ -150,30 +159,97 @@ __global__ void __launch_bounds__(256) msm_count_kernel(RecodeArgs a, uint32_t* 
     for (uint32_t w = 0; w < a.W; w++) {
         uint32_t key = INVALID_KEY, val = 0;
         if (active) recode_window(a, l, i, w, carry, key, val);
-        const uint32_t peers = __match_any_sync(0xffffffffu, key);
-        if (key != INVALID_KEY && (peers & ((1u << lane) - 1)) == 0) atomicAdd(cnt + key, (uint32_t)__popc(peers));
+        if (a.digits && active) a.digits[(size_t)w * a.n + i] = (key & 0x7fffffffu) | (val & 0x80000000u);  // zero digit: 0x7fffffff
+        if (AGG) {
+            const uint32_t peers = __match_any_sync(0xffffffffu, key);
+            if (key != INVALID_KEY && (peers & ((1u << lane) - 1)) == 0) atomicAdd(cnt + key, (uint32_t)__popc(peers));
+        } else {
+            const uint32_t k0 = __shfl_sync(0xffffffffu, key, 0);
+            if (__all_sync(0xffffffffu, key == k0)) {
+                if (lane == 0 && key != INVALID_KEY) atomicAdd(cnt + key, 32u);
+            } else if (key != INVALID_KEY) {
+                atomicAdd(cnt + key, 1u);
+            }
+        }
     }
 }
 
-// Counting-sort scatter: cursor[b] starts at the first level-0 slot of bucket b (K2).  The order of the entries inside a
-// bucket depends on the order in which warps arrive; the bucket SUM (a group element, output in affine form) does not.
+// position of one entry: the bucket's (or partition's) cursor advances by one per entry.  `agg` (warp-uniform): combine
+// the lanes of a warp that hit the same cursor first -- one atomic per distinct cursor instead of one per lane.
+__device__ __forceinline__ uint32_t cursor_take(uint32_t* cursors, uint32_t idx, bool valid, bool agg, uint32_t lane) {
+    if (agg) {
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? idx : INVALID_KEY);
+        const uint32_t leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (valid && lane == leader) base = atomicAdd(cursors + idx, (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        return base + __popc(peers & ((1u << lane) - 1));
+    }
+    return valid ? atomicAdd(cursors + idx, 1u) : 0u;
+}
+
+// Counting-sort scatter, one pass: cursor[b] starts at the first level-0 slot of bucket b (K2).  The order of the entries
+// inside a bucket depends on the order in which warps arrive; the bucket SUM (a group element, output in affine form) does
+// not.  Used while the level-0 list is small enough to stay in L2; beyond that the random 8-byte stores become partial
+// sector writes to HBM (measured 6.7 ms for 2^24 x 12 entries) and the two-pass form below takes over.
 __global__ void __launch_bounds__(256) msm_scatter_kernel(RecodeArgs a, uint32_t* __restrict__ cursor,
+                                                           const uint32_t* __restrict__ skew, uint32_t force_agg,
                                                            uint2* __restrict__ kv0) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     const bool active = i < a.n;
+    const bool agg = force_agg || *skew != 0;
     uint32_t l[10];
     if (active) recode_limbs(a, i, l);
     uint32_t carry = 0;
     for (uint32_t w = 0; w < a.W; w++) {
         uint32_t key = INVALID_KEY, val = 0;
         if (active) recode_window(a, l, i, w, carry, key, val);
-        const uint32_t peers = __match_any_sync(0xffffffffu, key);
-        const uint32_t leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (key != INVALID_KEY && lane == leader) base = atomicAdd(cursor + key, (uint32_t)__popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (key != INVALID_KEY) kv0[base + __popc(peers & ((1u << lane) - 1))] = make_uint2(key, val);
+        const uint32_t pos = cursor_take(cursor, key, key != INVALID_KEY, agg, lane);
+        if (key != INVALID_KEY) kv0[pos] = make_uint2(key, val);
+    }
+}
+
+// Scatter for large inputs, in PHASES over the bucket range.  A phase places only the entries whose bucket lies in
+// [key_lo, key_hi): its random 8-byte stores are confined to that range's slice of the level-0 list, so that L2 merges
+// more of them into whole sectors before they reach HBM (measured at 2^24 x 12 entries: 1 phase 6.9 ms, 5 phases 4.1 ms).
+// The recoded windows come from the cache the counting pass wrote ([W][n] words, read with the streaming hint), so a phase
+// costs one 4-byte load and a compare per entry.  `skew` (set by the layout scan when one bucket holds a large share
+// of the entries) switches to warp-aggregated cursor updates.
+constexpr uint32_t RANGE_ITEMS = 8;  // cached digits per thread and phase (two 16-byte loads)
+__global__ void __launch_bounds__(256) msm_scatter_range_kernel(RecodeArgs a, uint32_t* __restrict__ cursor,
+                                                                 const uint32_t* __restrict__ skew, uint32_t key_lo,
+                                                                 uint32_t key_hi, uint2* __restrict__ kv0) {
+    const size_t M = (size_t)a.W * a.n;
+    const size_t e0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * RANGE_ITEMS;
+    const uint32_t lane = threadIdx.x & 31;
+    const bool agg = *skew != 0;
+    uint32_t d[RANGE_ITEMS];
+    if (e0 + RANGE_ITEMS <= M) {
+        const uint4* q = reinterpret_cast<const uint4*>(a.digits + e0);
+        const uint4 u = __ldcs(q), v = __ldcs(q + 1);
+        d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
+        d[4] = v.x; d[5] = v.y; d[6] = v.z; d[7] = v.w;
+    } else {
+#pragma unroll
+        for (uint32_t k = 0; k < RANGE_ITEMS; k++) d[k] = e0 + k < M ? a.digits[e0 + k] : 0x7fffffffu;
+    }
+    uint32_t w = (uint32_t)(e0 / a.n), i = (uint32_t)(e0 - (size_t)w * a.n);
+#pragma unroll
+    for (uint32_t k = 0; k < RANGE_ITEMS; k++) {
+        const uint32_t key = d[k] & 0x7fffffffu;
+        const bool mine = key >= key_lo && key < key_hi;   // a zero digit (0x7fffffff) is above every range
+        const uint32_t val = (w * a.val_stride + i) | (d[k] & 0x80000000u);
+        if (agg) {
+            const uint32_t pos = cursor_take(cursor, key, mine, true, lane);
+            if (mine) kv0[pos] = make_uint2(key, val);
+        } else if (mine) {
+            kv0[atomicAdd(cursor + key, 1u)] = make_uint2(key, val);
+        }
+        if (++i == a.n) {
+            i = 0;
+            w++;
+        }
     }
 }
 
@@ -220,7 +296,8 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& t
     return incl - v + smem[warp];
 }
 
-// stats: [0] entries at level 0, [1] entries at level L (finished buckets count 1), [2] non-empty buckets
+// stats: [0] entries at level 0, [1] entries at level L (finished buckets count 1), [2] non-empty buckets,
+// [3] (low word) skew flag: some bucket holds more than 2^15 entries
 __global__ void __launch_bounds__(SCAN_THREADS) msm_level_sums_kernel(const uint32_t* __restrict__ cnt, uint32_t nb, int L,
                                                                        uint32_t nblk, uint32_t* __restrict__ blocksums,
                                                                        unsigned long long* __restrict__ stats) {
@@ -237,13 +314,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) msm_level_sums_kernel(const uint
         block_exclusive_scan(s, total, smem);
         if (threadIdx.x == 0) blocksums[(size_t)l * nblk + blockIdx.x] = total;
     }
-    uint32_t e0 = 0, eL = 0, ne = 0;
+    uint32_t e0 = 0, eL = 0, ne = 0, heavy = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         e0 += c0[k];
         eL += c0[k] ? level_entries(c0[k], L) : 0;
         ne += c0[k] != 0;
+        heavy |= c0[k] > (1u << 15);
     }
+    if (heavy) *reinterpret_cast<volatile uint32_t*>(stats + 3) = 1u;
     uint32_t t0, tL, tn;
     block_exclusive_scan(e0, t0, smem);
     block_exclusive_scan(eL, tL, smem);
@@ -1062,6 +1141,8 @@ struct MsmWork {
     uint32_t *cnt0, *cursor, *off, *blocksums, *totals;
     unsigned long long* stats;
     uint2* kv0;
+    uint32_t* digits;         // [W][n] recoded windows for the phased scatter of large inputs (null: one-pass scatter)
+    uint32_t phases;
     uint32_t* keys_lvl[2];    // [odd levels, even levels >= 2]
     affine_t* pts_lvl[2];
     uint4* scratch;
@@ -1097,7 +1178,17 @@ static int msm_workspace(bpk_ctx* ctx, const MsmPlan& pl, size_t n, MsmWork* w) 
         w->totals = (uint32_t*)(base + 2 * b_cnt + b_off + b_sums);
         w->stats = (unsigned long long*)(base + 2 * b_cnt + b_off + b_sums + b_tot);
     }
-    BPK_TRY(ws_reserve(ctx, 2, (level_ub(w->M, w->nb, 0) + 2) * sizeof(uint2), (void**)&w->kv0));
+    const size_t kv_bytes = (level_ub(w->M, w->nb, 0) + 2) * sizeof(uint2);
+    BPK_TRY(ws_reserve(ctx, 2, kv_bytes, (void**)&w->kv0));
+    // the level-0 list is scattered in as many phases (bucket ranges) as it takes for one phase's slice to stay in L2
+    w->digits = nullptr;
+    w->phases = 1;
+    const size_t slice = (size_t)(ctx->opt_msm_scatter_l2_mib < 1 ? 1 : ctx->opt_msm_scatter_l2_mib) << 20;
+    if (kv_bytes > slice) {
+        w->phases = (uint32_t)((kv_bytes + slice - 1) / slice);
+        if (w->phases > 64) w->phases = 64;
+        BPK_TRY(ws_reserve(ctx, 20, w->M * sizeof(uint32_t), (void**)&w->digits));
+    }
     w->keys_lvl[0] = w->keys_lvl[1] = nullptr;
     w->pts_lvl[0] = w->pts_lvl[1] = nullptr;
     w->scratch = nullptr;
@@ -1141,16 +1232,23 @@ static int msm_workspace(bpk_ctx* ctx, const MsmPlan& pl, size_t n, MsmWork* w) 
 }
 
 template <bool LEVEL0>
-static int msm_launch_tail(bpk_ctx* ctx, const MsmWork& w, const TailSrc& src, xyzz_t* buckets) {
+static int msm_launch_tail_accumulate(bpk_ctx* ctx, const MsmWork& w, const TailSrc& src, xyzz_t* buckets) {
     const unsigned grid = (unsigned)((w.num_chunks + 127) / 128);
     msm_accumulate_kernel<LEVEL0><<<grid, 128, 0, ctx->stream>>>(src, w.chunk, w.num_chunks, buckets, w.pkeys, w.pvals);
+    count_launch(ctx);
+    BPK_CUDA(cudaGetLastError());
+    return BPK_OK;
+}
+template <bool LEVEL0>
+static int msm_launch_tail_merge(bpk_ctx* ctx, const MsmWork& w, const TailSrc& src, xyzz_t* buckets) {
+    const unsigned grid = (unsigned)((w.num_chunks + 127) / 128);
     msm_merge_partials_kernel<LEVEL0><<<grid, 128, 0, ctx->stream>>>(w.pkeys, w.pvals, w.num_chunks, buckets, src, w.chunk,
                                                                     w.long_runs, w.long_count, w.warp_runs, w.warp_count);
     msm_merge_warp_runs_kernel<<<(unsigned)ctx->sm_count * 4, 128, 0, ctx->stream>>>(w.warp_runs, w.warp_count, w.pvals,
                                                                                      buckets);
     msm_merge_long_runs_kernel<<<(unsigned)ctx->sm_count * 2, MERGE_BLOCK, 0, ctx->stream>>>(w.long_runs, w.long_count,
                                                                                           w.pvals, buckets);
-    count_launch(ctx, 4);
+    count_launch(ctx, 3);
     BPK_CUDA(cudaGetLastError());
     return BPK_OK;
 }
@@ -1181,6 +1279,7 @@ static int msm_fill_buckets(bpk_ctx* ctx, const MsmPlan& pl, const MsmPoints& pt
 
     RecodeArgs ra;
     ra.scalars = d_scalars;
+    ra.digits = w.digits;
     ra.n = (uint32_t)n;
     ra.c = pl.c;
     ra.W = pl.W;
@@ -1192,7 +1291,12 @@ static int msm_fill_buckets(bpk_ctx* ctx, const MsmPlan& pl, const MsmPoints& pt
         StageTimer t(ctx, "msm.recode");  // digits + histogram
         BPK_CUDA(cudaMemsetAsync(w.cnt0, 0, (size_t)w.nb * 4, ctx->stream));
         BPK_CUDA(cudaMemsetAsync(w.stats, 0, 32, ctx->stream));
-        msm_count_kernel<<<rgrid, 256, 0, ctx->stream>>>(ra, w.cnt0);
+        // many entries per bucket (few buckets): combine the lanes of a warp before every cursor / counter update
+        const bool dense = w.M / w.nb > 256;
+        if (dense)
+            msm_count_kernel<true><<<rgrid, 256, 0, ctx->stream>>>(ra, w.cnt0);
+        else
+            msm_count_kernel<false><<<rgrid, 256, 0, ctx->stream>>>(ra, w.cnt0);
         count_launch(ctx);
         BPK_CUDA(cudaGetLastError());
         t.end();
@@ -1203,11 +1307,29 @@ static int msm_fill_buckets(bpk_ctx* ctx, const MsmPlan& pl, const MsmPoints& pt
         msm_level_scan_kernel<<<L + 1, 1024, 0, ctx->stream>>>(w.blocksums, w.nblk, w.totals);
         msm_level_offsets_kernel<<<w.nblk, SCAN_THREADS, 0, ctx->stream>>>(w.cnt0, w.nb, L, w.nblk, w.blocksums, w.off,
                                                                         w.cursor, w.kv0);
-        msm_scatter_kernel<<<rgrid, 256, 0, ctx->stream>>>(ra, w.cursor, w.kv0);
-        count_launch(ctx, 4);
+        count_launch(ctx, 3);
+        if (w.digits) {
+            const uint32_t* skew = reinterpret_cast<const uint32_t*>(w.stats + 3);
+            for (uint32_t ph = 0; ph < w.phases; ph++) {
+                const uint32_t lo = (uint32_t)((uint64_t)w.nb * ph / w.phases), hi = (uint32_t)((uint64_t)w.nb * (ph + 1) / w.phases);
+                const size_t threads = (w.M + RANGE_ITEMS - 1) / RANGE_ITEMS;
+                msm_scatter_range_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ra, w.cursor, skew, lo, hi,
+                                                                                               w.kv0);
+                count_launch(ctx);
+            }
+        } else {
+            msm_scatter_kernel<<<rgrid, 256, 0, ctx->stream>>>(ra, w.cursor, reinterpret_cast<const uint32_t*>(w.stats + 3),
+                                                               w.M / w.nb > 256 ? 1u : 0u, w.kv0);
+            count_launch(ctx);
+        }
         BPK_CUDA(cudaGetLastError());
         t.end();
     }
+    TailSrc src;
+    src.kv0 = L == 0 ? w.kv0 : nullptr;
+    src.keys = L == 0 ? nullptr : w.keys_lvl[(L & 1) ? 0 : 1];
+    src.pts = L == 0 ? pts.base : w.pts_lvl[(L & 1) ? 0 : 1];
+    src.total = w.totals + L;
     {
         StageTimer t(ctx, "msm.accumulate");
         BPK_CUDA(cudaMemsetAsync(buckets, 0, (size_t)w.nb * sizeof(xyzz_t), ctx->stream));
@@ -1234,21 +1356,20 @@ static int msm_fill_buckets(bpk_ctx* ctx, const MsmPlan& pl, const MsmPoints& pt
                 msm_affine_level_kernel<false><<<grid, AFF_THREADS, AFF_SMEM_BYTES, ctx->stream>>>(a);
             count_launch(ctx);
         }
-        BPK_CUDA(cudaGetLastError());
+        // the XYZZ tail of the tree (everything, when no affine level runs)
+        BPK_CUDA(cudaMemsetAsync(w.long_count, 0, 2 * sizeof(uint32_t), ctx->stream));
+        if (L == 0)
+            BPK_TRY(msm_launch_tail_accumulate<true>(ctx, w, src, buckets));
+        else
+            BPK_TRY(msm_launch_tail_accumulate<false>(ctx, w, src, buckets));
         t.end();
     }
     {
-        StageTimer t(ctx, "msm.merge");  // XYZZ tail of the tree + merge of the chunk partials
-        BPK_CUDA(cudaMemsetAsync(w.long_count, 0, 2 * sizeof(uint32_t), ctx->stream));
-        TailSrc src;
-        src.kv0 = L == 0 ? w.kv0 : nullptr;
-        src.keys = L == 0 ? nullptr : w.keys_lvl[(L & 1) ? 0 : 1];
-        src.pts = L == 0 ? pts.base : w.pts_lvl[(L & 1) ? 0 : 1];
-        src.total = w.totals + L;
+        StageTimer t(ctx, "msm.merge");  // partial sums of the runs that cross chunk borders
         if (L == 0)
-            BPK_TRY(msm_launch_tail<true>(ctx, w, src, buckets));
+            BPK_TRY(msm_launch_tail_merge<true>(ctx, w, src, buckets));
         else
-            BPK_TRY(msm_launch_tail<false>(ctx, w, src, buckets));
+            BPK_TRY(msm_launch_tail_merge<false>(ctx, w, src, buckets));
         t.end();
     }
     return BPK_OK;

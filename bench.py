@@ -171,7 +171,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # CPU legs (oracle/ as the thing TIMED: only here and in run_reference)
 # ---------------------------------------------------------------------------------------------------------
-SAMPLE_PAIRS_PER_THREAD_LOG2 = 15   # ~4-8 s of the reference algorithm on every host thread
+SAMPLE_PAIRS_PER_THREAD_LOG2 = 16   # ~7-15 s of the reference algorithm on every host thread
 
 
 def _par(fn, jobs, threads):

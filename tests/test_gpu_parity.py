@@ -446,8 +446,8 @@ def test_msm_precomputed_degenerate_points(ctx):
 
 class options:
     """set library tunables for a block, restore the defaults afterwards"""
-    DEFAULTS = {"msm.affine_levels": -1, "msm.batch": 256, "msm.min_pairs": 1 << 16, "msm.window": 0, "msm.chunk": 0,
-                "msm.tree_top": 1, "msm.level_mib": 48 << 10}
+    DEFAULTS = {"msm.affine_levels": -1, "msm.batch": 256, "msm.min_pairs": 1 << 19, "msm.window": 0, "msm.chunk": 0,
+                "msm.tree_top": 1, "msm.level_mib": 48 << 10, "msm.scatter_l2_mib": 400}
 
     def __init__(self, ctx, **kw):
         self.ctx, self.kw = ctx, {k.replace("_", ".", 1): v for k, v in kw.items()}
@@ -513,6 +513,26 @@ def test_msm_affine_tree_degenerate_points(ctx, levels):
         s.precompute(6)
         assert bpk.point_to_affine(s.commit_scalars(S(sc))) == O.msm_naive(pts, sc)
         s.free()
+
+
+@pytest.mark.parametrize("levels", [0, 2, 12])
+def test_msm_phased_scatter(ctx, levels):
+    """the scatter in phases over the bucket range that large inputs take (forced here: 1 MiB slices -> ~10 phases), with
+    few buckets and many, uniform and skewed scalars (the skew flag switches to aggregated cursor updates)"""
+    n = 40000
+    setup = bpk.Setup.generate_srs(n, 101, ctx)
+    rng = random.Random(levels)
+    cases = [O.random_fr(50 + levels, n), [0xABCDEF0123456789] * n, [rng.choice([1, 2, O.Q - 1]) for _ in range(n)]]
+    with options(ctx, msm_scatter_l2_mib=1, msm_affine_levels=levels):
+        for sc in cases:
+            want = horner_expected(sc, 101)
+            for window in (0, 14):          # 29 x 2^8 buckets / 19 x 2^13 buckets (many partitions)
+                with options(ctx, msm_window=window):
+                    assert bpk.point_to_affine(setup.commit_scalars(S(sc))) == want
+        setup.precompute(8)                 # 128 buckets
+        for sc in cases:
+            assert bpk.point_to_affine(setup.commit_scalars(S(sc))) == horner_expected(sc, 101)
+    setup.free()
 
 
 def test_msm_tree_top_and_per_level_reduction_agree(ctx):
@@ -847,3 +867,18 @@ def test_device_memory_helpers(ctx):
     ctx.check(lib.bpk_dev_free(h, c), "free")
     assert lib.bpk_dev_free(h, None) == 0
     assert lib.bpk_dev_alloc(h, 16, None) == -3
+
+
+def test_bench_workload_generator_is_survey_8d(ctx):
+    """bench.py's scalars (SplitMix64(12345) -> 64 bytes -> from_bytes_wide, reduced on the device) are SURVEY 8d's:
+    the device reduction, the CPU generator and the oracle's random_fr agree, at an offset into the stream too"""
+    import importlib
+    import torch
+    bench = importlib.import_module("bench")
+    want = O.random_fr(bench.SCALAR_SEED, 300)
+    got = bench.scalars_device_mont(ctx, bpk, torch, 0, 300).cpu().numpy().view(np.uint64)
+    assert bpk.scalars_to_ints(got) == want
+    got = bench.scalars_device_mont(ctx, bpk, torch, 137, 300).cpu().numpy().view(np.uint64)
+    assert bpk.scalars_to_ints(got) == want[137:]
+    assert bench.scalars_host_ints(137, 300) == want[137:]
+    assert bpk.scalars_to_ints(bench.scalars_host_mont(0, 50)) == want[:50]
