@@ -122,6 +122,10 @@ _SIGNATURES = {
                                 [ctypes.c_void_p] * 5),
     "bpk_plonk_quotient_evals": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                                 ctypes.c_size_t] + [ctypes.c_void_p] * 7),
+    "bpk_fr_fold": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t,
+                                   ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
+    "bpk_plonk_quotient_evals_shard": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                      ctypes.c_uint] + [ctypes.c_void_p] * 7),
     "bpk_keccak_f1600": (None, [ctypes.c_void_p]),
     "bpk_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "bpk_profile_reset": (ctypes.c_int, [ctypes.c_void_p]),
@@ -293,6 +297,19 @@ class Context:
 
     def synchronize(self):
         self.check(self.lib.bpk_synchronize(self.handle), "bpk_synchronize")
+
+    def set_stream(self, cuda_stream: int):
+        """run all later work of this context on the given cudaStream_t (0 = the legacy default stream)"""
+        if getattr(self, "_stream", 0) != int(cuda_stream):
+            self.check(self.lib.bpk_set_stream(self.handle, ctypes.c_void_p(int(cuda_stream))), "bpk_set_stream")
+            self._stream = int(cuda_stream)
+
+    def bind_torch_stream(self, torch):
+        """Callers that interleave torch ops (copies, NCCL collectives) with this library's kernels must keep both on
+        ONE stream: torch's current stream.  Outside `torch.cuda.stream(...)` that is the legacy default stream, which
+        is also the context's default, so this is a no-op then; inside, the context follows torch."""
+        s = torch.cuda.current_stream(self.device)
+        self.set_stream(0 if s == torch.cuda.default_stream(self.device) else s.cuda_stream)
 
     def imad_peak(self, mode: int = 0):
         self.set_option("imad.mode", mode)

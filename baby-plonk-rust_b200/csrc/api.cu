@@ -305,6 +305,9 @@ extern "C" int bpk_set_option(bpk_ctx* ctx, const char* key, long value) {
     } else if (k == "ntt.direct_max_log2") {
         if (value < 0 || value > 28) return BPK_ERR_INVALID_ARG;
         ctx->opt_ntt_direct_max_log2 = value;
+    } else if (k == "ntt.direct_budget_mib") {
+        if (value < 0) return BPK_ERR_INVALID_ARG;
+        ctx->opt_ntt_direct_budget_mib = value;
     } else if (k == "ntt.threads") {
         if (value != 0 && (value < 32 || value > 1024 || (value & 31))) return BPK_ERR_INVALID_ARG;
         ctx->opt_ntt_threads = value;
@@ -883,6 +886,31 @@ extern "C" int bpk_plonk_quotient_evals(bpk_ctx* ctx, const void* d_witness_eval
     for (size_t i = 0; i < domain / n; ++i) zh[i] = fr_from_host(zh_inv_mont + 4 * i);
     return plonk_quotient_evals(ctx, (const fr_t*)d_witness_evals, (const fr_t*)d_circuit_evals, domain, n, fr_from_host(beta), fr_from_host(gamma),
                                 fr_from_host(alpha), fr_from_host(k1), fr_from_host(k2), zh, (fr_t*)d_out);
+}
+
+extern "C" int bpk_plonk_quotient_evals_shard(bpk_ctx* ctx, const void* d_witness_evals, const void* d_circuit_evals,
+                                              size_t points, unsigned zh_period, const uint64_t beta[4],
+                                              const uint64_t gamma[4], const uint64_t alpha[4], const uint64_t k1[4],
+                                              const uint64_t k2[4], const uint64_t* zh_inv_mont, void* d_out) {
+    if (!ctx || !d_witness_evals || !d_circuit_evals || !beta || !gamma || !alpha || !k1 || !k2 || !zh_inv_mont || !d_out)
+        return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
+    if (points == 0 || zh_period == 0 || zh_period > 64 || (zh_period & (zh_period - 1))) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    fr_t zh[64];
+    for (unsigned i = 0; i < zh_period; ++i) zh[i] = fr_from_host(zh_inv_mont + 4 * i);
+    return plonk_quotient_evals_shard(ctx, (const fr_t*)d_witness_evals, (const fr_t*)d_circuit_evals, points, zh_period,
+                                      fr_from_host(beta), fr_from_host(gamma), fr_from_host(alpha), fr_from_host(k1),
+                                      fr_from_host(k2), zh, (fr_t*)d_out);
+}
+
+extern "C" int bpk_fr_fold(bpk_ctx* ctx, const void* d_in, size_t rows, size_t row_stride, size_t len, size_t m,
+                           const uint64_t s_mont[4], void* d_out) {
+    if (!ctx || !s_mont || (rows && m && (!d_in || !d_out))) return BPK_ERR_INVALID_ARG;
+    BPK_LOCK(ctx);
+    if (len > row_stride || (rows && m && len == 0)) return BPK_ERR_INVALID_ARG;
+    BPK_CUDA(cudaSetDevice(ctx->device));
+    return fr_fold(ctx, (const fr_t*)d_in, rows, row_stride, len, m, fr_from_host(s_mont), (fr_t*)d_out);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -68,6 +68,7 @@ struct bpk_ctx {
     bpk::fr_t* tw_hi[2] = {nullptr, nullptr};
     // per-size inter-pass twiddle tables w_{2^lg}^e, e < 2^lg (built on first use, forward / inverse)
     bpk::fr_t* tw_direct[2][bpk::NTT_MAX_LOG + 1] = {};
+    size_t tw_direct_bytes = 0;
     // coset tables for the last shift used (lo: g^i, hi: g^(i << TW_LO_BITS)), forward / inverse
     bpk::fr_t* coset_lo[2] = {nullptr, nullptr};
     bpk::fr_t* coset_hi[2] = {nullptr, nullptr};
@@ -111,6 +112,7 @@ struct bpk_ctx {
     long opt_ntt_threads = 0;
     long opt_ntt_kernel = 0;  // 0: auto, 1: one radix-2 stage per barrier, 2: register-blocked radix-8 steps
     long opt_ntt_direct_max_log2 = 25;  // largest direct twiddle table (2^25 x 32 B = 1 GiB)
+    long opt_ntt_direct_budget_mib = 3072;  // all direct tables together; beyond it they are dropped and rebuilt on demand
     long opt_imad_mode = 0;
 
     // plan of the most recent MSM (window bits, windows, pairs per accumulate thread, buckets)
@@ -162,6 +164,7 @@ inline void count_launch(bpk_ctx* ctx, uint64_t n = 1) { ctx->launches += n; }
 
 // ---- ntt.cu ----
 int ntt_init_tables(bpk_ctx* ctx);
+int ntt_drop_direct_tables(bpk_ctx* ctx);
 int ntt_run(bpk_ctx* ctx, const fr_t* d_in, fr_t* d_out, size_t n, size_t batch, bool inverse,
             const fr_t* shift /* host, Montgomery, or null */);
 int pointwise_mul(bpk_ctx* ctx, fr_t* d_a, const fr_t* d_b, size_t n);
@@ -180,6 +183,11 @@ int plonk_grand_product(bpk_ctx* ctx, const fr_t* A, const fr_t* B, const fr_t* 
                         fr_t* Z);
 int plonk_quotient_evals(bpk_ctx* ctx, const fr_t* wv, const fr_t* cv, size_t D, size_t n, const fr_t& beta,
                          const fr_t& gamma, const fr_t& alpha, const fr_t& k1, const fr_t& k2, const fr_t* zh_inv_host, fr_t* out);
+
+int plonk_quotient_evals_shard(bpk_ctx* ctx, const fr_t* wv, const fr_t* cv, size_t m, uint32_t period, const fr_t& beta,
+                               const fr_t& gamma, const fr_t& alpha, const fr_t& k1, const fr_t& k2, const fr_t* zh_inv_host,
+                               fr_t* out);
+int fr_fold(bpk_ctx* ctx, const fr_t* in, size_t rows, size_t stride, size_t len, size_t m, const fr_t& s, fr_t* out);
 
 // ---- msm.cu ----
 int msm_run(bpk_ctx* ctx, const MsmPoints& pts, const fr_t* d_scalars, size_t n, unsigned rshift,

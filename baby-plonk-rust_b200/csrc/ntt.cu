@@ -512,6 +512,19 @@ int ntt_init_tables(bpk_ctx* ctx) {
     return BPK_OK;
 }
 
+// frees every per-size twiddle table (they are rebuilt on demand); earlier passes on the stream may still read them
+int ntt_drop_direct_tables(bpk_ctx* ctx) {
+    BPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int d = 0; d < 2; d++)
+        for (auto& t : ctx->tw_direct[d])
+            if (t) {
+                cudaFree(t);
+                t = nullptr;
+            }
+    ctx->tw_direct_bytes = 0;
+    return BPK_OK;
+}
+
 static void plan_passes(uint32_t logn, uint32_t max_logR, std::vector<uint32_t>& out) {
     out.clear();
     if (logn == 0) return;
@@ -601,11 +614,30 @@ int ntt_run(bpk_ctx* ctx, const fr_t* d_in, fr_t* d_out, size_t n, size_t batch,
             const uint32_t lg = logNs + logR;
             fr_t*& tab = ctx->tw_direct[dir][lg];
             if (tab == nullptr) {
-                BPK_CUDA(cudaMalloc(&tab, sizeof(fr_t) << lg));
-                direct_table_kernel<<<(unsigned)(((size_t)1 << lg) + 255) / 256, 256, 0, ctx->stream>>>(
-                    tab, ctx->tw_lo[dir], ctx->tw_hi[dir], 1u << lg, NTT_MAX_LOG - lg);
-                count_launch(ctx);
-                BPK_CUDA(cudaGetLastError());
+                // the per-size tables are a cache: keep their total under the budget (a context that transforms at many
+                // sizes would otherwise pin GiBs next to the SRS), and give them back when HBM is short
+                const size_t want = sizeof(fr_t) << lg;
+                const size_t budget = (size_t)ctx->opt_ntt_direct_budget_mib << 20;
+                if (want <= budget) {
+                    if (ctx->tw_direct_bytes + want > budget) BPK_TRY(ntt_drop_direct_tables(ctx));
+                    cudaError_t e = cudaMalloc(&tab, want);
+                    if (e == cudaErrorMemoryAllocation) {
+                        cudaGetLastError();
+                        BPK_TRY(ntt_drop_direct_tables(ctx));
+                        e = cudaMalloc(&tab, want);
+                    }
+                    if (e == cudaErrorMemoryAllocation) {  // still no room: this pass multiplies two table entries instead
+                        cudaGetLastError();
+                        tab = nullptr;
+                    } else {
+                        BPK_CUDA(e);
+                        ctx->tw_direct_bytes += want;
+                        direct_table_kernel<<<(unsigned)(((size_t)1 << lg) + 255) / 256, 256, 0, ctx->stream>>>(
+                            tab, ctx->tw_lo[dir], ctx->tw_hi[dir], 1u << lg, NTT_MAX_LOG - lg);
+                        count_launch(ctx);
+                        BPK_CUDA(cudaGetLastError());
+                    }
+                }
             }
             p.tw_direct = tab;
         }

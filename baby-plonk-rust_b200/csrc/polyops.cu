@@ -168,8 +168,11 @@ __global__ void __launch_bounds__(128) plonk_ratio_kernel(const fr_t* __restrict
 struct QuotientParams {
     fr_t beta, gamma, alpha, alpha2, k1, k2;
 };
+// Sharded form (one rank of a multi-GPU proof evaluates t on ONE sub-coset of the quotient domain): z(w x) is not a
+// rotation of z's row there, so it comes as a sixth witness row (`zw_row`), and 1 / Z_H has `ratio` = max(1, 4 / ranks)
+// distinct values.
 __global__ void __launch_bounds__(256) plonk_quotient_kernel(const fr_t* __restrict__ wv, const fr_t* __restrict__ cv,
-                                                              size_t D, uint32_t ratio,
+                                                              size_t D, uint32_t ratio, int zw_row,
                                                               const fr_t* __restrict__ zh_inv, QuotientParams P,
                                                               fr_t* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -186,9 +189,14 @@ __global__ void __launch_bounds__(256) plonk_quotient_kernel(const fr_t* __restr
         fr_t bx = mul(P.beta, cir(9));
         fr_t ag = add(a, P.gamma), bg = add(b, P.gamma), cg = add(c, P.gamma);
         fr_t lhs = mul(mul(add(ag, bx), add(bg, mul(bx, P.k1))), mul(add(cg, mul(bx, P.k2)), z));
-        size_t j = i + ratio;
-        if (j >= D) j -= D;
-        fr_t zw = pld(wv + 3 * D + j);
+        fr_t zw;
+        if (zw_row) {
+            zw = wit(5);
+        } else {
+            size_t j = i + ratio;
+            if (j >= D) j -= D;
+            zw = pld(wv + 3 * D + j);
+        }
         fr_t rhs = mul(mul(add(ag, mul(P.beta, cir(5))), add(bg, mul(P.beta, cir(6)))),
                        mul(add(cg, mul(P.beta, cir(7))), zw));
         fr_t first = mul(sub(z, fr_t::one()), cir(8));
@@ -363,10 +371,61 @@ int plonk_quotient_evals(bpk_ctx* ctx, const fr_t* wv, const fr_t* cv, size_t D,
     BPK_TRY(ws_reserve(ctx, 12, 64 * sizeof(fr_t), (void**)&d_zh));
     BPK_CUDA(cudaMemcpyAsync(d_zh, zh_inv_host, ratio * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
     QuotientParams P{beta, gamma, alpha, mul(alpha, alpha), k1, k2};
-    plonk_quotient_kernel<<<grid_for(ctx, D, 256), 256, 0, ctx->stream>>>(wv, cv, D, ratio, d_zh, P, out);
+    plonk_quotient_kernel<<<grid_for(ctx, D, 256), 256, 0, ctx->stream>>>(wv, cv, D, ratio, 0, d_zh, P, out);
     count_launch(ctx);
     BPK_CUDA(cudaGetLastError());
     // the pageable H2D copy above is staged by the runtime before it returns, so zh_inv_host may be reused
+    t.end();
+    return BPK_OK;
+}
+
+// the same on one sub-coset of `m` points: witness rows a b c z PI z(wX), `period` values of 1 / Z_H
+int plonk_quotient_evals_shard(bpk_ctx* ctx, const fr_t* wv, const fr_t* cv, size_t m, uint32_t period, const fr_t& beta,
+                               const fr_t& gamma, const fr_t& alpha, const fr_t& k1, const fr_t& k2, const fr_t* zh_inv_host,
+                               fr_t* out) {
+    if (m == 0 || period == 0 || period > 64 || (period & (period - 1))) return BPK_ERR_INVALID_ARG;
+    StageTimer t(ctx, "plonk.quotient");
+    fr_t* d_zh;
+    BPK_TRY(ws_reserve(ctx, 12, 64 * sizeof(fr_t), (void**)&d_zh));
+    BPK_CUDA(cudaMemcpyAsync(d_zh, zh_inv_host, period * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    QuotientParams P{beta, gamma, alpha, mul(alpha, alpha), k1, k2};
+    plonk_quotient_kernel<<<grid_for(ctx, m, 256), 256, 0, ctx->stream>>>(wv, cv, m, period, 1, d_zh, P, out);
+    count_launch(ctx);
+    BPK_CUDA(cudaGetLastError());
+    t.end();
+    return BPK_OK;
+}
+
+// out[r][k] = sum_q in[r][k + q m] * s^q  (k < m, k + q m < len): the coefficients of p(X) mod (X^m - s), i.e. of the
+// polynomial that agrees with p wherever X^m = s -- on a coset of the m-th roots of unity.  rows stored `stride` apart.
+__global__ void __launch_bounds__(256) fr_fold_kernel(const fr_t* __restrict__ in, size_t rows, size_t stride, size_t len,
+                                                       size_t m, fr_t s, fr_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+    for (; i < rows * m; i += step) {
+        const size_t r = i / m, k = i - r * m;
+        const fr_t* src = in + r * stride;
+        if (k >= len) {
+            pst(out + i, fr_t::zero());
+            continue;
+        }
+        size_t top = k;
+        while (top + m < len) top += m;  // Horner from the highest chunk down
+        fr_t acc = pld(src + top);
+        while (top >= m + k) {
+            top -= m;
+            acc = add(mul(acc, s), pld(src + top));
+        }
+        pst(out + i, acc);
+    }
+}
+
+int fr_fold(bpk_ctx* ctx, const fr_t* in, size_t rows, size_t stride, size_t len, size_t m, const fr_t& s, fr_t* out) {
+    if (rows == 0 || m == 0) return BPK_OK;
+    StageTimer t(ctx, "fr.fold");
+    fr_fold_kernel<<<grid_for(ctx, rows * m, 256), 256, 0, ctx->stream>>>(in, rows, stride, len, m, s, out);
+    count_launch(ctx);
+    BPK_CUDA(cudaGetLastError());
     t.end();
     return BPK_OK;
 }

@@ -81,8 +81,10 @@ class ShardedCommitter:
     def commit_device(self, d_scalars) -> "torch.Tensor":
         """d_scalars: int64 tensor holding this rank's (hi - lo) x 4 u64 Montgomery limbs in HBM.
         Returns the normalised commitment (int64[18] on the device), identical on every rank."""
+        import torch
         import torch.distributed as dist
 
+        self.ctx.bind_torch_stream(torch)
         lib, h = self.ctx.lib, self.ctx.handle
         n = self.hi - self.lo
         if self.world == 1:
@@ -101,8 +103,10 @@ class ShardedCommitter:
         rank's HBM (the device prover keeps identical state on all ranks): each rank multiplies only its own
         index range of the coefficients with its SRS slice, then the partial sums are gathered and added.
         d_coeffs: int64 tensor [>= length, 4].  Returns the normalised commitment, identical on every rank."""
+        import torch
         import torch.distributed as dist
 
+        self.ctx.bind_torch_stream(torch)
         lib, h = self.ctx.lib, self.ctx.handle
         first, count = slice_of_prefix(self.lo, self.hi, length)
         src = d_coeffs[first:first + count] if count else d_coeffs[0:1]
@@ -125,6 +129,7 @@ class ShardedCommitter:
         import torch
         import torch.distributed as dist
 
+        self.ctx.bind_torch_stream(torch)
         lib, h = self.ctx.lib, self.ctx.handle
         k = len(items)
         srcs, counts = [], []
@@ -152,8 +157,10 @@ class ShardedCommitter:
     def commit_host(self, scalars: np.ndarray, d_staging=None) -> np.ndarray:
         """end-to-end: this rank's scalars in (pinned) host memory -> sharded MSM -> commitment on the host.
         The upload is pipelined with the accumulation inside bpk_msm_g1_from_host (include/bpk.h)."""
+        import torch
         import torch.distributed as dist
 
+        self.ctx.bind_torch_stream(torch)
         lib, h = self.ctx.lib, self.ctx.handle
         sc = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
         n = sc.shape[0]

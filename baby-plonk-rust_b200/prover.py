@@ -106,7 +106,7 @@ class DeviceProver:
     """
 
     def __init__(self, setup: Setup, group_order: int, selectors: Sequence[np.ndarray], sigmas: Sequence[np.ndarray],
-                 cache_preprocessed: bool = False, committer=None):
+                 cache_preprocessed: bool = False, committer=None, round3_shards: int = 0):
         import torch  # device memory only
 
         if not is_power_of_two(group_order):
@@ -133,6 +133,17 @@ class DeviceProver:
         self.pk_lagrange = self._upload(np.stack(cols))          # [8, n, 4]: ql qr qm qo qc s1 s2 s3
         self.cache_preprocessed = cache_preprocessed
         self._pre = None
+        # Round 3 dealt over the ranks ("independent NTTs of a round are dealt to different GPUs"): the quotient
+        # domain g<w_D> is the union of R sub-cosets (g w_D^j)<w_m>, m = D / R; rank j transforms the sixteen
+        # polynomials of the round onto ITS sub-coset only (fold mod X^m - s, one size-m coset transform each),
+        # evaluates t there, and the ranks exchange m x 32 bytes each.  Without a committer, round3_shards = R > 1 runs
+        # the R parts one after the other on this GPU (same arithmetic, used by the single-GPU parity tests).
+        world = 1 if committer is None else committer.world
+        self.shards = int(round3_shards) if round3_shards else world
+        if self.shards < 1 or self.shards & (self.shards - 1) or self.shards > self.domain:
+            raise ValueError("round3_shards must be a power of two <= the quotient domain")
+        if committer is not None and world > 1 and self.shards != world:
+            raise ValueError("with a committer, round 3 is dealt over exactly its ranks")
         w = root_of_unity(self.domain)
         gn = pow(COSET_SHIFT, n, Q)
         wn = pow(w, n, Q)
@@ -233,6 +244,78 @@ class DeviceProver:
         self._ck(self.lib.bpk_fr_poly_div_linear(self.ctx.handle, coeffs.data_ptr(), length, rm.ctypes.data,
                                                  out.data_ptr()), "bpk_fr_poly_div_linear")
 
+    # ---- round 3 on sub-cosets ---------------------------------------------------------------------
+    def _subcoset_shift(self, j: int) -> int:
+        return COSET_SHIFT * pow(root_of_unity(self.domain), j, Q) % Q
+
+    def _subcoset_evals(self, rows, length: int, j: int):
+        """rows: [k, stride, 4] coefficient rows (`length` coefficients each) -> their values on sub-coset j, [k, m, 4]:
+        p mod (X^m - s^m) has p's values wherever X^m = s^m, so fold, then one size-m coset transform per row"""
+        m = self.domain // self.shards
+        k, stride = rows.shape[0], rows.shape[1]
+        s = self._subcoset_shift(j)
+        out = self._empty(k, m)
+        sm = _mont(pow(s, m, Q))
+        self._ck(self.lib.bpk_fr_fold(self.ctx.handle, rows.data_ptr(), k, stride, length, m, sm.ctypes.data,
+                                      out.data_ptr()), "bpk_fr_fold")
+        sh = _mont(s)
+        self._ck(self.lib.bpk_ntt_fr_dev(self.ctx.handle, out.data_ptr(), out.data_ptr(), m, k, 2, sh.ctypes.data),
+                 "bpk_ntt_fr_dev")
+        return out
+
+    def _zh_inv_subcoset(self, j: int):
+        """1 / Z_H on sub-coset j: x^n = s^n (w_m^n)^i takes max(1, ratio / R) values"""
+        n, m = self.n, self.domain // self.shards
+        period = max(1, self.ratio // self.shards)
+        sn = pow(self._subcoset_shift(j), n, Q)
+        wmn = pow(root_of_unity(self.domain), self.shards * n, Q)
+        return period, scalars_from_ints([pow((sn * pow(wmn, i, Q) - 1) % Q, -1, Q) for i in range(period)])
+
+    def _circuit_rows(self, coeffs):
+        """coefficient rows of the ten per-circuit polynomials of round 3: ql qr qm qo qc s1 s2 s3 L1 X"""
+        n = self.n
+        rows = self._zeros(10, n)
+        rows[0:8].copy_(coeffs)
+        rows[8, :n] = self.torch.from_numpy(_mont(pow(n, -1, Q)).view(np.int64)).to(self.dev)   # L1 = (1/n) sum X^i
+        rows[9, 1] = self.torch.from_numpy(self._one.view(np.int64)).to(self.dev)              # the polynomial X
+        return rows
+
+    def _quotient_sharded(self, wv, coeffs, beta, gamma, alpha):
+        """t on the whole quotient domain (natural order), computed sub-coset by sub-coset: this rank's part and an
+        all-gather with a committer, all R parts locally without one"""
+        torch, n, D, L, R = self.torch, self.n, self.domain, self.stride, self.shards
+        m = D // R
+        rows6 = self._zeros(6, L)
+        rows6[0:5].copy_(wv[:, :L])
+        one = self._one
+        wm = _mont(self.omega)
+        self._ck(self.lib.bpk_fr_scale_powers(self.ctx.handle, rows6[3].data_ptr(), wm.ctypes.data, one.ctypes.data,
+                                              rows6[5].data_ptr(), n + 3), "bpk_fr_scale_powers")     # z(wX)
+        crow = self._circuit_rows(coeffs)
+        sc = _Scalars(beta, gamma, alpha, K1, K2)
+        multi = self.committer is not None and self.committer.world > 1
+        mine = [self.committer.rank] if multi else list(range(R))
+        parts = self._empty(len(mine), m)
+        for slot, j in enumerate(mine):
+            if self.cache_preprocessed and self._pre is not None and j in self._pre[2]:
+                ec = self._pre[2][j]
+            else:
+                ec = self._subcoset_evals(crow, n, j)
+                if self.cache_preprocessed and self._pre is not None:
+                    self._pre[2][j] = ec
+            ew = self._subcoset_evals(rows6, L, j)
+            period, zh = self._zh_inv_subcoset(j)
+            self._ck(self.lib.bpk_plonk_quotient_evals_shard(
+                self.ctx.handle, ew.data_ptr(), ec.data_ptr(), m, period, *sc.ptrs(), zh.ctypes.data,
+                parts[slot].data_ptr()), "bpk_plonk_quotient_evals_shard")
+        if multi:
+            import torch.distributed as dist
+            gathered = self._empty(R, m)
+            dist.all_gather_into_tensor(gathered.view(-1), parts.view(-1), group=self.committer.group)
+            parts = gathered
+        # point j + R i of the domain is point i of sub-coset j
+        return parts.permute(1, 0, 2).contiguous().view(D, 4)
+
     def _preprocessed(self):
         """Per-circuit data of round 3: coefficient forms of the eight pre-processed columns (the reference
         runs these i_ntt_381 on every prove, prover.rs round 3) and the coset evaluations of
@@ -242,13 +325,18 @@ class DeviceProver:
         n, D = self.n, self.domain
         coeffs = self._empty(8, n)
         self._intt(self.pk_lagrange, coeffs, n, 8)
+        if self.shards > 1:   # the per-circuit evaluations are made per sub-coset (and cached there)
+            pre = (coeffs, None, {})
+            if self.cache_preprocessed:
+                self._pre = pre
+            return pre
         cv = self._zeros(10, D)
         cv[0:8, :n].copy_(coeffs)
         cv[8, :n] = self.torch.from_numpy(_mont(pow(n, -1, Q)).view(np.int64)).to(self.dev)   # L1 = (1/n) sum X^i
         cv[9, 1] = self.torch.from_numpy(self._one.view(np.int64)).to(self.dev)              # the polynomial X
         self._ck(self.lib.bpk_ntt_fr_dev(self.ctx.handle, cv.data_ptr(), cv.data_ptr(), D, 10, 2,    # 2 = coset
                                          self._shift.ctypes.data), "bpk_ntt_fr_dev")
-        pre = (coeffs, cv)
+        pre = (coeffs, cv, {})
         if self.cache_preprocessed:
             self._pre = pre
         return pre
@@ -279,6 +367,7 @@ class DeviceProver:
         values in declaration order; ``blinding`` the 11 scalars b_1..b_11 the reference draws from
         thread_rng (prover.rs:108-110)."""
         torch = self.torch
+        self.ctx.bind_torch_stream(torch)   # torch copies / collectives and the library's kernels share one stream
         n, D, L = self.n, self.domain, self.stride
         b = [int(x) % Q for x in blinding]
         if len(b) != 11:
@@ -332,7 +421,7 @@ class DeviceProver:
         marks.append(("round2", time.perf_counter()))
 
         # ---- round 3 (prover.rs:370-500)
-        pk, cv = self._preprocessed()
+        pk, cv, _ = self._preprocessed()
         ql, qr, qm, qo, qc, s1c, s2c, s3c = (pk[i] for i in range(8))
         pi_l = self._zeros(n)
         if len(public_inputs):
@@ -341,13 +430,16 @@ class DeviceProver:
         # keep the coefficient forms (rounds 4-5 need them), transform a copy
         keep = self._empty(5, L)
         keep.copy_(wv[:, :L])
-        self._ck(self.lib.bpk_ntt_fr_dev(self.ctx.handle, wv.data_ptr(), wv.data_ptr(), D, 5, 2,     # 2 = coset
-                                         self._shift.ctypes.data), "bpk_ntt_fr_dev")
-        t = self._empty(D)
-        sc = _Scalars(beta, gamma, alpha, K1, K2)
-        self._ck(self.lib.bpk_plonk_quotient_evals(
-            self.ctx.handle, wv.data_ptr(), cv.data_ptr(), D, n, *sc.ptrs(), self._zh_inv.ctypes.data, t.data_ptr()),
-            "bpk_plonk_quotient_evals")
+        if self.shards > 1:
+            t = self._quotient_sharded(wv, pk, beta, gamma, alpha)
+        else:
+            self._ck(self.lib.bpk_ntt_fr_dev(self.ctx.handle, wv.data_ptr(), wv.data_ptr(), D, 5, 2,     # 2 = coset
+                                             self._shift.ctypes.data), "bpk_ntt_fr_dev")
+            t = self._empty(D)
+            sc = _Scalars(beta, gamma, alpha, K1, K2)
+            self._ck(self.lib.bpk_plonk_quotient_evals(
+                self.ctx.handle, wv.data_ptr(), cv.data_ptr(), D, n, *sc.ptrs(), self._zh_inv.ctypes.data, t.data_ptr()),
+                "bpk_plonk_quotient_evals")
         del wv, cv
         row = {name: keep[i] for i, name in enumerate(("a", "b", "c", "z", "pi"))}
         z = row["z"]

@@ -195,6 +195,23 @@ int bpk_plonk_quotient_evals(bpk_ctx* ctx, const void* d_witness_evals, const vo
                              size_t n, const uint64_t beta[4], const uint64_t gamma[4], const uint64_t alpha[4],
                              const uint64_t k1[4], const uint64_t k2[4], const uint64_t* zh_inv_mont, void* d_out);
 
+/* Multi-GPU form of round 3 (the independent transforms of the round dealt over the ranks): the quotient
+ * domain g <w_4n> is the union of R sub-cosets (g w_4n^j) <w_m>, m = 4n / R; rank j evaluates t on its own one.
+ *   bpk_fr_fold             out[r][k] = sum_q in[r][k + q m] s^q: coefficients of p mod (X^m - s), s = (g w_4n^j)^m; a coset
+ *                           NTT of size m with shift g w_4n^j (bpk_ntt_fr_dev) then yields p on the sub-coset.  `rows`
+ *                           polynomials of `len` coefficients, stored row_stride apart.
+ *   bpk_plonk_quotient_evals_shard   as bpk_plonk_quotient_evals on `points` = m points, witness rows a, b, c, z, PI and
+ *                           z(wX) (a sixth row: on a sub-coset it is not a rotation of z's), zh_period = max(1, 4 / R)
+ *                           values 1 / Z_H(g w_4n^j w_m^i), i < zh_period.
+ * The ranks' parts are gathered (NCCL all-gather of m x 32 B per rank), interleaved (point j + R i) and interpolated by
+ * one inverse coset NTT of size 4n. */
+int bpk_fr_fold(bpk_ctx* ctx, const void* d_in, size_t rows, size_t row_stride, size_t len, size_t m,
+                const uint64_t s_mont[4], void* d_out);
+int bpk_plonk_quotient_evals_shard(bpk_ctx* ctx, const void* d_witness_evals, const void* d_circuit_evals, size_t points,
+                                   unsigned zh_period, const uint64_t beta[4], const uint64_t gamma[4],
+                                   const uint64_t alpha[4], const uint64_t k1[4], const uint64_t k2[4],
+                                   const uint64_t* zh_inv_mont, void* d_out);
+
 /* ---- host utility ---------------------------------------------------------------------------------
  * keccak-f[1600] on 25 little-endian 64-bit lanes (lane x + 5 y), in place; runs on the host.  The Fiat-Shamir
  * transcript of the reference (src/transcript.rs over merlin / STROBE-128) sits on it; the Python host layer calls
@@ -228,7 +245,8 @@ int bpk_imad_peak(bpk_ctx* ctx, double* wide_imad_per_s_out, double* seconds_out
  *   "ntt.tile_log2" log2 of the R x C tile per CTA (default 10), "ntt.max_radix_log2" (0 = auto), "ntt.threads",
  *   "ntt.kernel" 0 = auto, 1 = one radix-2 stage per barrier, 2 = register-blocked radix-8 steps, 3 = 4 rows per
  *   thread with two products per call (auto uses it below 2^18 elements),
- *   "ntt.direct_max_log2" largest per-size inter-pass twiddle table, "imad.mode" probe form of bpk_imad_peak.
+ *   "ntt.direct_max_log2" largest per-size inter-pass twiddle table, "ntt.direct_budget_mib" HBM budget of all
+ *   such tables together (a cache: dropped and rebuilt on demand beyond it, or when an allocation fails), "imad.mode" probe form of bpk_imad_peak.
  * Unknown keys and out-of-range values return BPK_ERR_INVALID_ARG. */
 int bpk_set_option(bpk_ctx* ctx, const char* key, long value);
 

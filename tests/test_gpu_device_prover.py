@@ -294,3 +294,29 @@ def test_full_size_proofs_verify_against_oracle_commitments(ctx, logn):
         assert not P.verify_columns(n, sel, sig, proof, pub, 101)
         proof.t_mid_1 = O.g1_add(proof.t_mid_1, O.g1_neg(O.G1_GEN))
         assert not P.verify_columns(n, sel, sig, proof, [pub[0] + 1], 101)
+
+
+@pytest.mark.parametrize("shards", [2, 4, 8, 16])
+def test_round3_on_subcosets_gives_the_same_proof(ctx, shards):
+    """the multi-GPU form of round 3 (each rank evaluates the quotient on one sub-coset of the 4n domain: fold mod
+    X^m - s, size-m coset transforms, sharded quotient kernel, interleave, one inverse transform) run on ONE GPU, all
+    parts in turn: byte-identical proofs for the reference's own test program and for synthetic circuits, with and
+    without cached per-circuit evaluations"""
+    prover_mod = importlib.import_module("baby-plonk-rust_b200.prover")
+    prog, wit, pub = P.reference_test_circuit()
+    setup = bpk.Setup.generate_srs(14, 101, ctx)
+    wires, sel, sig = columns(prog, wit)
+    prover = prover_mod.DeviceProver(setup, prog.n, sel, sig, round3_shards=shards)
+    proof = prover.prove(wires, pub, list(range(1, 12)))
+    assert proof.sha256() == "479cc377c535fd831b5fcaf30af5c2756c535a3ddbc20589ab6759843e974967"   # SURVEY 8c
+    setup.free()
+    for n, used, cache in ((64, 50, False), (512, 500, True)):
+        prog, wit, pub = P.synthetic_circuit(n, used, seed=shards + n)
+        setup = bpk.Setup.generate_srs(n + 6, 101, ctx)
+        wires, sel, sig = columns(prog, wit)
+        plain = prover_mod.DeviceProver(setup, n, sel, sig)
+        dealt = prover_mod.DeviceProver(setup, n, sel, sig, cache_preprocessed=cache, round3_shards=shards)
+        for seed in (42, 43):
+            blinding = O.random_fr(seed, 11)
+            assert dealt.prove(wires, pub, blinding).to_bytes() == plain.prove(wires, pub, blinding).to_bytes()
+        setup.free()

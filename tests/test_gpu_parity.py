@@ -689,7 +689,7 @@ def test_kernels_really_launch(ctx):
     ms_ntt, l_ntt = ctx.profile_get("ntt.pass")
     ms_acc, l_acc = ctx.profile_get("msm.accumulate")
     ctx.profile_enable(False)
-    assert l_ntt == 2 and ms_ntt > 0
+    assert l_ntt in (2, 3) and ms_ntt > 0      # two passes (+ the lazily built inter-pass twiddle table)
     assert l_acc == 1 and ms_acc > 0
     assert ctx.launch_count() >= 8
     setup.free()
