@@ -232,6 +232,13 @@ def cpu_reference_sample(n_target, threads):
     return run, check, n_s, sample
 
 
+def workload_name(logn, world):
+    """config.workload, shared by both arms so that the driver compares like with like"""
+    return ("configs[1]: standalone G1 MSM, 2^%d uniform Fr scalars (SplitMix64 seed %d, from_bytes_wide) x "
+            "synthetic SRS [tau^i]G (tau=%d)" % (logn, SCALAR_SEED, TAU)
+            + (", sharded over %d GPUs by index range + NCCL all-gather of partials (configs[4])" % world if world > 1 else ""))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -252,8 +259,8 @@ def run_reference(args):
         "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": "configs[1]/[4]: standalone G1 MSM, 2^%d uniform Fr scalars (SplitMix64 seed %d) x synthetic "
-                               "SRS [tau^i]G (tau=%d), reference CPU algorithm on host cores" % (args.logn, SCALAR_SEED, TAU)},
+        "config": {"workload": workload_name(args.logn, args.gpus), "pairs": n,
+                   "arm": "reference CPU algorithm on the host cores (the GPUs are not used)"},
         "cpu_baseline": {"value": ms, "unit": "ms", "cores": threads, "kind": "port", "sample": sample,
                          "sample_seconds_per_step": float(np.mean(times)) * n_s / n / 1e3, "sample_verified": bool(ok)},
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -438,6 +445,7 @@ def main():
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     launches = ctx.launch_count()
     plan = ctx.msm_last_plan()
+    stats = ctx.msm_last_stats()      # of the device-resident MSM just timed (the e2e legs below run two slices)
     stages = {}
     for nm in STAGES:
         ms, cnt = ctx.profile_get(nm)
@@ -490,7 +498,6 @@ def main():
     # a 32x32->64 IMAD.WIDE retires at 32 / clk / SM on sm_100 in every form (profiles/r1_imad_forms.md) and counts
     # as 2 lo/hi IMADs in SURVEY 8d's algorithmic figure, so the measured peak in those units is 2 x the probe rate
     peak = 2.0 * max(chain_rate, fused_rate) / 1e12
-    stats = ctx.msm_last_stats()
     executed = stats["affine_adds"] * IMAD_ADD_AFFINE + stats["xyzz_adds_bound"] * IMAD_MADD_XYZZ
     traffic, traffic_source = ncu_traffic(args, world)
     roofline = {
@@ -542,9 +549,7 @@ def main():
             "value": ms_step, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic", "verified": verified,
-            "config": {"workload": "configs[1]: standalone G1 MSM, 2^%d uniform Fr scalars (SplitMix64 seed %d, from_bytes_wide) x "
-                                   "synthetic SRS [tau^i]G (tau=%d)" % (args.logn, SCALAR_SEED, TAU)
-                                   + (", sharded over %d GPUs by index range + NCCL all-gather of partials (configs[4])" % world if world > 1 else ""),
+            "config": {"workload": workload_name(args.logn, world),
                        "pairs": n_total, "pairs_per_gpu": n_local, "l2": "inputs larger than L2 (scalars %d MiB + SRS %d MiB per GPU)"
                        % (n_local * 32 >> 20, n_local * 96 >> 20), "parallelism": "index-range shards x%d" % world,
                        "srs": "resident in HBM" + ("" if args.no_precompute else " with precomputed window levels (bpk_srs_precompute)"),

@@ -1,0 +1,14 @@
+#!/bin/bash
+# Round 2, end of round: launch list of the default bench + ncu --set full of the MSM tree levels, the sort kernels
+# and the NTT passes (run under gpurun, 1 GPU).  usage: profiles/scripts/r2_profile_final.sh <tag>
+TAG=${1:-r2z}
+CMD="python bench.py --steps 1 --warmup 1 --no-extras --no-cpu --no-verify"
+NTT="python profiles/scripts/ntt_only.py 22"
+mkdir -p gpurun_out
+$CMD > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
+# the timed MSM is the second one: skip the levels of the warm-up MSM
+ncu --set full --clock-control none --import-source on -k regex:msm_affine_level -s 8 -c 8 -o gpurun_out/${TAG}_affine $CMD > gpurun_out/${TAG}_ncu_affine.log 2>&1
+ncu --set full --clock-control none -k regex:"msm_scatter|msm_count|msm_level_offsets|msm_accumulate_kernel|msm_plane_tree_level" -s 12 -c 10 -o gpurun_out/${TAG}_sort $CMD > gpurun_out/${TAG}_ncu_sort.log 2>&1
+$NTT > gpurun_out/${TAG}_ntt_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:ntt_pass_r8 -s 9 -c 3 -o gpurun_out/${TAG}_ntt $NTT > gpurun_out/${TAG}_ncu_ntt.log 2>&1
+ls -la gpurun_out/${TAG}_*
