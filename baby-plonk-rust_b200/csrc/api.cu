@@ -67,6 +67,53 @@ int profile_collect(bpk_ctx* ctx) {
     return BPK_OK;
 }
 
+// ---- uploads from pageable host memory ------------------------------------------------------------
+int upload_host(bpk_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, cudaStream_t stream) {
+    if (bytes == 0) return BPK_OK;
+    bool pageable = false;
+    if (bytes >= ((size_t)8 << 20) && ctx->opt_host_stage_threads > 0) {
+        cudaPointerAttributes attr;
+        cudaError_t e = cudaPointerGetAttributes(&attr, h_src);
+        if (e != cudaSuccess) cudaGetLastError();
+        pageable = e == cudaSuccess && attr.type == cudaMemoryTypeUnregistered;
+    }
+    if (!pageable) {
+        BPK_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream));
+        return BPK_OK;
+    }
+    for (int i = 0; i < bpk_ctx::STAGE_RING; i++) {
+        if (!ctx->stage_buf[i]) {
+            BPK_CUDA(cudaHostAlloc(&ctx->stage_buf[i], bpk_ctx::STAGE_CHUNK, cudaHostAllocDefault));
+            BPK_CUDA(cudaEventCreateWithFlags(&ctx->stage_done[i], cudaEventDisableTiming));
+            BPK_CUDA(cudaEventRecord(ctx->stage_done[i], stream));
+        }
+    }
+    const int nthreads = (int)(ctx->opt_host_stage_threads > 16 ? 16 : ctx->opt_host_stage_threads);
+    const char* src = static_cast<const char*>(h_src);
+    char* dst = static_cast<char*>(d_dst);
+    size_t k = 0;
+    for (size_t off = 0; off < bytes; off += bpk_ctx::STAGE_CHUNK, k++) {
+        const size_t len = bytes - off < bpk_ctx::STAGE_CHUNK ? bytes - off : bpk_ctx::STAGE_CHUNK;
+        const int slot = (int)(k % bpk_ctx::STAGE_RING);
+        BPK_CUDA(cudaEventSynchronize(ctx->stage_done[slot]));   // the copy that last used this buffer has drained
+        char* stage = static_cast<char*>(ctx->stage_buf[slot]);
+        std::thread workers[16];
+        const size_t per = ((len + nthreads - 1) / nthreads + 4095) & ~(size_t)4095;
+        int started = 0;
+        for (int t = 1; t < nthreads; t++) {
+            const size_t lo = per * t;
+            if (lo >= len) break;
+            const size_t cnt = len - lo < per ? len - lo : per;
+            workers[started++] = std::thread([=] { memcpy(stage + lo, src + off + lo, cnt); });
+        }
+        memcpy(stage, src + off, len < per ? len : per);
+        for (int t = 0; t < started; t++) workers[t].join();
+        BPK_CUDA(cudaMemcpyAsync(dst + off, stage, len, cudaMemcpyHostToDevice, stream));
+        BPK_CUDA(cudaEventRecord(ctx->stage_done[slot], stream));
+    }
+    return BPK_OK;
+}
+
 // ---- IMAD throughput probe ---------------------------------------------------------------------
 // (hi:lo) += a * b: the mad.lo.cc / madc.hi pair that ptxas fuses into one IMAD.WIDE.U32 Rd, Ra, Rb, Rd
 __device__ __forceinline__ void probe_mad_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
@@ -252,6 +299,10 @@ extern "C" void bpk_destroy(bpk_ctx* ctx) {
     if (ctx->lane_fork) cudaEventDestroy(ctx->lane_fork);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    for (int i = 0; i < bpk_ctx::STAGE_RING; i++) {
+        if (ctx->stage_buf[i]) cudaFreeHost(ctx->stage_buf[i]);
+        if (ctx->stage_done[i]) cudaEventDestroy(ctx->stage_done[i]);
+    }
     delete ctx;
 }
 
@@ -312,7 +363,10 @@ extern "C" int bpk_set_option(bpk_ctx* ctx, const char* key, long value) {
         if (value != 0 && (value < 32 || value > 1024 || (value & 31))) return BPK_ERR_INVALID_ARG;
         ctx->opt_ntt_threads = value;
     } else if (k == "ntt.kernel") ctx->opt_ntt_kernel = value;
-    else if (k == "imad.mode") ctx->opt_imad_mode = value;
+    else if (k == "host.stage_threads") {
+        if (value < 0 || value > 16) return BPK_ERR_INVALID_ARG;
+        ctx->opt_host_stage_threads = value;
+    } else if (k == "imad.mode") ctx->opt_imad_mode = value;
     else return BPK_ERR_INVALID_ARG;
     return BPK_OK;
 }
@@ -344,9 +398,9 @@ extern "C" int bpk_srs_load(bpk_ctx* ctx, const uint64_t* points_xyz, size_t n, 
         if (s != BPK_OK) { cudaFree(pts); return s; }
         for (size_t off = 0; off < n; off += slice) {
             size_t cnt = n - off < slice ? n - off : slice;
-            cudaError_t e = cudaMemcpyAsync(d_xyz, points_xyz + 18 * off, cnt * 18 * sizeof(uint64_t),
-                                            cudaMemcpyHostToDevice, ctx->stream);
-            if (e != cudaSuccess) { cudaFree(pts); return cuda_fail(ctx, e, "srs upload", __FILE__, __LINE__); }
+            s = upload_host(ctx, d_xyz, points_xyz + 18 * off, cnt * 18 * sizeof(uint64_t), ctx->stream);
+            if (s != BPK_OK) { cudaFree(pts); return s; }
+            cudaError_t e;
             s = srs_from_projective(ctx, d_xyz, cnt, pts + off);
             if (s != BPK_OK) { cudaFree(pts); return s; }
             e = cudaStreamSynchronize(ctx->stream);
@@ -636,7 +690,7 @@ static int ntt_host(bpk_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, s
     size_t bytes = n * batch * sizeof(fr_t);
     fr_t* d_buf;
     BPK_TRY(ws_reserve(ctx, 9, bytes, (void**)&d_buf));
-    BPK_CUDA(cudaMemcpyAsync(d_buf, in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    BPK_TRY(upload_host(ctx, d_buf, in, bytes, ctx->stream));
     fr_t sh;
     if (shift) sh = fr_from_host(shift);
     BPK_TRY(ntt_run(ctx, d_buf, d_buf, n, batch, inverse, shift ? &sh : nullptr));
@@ -686,8 +740,8 @@ extern "C" int bpk_poly_mul_fr(bpk_ctx* ctx, const uint64_t* a, size_t la, const
     fr_t* d_buf;
     BPK_TRY(ws_reserve(ctx, 9, 2 * D * sizeof(fr_t), (void**)&d_buf));
     BPK_CUDA(cudaMemsetAsync(d_buf, 0, 2 * D * sizeof(fr_t), ctx->stream));
-    BPK_CUDA(cudaMemcpyAsync(d_buf, a, la * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
-    BPK_CUDA(cudaMemcpyAsync(d_buf + D, b, lb * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    BPK_TRY(upload_host(ctx, d_buf, a, la * sizeof(fr_t), ctx->stream));
+    BPK_TRY(upload_host(ctx, d_buf + D, b, lb * sizeof(fr_t), ctx->stream));
     BPK_TRY(ntt_run(ctx, d_buf, d_buf, D, 2, false, nullptr));      // both operands to evaluation form
     BPK_TRY(pointwise_mul(ctx, d_buf, d_buf + D, D));               // polynomial.rs:262-266
     BPK_TRY(ntt_run(ctx, d_buf, d_buf, D, 1, true, nullptr));       // i_ntt_381 (polynomial.rs:270)

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -84,6 +85,12 @@ struct bpk_ctx {
     cudaEvent_t lane_fork = nullptr;
     cudaStream_t copy_stream = nullptr;  // uploads the tail of a host-resident MSM input under the head's accumulation
     cudaEvent_t copy_done = nullptr;
+    // ring of pinned buffers through which PAGEABLE host memory (a Rust Vec) is uploaded at copy-engine speed
+    static constexpr int STAGE_RING = 3;
+    static constexpr size_t STAGE_CHUNK = (size_t)32 << 20;
+    void* stage_buf[STAGE_RING] = {};
+    cudaEvent_t stage_done[STAGE_RING] = {};
+    long opt_host_stage_threads = 6;   // 0: hand pageable memory to cudaMemcpyAsync (the driver stages it, ~12 GB/s)
 
     // bpk_dev_alloc / bpk_dev_free: freed blocks are kept by size and handed out again (a prover allocates the same
     // sizes for every proof; cudaMalloc / cudaFree would synchronise the device each time)
@@ -102,7 +109,7 @@ struct bpk_ctx {
     long opt_msm_lanes = bpk::MSM_LANES;  // 1: bpk_msm_g1_dev_batch runs its MSMs one after the other
     long opt_msm_host_slices = 1;  // 0: upload all scalars before the MSM starts
     long opt_msm_affine_levels = -1;  // levels of the batched-affine pairwise tree (-1: from the expected bucket load, 0: XYZZ only)
-    long opt_msm_min_pairs = 1 << 19;  // a tree level expected to hold fewer pairs is left to the XYZZ tail (r2_msm_plan_sweep.md)
+    long opt_msm_min_pairs = 1 << 18;  // a tree level expected to hold fewer pairs is left to the XYZZ tail (r2_msm_plan_sweep.md)
     long opt_msm_batch = 256;          // additions that share one inversion (per thread)
     long opt_msm_level_mib = 48 << 10; // budget of the tree's level buffers
     long opt_msm_tree_top = 1;         // narrow top of the bucket-reduction tree in one block
@@ -159,6 +166,9 @@ struct StageTimer {
     void end();
 };
 int profile_collect(bpk_ctx* ctx);
+// host -> device copy, ordered on `stream`; on return the source may be reused.  Pageable sources are staged through
+// the context's pinned ring by several threads (the driver's own staging of pageable memory is single-threaded).
+int upload_host(bpk_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, cudaStream_t stream);
 
 inline void count_launch(bpk_ctx* ctx, uint64_t n = 1) { ctx->launches += n; }
 

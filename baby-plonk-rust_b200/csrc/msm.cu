@@ -1455,7 +1455,7 @@ int msm_run_from_host(bpk_ctx* ctx, const MsmPoints& pts, const uint64_t* h_scal
     if (n >= ((size_t)1 << 31)) return BPK_ERR_TOO_LARGE;
     const size_t head = n / 8;
     if (n < ((size_t)1 << 22) || ctx->opt_msm_host_slices == 0) {
-        if (n) BPK_CUDA(cudaMemcpyAsync(d_stage, h_scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+        if (n) BPK_TRY(upload_host(ctx, d_stage, h_scalars, n * sizeof(fr_t), ctx->stream));
         return msm_run(ctx, pts, d_stage, n, rshift, normalise, d_out);
     }
     // both slices use the geometry (window, tree depth) of the larger one, and its workspace
@@ -1474,10 +1474,9 @@ int msm_run_from_host(bpk_ctx* ctx, const MsmPoints& pts, const uint64_t* h_scal
     // the staging buffer may still be read by earlier work on the main stream
     BPK_CUDA(cudaEventRecord(ctx->lane_fork, ctx->stream));
     BPK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->lane_fork, 0));
-    BPK_CUDA(cudaMemcpyAsync(d_stage, h_scalars, head * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    BPK_TRY(upload_host(ctx, d_stage, h_scalars, head * sizeof(fr_t), ctx->stream));
     BPK_TRY(msm_fill_buckets(ctx, pl, pts, d_stage, head, rshift, buckets));
-    BPK_CUDA(cudaMemcpyAsync(d_stage + head, h_scalars + 4 * head, (n - head) * sizeof(fr_t), cudaMemcpyHostToDevice,
-                             ctx->copy_stream));
+    BPK_TRY(upload_host(ctx, d_stage + head, h_scalars + 4 * head, (n - head) * sizeof(fr_t), ctx->copy_stream));
     BPK_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
     BPK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
     MsmPoints rest = pts;

@@ -246,7 +246,8 @@ int bpk_imad_peak(bpk_ctx* ctx, double* wide_imad_per_s_out, double* seconds_out
  *   "ntt.kernel" 0 = auto, 1 = one radix-2 stage per barrier, 2 = register-blocked radix-8 steps, 3 = 4 rows per
  *   thread with two products per call (auto uses it below 2^18 elements),
  *   "ntt.direct_max_log2" largest per-size inter-pass twiddle table, "ntt.direct_budget_mib" HBM budget of all
- *   such tables together (a cache: dropped and rebuilt on demand beyond it, or when an allocation fails), "imad.mode" probe form of bpk_imad_peak.
+ *   such tables together (a cache: dropped and rebuilt on demand beyond it, or when an allocation fails), "imad.mode" probe form of bpk_imad_peak,
+ *   "host.stage_threads" threads that stage PAGEABLE host inputs through pinned buffers (0 = leave it to the driver).
  * Unknown keys and out-of-range values return BPK_ERR_INVALID_ARG. */
 int bpk_set_option(bpk_ctx* ctx, const char* key, long value);
 

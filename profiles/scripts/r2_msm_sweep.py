@@ -43,5 +43,5 @@ for logn in logns:
             res.append({"logn": logn, "c": c, "min_pairs": mp, "ms": min(ts[2:]), "levels": st["tree_levels"]})
             print(res[-1], flush=True)
         setup.free()
-    ctx.set_option("msm.min_pairs", 1 << 19)
+    ctx.set_option("msm.min_pairs", 1 << 18)
 json.dump(res, open(out_path, "w"), indent=1)

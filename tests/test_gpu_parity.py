@@ -446,7 +446,7 @@ def test_msm_precomputed_degenerate_points(ctx):
 
 class options:
     """set library tunables for a block, restore the defaults afterwards"""
-    DEFAULTS = {"msm.affine_levels": -1, "msm.batch": 256, "msm.min_pairs": 1 << 19, "msm.window": 0, "msm.chunk": 0,
+    DEFAULTS = {"msm.affine_levels": -1, "msm.batch": 256, "msm.min_pairs": 1 << 18, "msm.window": 0, "msm.chunk": 0,
                 "msm.tree_top": 1, "msm.level_mib": 48 << 10, "msm.scatter_l2_mib": 400}
 
     def __init__(self, ctx, **kw):
