@@ -4,8 +4,6 @@
 // Div by X^n - 1 and by X - zeta (:314-380), the grand-product loop of round 2 (src/prover.rs:286-317),
 // monomial_z_to_z_omega (src/prover.rs:661-674).  Every value is a canonical Montgomery residue, so the
 // results are bit-identical to the reference's whatever the evaluation order.
-#include <cub/device/device_scan.cuh>
-
 #include "internal.cuh"
 
 namespace bpk {
@@ -205,12 +203,131 @@ __global__ void __launch_bounds__(256) plonk_quotient_kernel(const fr_t* __restr
     }
 }
 
-struct FrAddOp {
-    __device__ __forceinline__ fr_t operator()(const fr_t& a, const fr_t& b) const { return add(a, b); }
-};
-struct FrMulOp {
-    __device__ __forceinline__ fr_t operator()(const fr_t& a, const fr_t& b) const { return mul(a, b); }
-};
+// ---- prefix scan over Fr (sum or product) -------------------------------------------------------------
+// Three launches: per-tile aggregates, one block that scans the aggregates, per-tile scan with the tile's base.
+// Both operations are associative and commutative on canonical residues, so the order of combination does not
+// show in the result.  MUL: running product (grand product of round 2), else running sum (division by X - zeta).
+constexpr int FSCAN_THREADS = 256, FSCAN_ITEMS = 4, FSCAN_TILE = FSCAN_THREADS * FSCAN_ITEMS;
+
+template <bool MUL>
+__device__ __forceinline__ fr_t fscan_op(const fr_t& a, const fr_t& b) {
+    return MUL ? mul(a, b) : add(a, b);
+}
+template <bool MUL>
+__device__ __forceinline__ fr_t fscan_identity() {
+    return MUL ? fr_t::one() : fr_t::zero();
+}
+__device__ __forceinline__ fr_t shfl_up_fr(const fr_t& v, int d) {
+    fr_t r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_up_sync(0xffffffffu, v.l[i], d);
+    return r;
+}
+// inclusive scan of one value per thread across the block; `total` = the block aggregate (all threads)
+template <bool MUL>
+__device__ __forceinline__ fr_t fscan_block(fr_t v, fr_t& total, fr_t* sm /* FSCAN_THREADS / 32 + 1 */) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        fr_t t = shfl_up_fr(v, d);
+        if (lane >= (uint32_t)d) v = fscan_op<MUL>(t, v);
+    }
+    __syncthreads();
+    if (lane == 31) sm[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        fr_t w = lane < FSCAN_THREADS / 32 ? sm[lane] : fscan_identity<MUL>();
+#pragma unroll
+        for (int d = 1; d < FSCAN_THREADS / 32; d <<= 1) {
+            fr_t t = shfl_up_fr(w, d);
+            if (lane >= (uint32_t)d) w = fscan_op<MUL>(t, w);
+        }
+        if (lane < FSCAN_THREADS / 32) sm[lane] = w;  // inclusive over the warps
+    }
+    __syncthreads();
+    total = sm[FSCAN_THREADS / 32 - 1];
+    if (warp > 0) v = fscan_op<MUL>(sm[warp - 1], v);
+    return v;
+}
+
+template <bool MUL>
+__global__ void __launch_bounds__(FSCAN_THREADS) fr_scan_tiles_kernel(const fr_t* __restrict__ in, size_t n,
+                                                                       fr_t* __restrict__ aggregates) {
+    __shared__ fr_t sm[FSCAN_THREADS / 32 + 1];
+    const size_t first = (size_t)blockIdx.x * FSCAN_TILE + (size_t)threadIdx.x * FSCAN_ITEMS;
+    fr_t acc = fscan_identity<MUL>();
+#pragma unroll
+    for (int k = 0; k < FSCAN_ITEMS; k++)
+        if (first + k < n) acc = fscan_op<MUL>(acc, pld(in + first + k));
+    fr_t total;
+    fscan_block<MUL>(acc, total, sm);
+    if (threadIdx.x == 0) pst(aggregates + blockIdx.x, total);
+}
+
+// exclusive scan of the tile aggregates in place, by one block
+template <bool MUL>
+__global__ void __launch_bounds__(FSCAN_THREADS) fr_scan_aggregates_kernel(fr_t* __restrict__ aggregates, size_t count) {
+    __shared__ fr_t sm[FSCAN_THREADS / 32 + 1];
+    const size_t per = (count + FSCAN_THREADS - 1) / FSCAN_THREADS;
+    const size_t lo = threadIdx.x * per, hi = lo + per < count ? lo + per : count;
+    fr_t acc = fscan_identity<MUL>();
+    for (size_t i = lo; i < hi; i++) acc = fscan_op<MUL>(acc, pld(aggregates + i));
+    fr_t total;
+    const fr_t incl = fscan_block<MUL>(acc, total, sm);
+    // exclusive base of this thread's range = inclusive value of the previous thread
+    __shared__ fr_t prev[FSCAN_THREADS];
+    prev[threadIdx.x] = incl;
+    __syncthreads();
+    fr_t run = threadIdx.x ? prev[threadIdx.x - 1] : fscan_identity<MUL>();
+    for (size_t i = lo; i < hi; i++) {
+        const fr_t v = pld(aggregates + i);
+        pst(aggregates + i, run);
+        run = fscan_op<MUL>(run, v);
+    }
+}
+
+// out[i] = in[0] o .. o in[i] (inclusive) or init o in[0] o .. o in[i-1] (exclusive)
+template <bool MUL, bool EXCLUSIVE>
+__global__ void __launch_bounds__(FSCAN_THREADS) fr_scan_apply_kernel(const fr_t* __restrict__ in, size_t n,
+                                                                       const fr_t* __restrict__ bases, fr_t init,
+                                                                       fr_t* __restrict__ out) {
+    __shared__ fr_t sm[FSCAN_THREADS / 32 + 1];
+    __shared__ fr_t prev[FSCAN_THREADS];
+    const size_t first = (size_t)blockIdx.x * FSCAN_TILE + (size_t)threadIdx.x * FSCAN_ITEMS;
+    fr_t x[FSCAN_ITEMS];
+    fr_t acc = fscan_identity<MUL>();
+#pragma unroll
+    for (int k = 0; k < FSCAN_ITEMS; k++) {
+        x[k] = first + k < n ? pld(in + first + k) : fscan_identity<MUL>();
+        acc = fscan_op<MUL>(acc, x[k]);
+    }
+    fr_t total;
+    const fr_t incl = fscan_block<MUL>(acc, total, sm);
+    prev[threadIdx.x] = incl;
+    __syncthreads();
+    fr_t run = fscan_op<MUL>(init, pld(bases + blockIdx.x));
+    if (threadIdx.x) run = fscan_op<MUL>(run, prev[threadIdx.x - 1]);
+#pragma unroll
+    for (int k = 0; k < FSCAN_ITEMS; k++) {
+        if (EXCLUSIVE && first + k < n) pst(out + first + k, run);
+        run = fscan_op<MUL>(run, x[k]);
+        if (!EXCLUSIVE && first + k < n) pst(out + first + k, run);
+    }
+}
+
+template <bool MUL, bool EXCLUSIVE>
+static int fr_scan(bpk_ctx* ctx, const fr_t* in, size_t n, const fr_t& init, fr_t* out) {
+    if (n == 0) return BPK_OK;
+    const size_t tiles = (n + FSCAN_TILE - 1) / FSCAN_TILE;
+    fr_t* aggregates;
+    BPK_TRY(ws_reserve(ctx, 14, tiles * sizeof(fr_t), (void**)&aggregates));
+    fr_scan_tiles_kernel<MUL><<<(unsigned)tiles, FSCAN_THREADS, 0, ctx->stream>>>(in, n, aggregates);
+    fr_scan_aggregates_kernel<MUL><<<1, FSCAN_THREADS, 0, ctx->stream>>>(aggregates, tiles);
+    fr_scan_apply_kernel<MUL, EXCLUSIVE><<<(unsigned)tiles, FSCAN_THREADS, 0, ctx->stream>>>(in, n, aggregates, init, out);
+    count_launch(ctx, 3);
+    BPK_CUDA(cudaGetLastError());
+    return BPK_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // host side
@@ -312,16 +429,12 @@ int fr_poly_div_linear(bpk_ctx* ctx, const fr_t* c, size_t n, const fr_t& root, 
     fr_t* scan = tmp + n;   // inclusive prefix sums of rev
     BPK_TRY(power_tables(ctx, root, fr_t::one(), n, &lo, &hi));
     fr_scale_powers_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(c, lo, hi, rev, n, 1);
-    size_t bytes = 0;
-    cub::DeviceScan::InclusiveScan(nullptr, bytes, rev, scan, FrAddOp(), (int)n, ctx->stream);
-    void* cub_tmp;
-    BPK_TRY(ws_reserve(ctx, 14, bytes, &cub_tmp));
-    BPK_CUDA(cub::DeviceScan::InclusiveScan(cub_tmp, bytes, rev, scan, FrAddOp(), (int)n, ctx->stream));
+    BPK_TRY((fr_scan<false, false>(ctx, rev, n, fr_t::zero(), scan)));
     // q_i = (sum_{j>i} c_j root^j) root^-(i+1)
     fr_t rinv = inv(root);
     BPK_TRY(power_tables(ctx, rinv, rinv, n, &lo, &hi));
     fr_div_linear_finish_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(scan, lo, hi, q, n);
-    count_launch(ctx, 4);
+    count_launch(ctx, 2);
     BPK_CUDA(cudaGetLastError());
     t.end();
     return BPK_OK;
@@ -350,12 +463,8 @@ int plonk_grand_product(bpk_ctx* ctx, const fr_t* A, const fr_t* B, const fr_t* 
     size_t ratio_threads = (n + RATIO_BATCH - 1) / RATIO_BATCH;
     plonk_ratio_kernel<<<(unsigned)((ratio_threads + 127) / 128), 128, 0, ctx->stream>>>(
         A, B, C, s1, s2, s3, ctx->tw_lo[0], ctx->tw_hi[0], logn, beta, gamma, k1, k2, r, n);
-    size_t bytes = 0;
-    cub::DeviceScan::ExclusiveScan(nullptr, bytes, r, Z, FrMulOp(), fr_t::one(), (int)(n + 1), ctx->stream);
-    void* cub_tmp;
-    BPK_TRY(ws_reserve(ctx, 14, bytes, &cub_tmp));
-    BPK_CUDA(cub::DeviceScan::ExclusiveScan(cub_tmp, bytes, r, Z, FrMulOp(), fr_t::one(), (int)(n + 1), ctx->stream));
-    count_launch(ctx, 3);
+    BPK_TRY((fr_scan<true, true>(ctx, r, n + 1, fr_t::one(), Z)));
+    count_launch(ctx, 1);
     BPK_CUDA(cudaGetLastError());
     t.end();
     return BPK_OK;

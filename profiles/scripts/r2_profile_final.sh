@@ -8,7 +8,14 @@ mkdir -p gpurun_out
 $CMD > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
 # the timed MSM is the second one: skip the levels of the warm-up MSM
-ncu --set full --clock-control none --import-source on -k regex:msm_affine_level -s 8 -c 8 -o gpurun_out/${TAG}_affine $CMD > gpurun_out/${TAG}_ncu_affine.log 2>&1
+ncu --set full --clock-control none -k regex:msm_affine_level -s 8 -c 8 -o gpurun_out/${TAG}_affine $CMD > gpurun_out/${TAG}_ncu_affine.log 2>&1
 ncu --set full --clock-control none -k regex:"msm_scatter|msm_count|msm_level_offsets|msm_accumulate_kernel|msm_plane_tree_level" -s 12 -c 10 -o gpurun_out/${TAG}_sort $CMD > gpurun_out/${TAG}_ncu_sort.log 2>&1
-$NTT > gpurun_out/${TAG}_ntt_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:ntt_pass_r8 -s 9 -c 3 -o gpurun_out/${TAG}_ntt $NTT > gpurun_out/${TAG}_ncu_ntt.log 2>&1
+$NTT > gpurun_out/${TAG}_ntt_plain.log 2>&1 && ncu --set full --clock-control none -k regex:ntt_pass_r8 -s 9 -c 3 -o gpurun_out/${TAG}_ntt $NTT > gpurun_out/${TAG}_ncu_ntt.log 2>&1
+# the reports are large: keep their raw pages as CSV (the summaries under profiles/ are made from these), drop the rest
+for r in affine sort ntt; do
+  if [ -f gpurun_out/${TAG}_$r.ncu-rep ]; then
+    ncu -i gpurun_out/${TAG}_$r.ncu-rep --page raw --csv > gpurun_out/${TAG}_${r}_raw.csv 2>/dev/null
+    rm -f gpurun_out/${TAG}_$r.ncu-rep
+  fi
+done
 ls -la gpurun_out/${TAG}_*
