@@ -127,6 +127,8 @@ _SIGNATURES = {
     "bpk_plonk_quotient_evals_shard": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                                       ctypes.c_uint] + [ctypes.c_void_p] * 7),
     "bpk_keccak_f1600": (None, [ctypes.c_void_p]),
+    "bpk_synthetic_chain_circuit": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_void_p,
+                                                   ctypes.c_void_p]),
     "bpk_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "bpk_profile_reset": (ctypes.c_int, [ctypes.c_void_p]),
     "bpk_profile_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double),

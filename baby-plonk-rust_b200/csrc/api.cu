@@ -1001,6 +1001,167 @@ extern "C" void bpk_keccak_f1600(uint64_t s[25]) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// host utility: the synthetic benchmark circuit (SURVEY 8d C4 family) as pre-processed columns.  Pure host code --
+// the interpreted generator in synthetic.py needs ~90 s for 2^24 rows, this one ~2 s; tests/test_synthetic_cpu.py
+// checks that both produce the same columns.
+// ------------------------------------------------------------------------------------------------
+namespace {
+typedef unsigned __int128 u128h;
+struct HFr {  // 4 x u64 Montgomery residue mod q (scalar.rs:22), host arithmetic
+    uint64_t l[4];
+};
+const uint64_t HQ[4] = {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull};
+const uint64_t HQ_INV = 0xfffffffeffffffffull;  // -q^-1 mod 2^64 (scalar.rs:164)
+const HFr HR2 = {{0xc999e990f3f29c6dull, 0x2b6cedcb87925c23ull, 0x05d314967254398full, 0x0748d9d99f59ff11ull}};
+inline void hfr_cond_sub(uint64_t r[4]) {
+    uint64_t t[4], borrow = 0;
+    for (int i = 0; i < 4; i++) {
+        u128h d = (u128h)r[i] - HQ[i] - borrow;
+        t[i] = (uint64_t)d;
+        borrow = (uint64_t)(d >> 64) & 1;
+    }
+    if (!borrow)
+        for (int i = 0; i < 4; i++) r[i] = t[i];
+}
+inline HFr hfr_mul(const HFr& a, const HFr& b) {
+    uint64_t t[9] = {0};
+    for (int i = 0; i < 4; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; j < 4; j++) {
+            u128h p = (u128h)a.l[j] * b.l[i] + t[i + j] + carry;
+            t[i + j] = (uint64_t)p;
+            carry = (uint64_t)(p >> 64);
+        }
+        u128h s = (u128h)t[i + 4] + carry;
+        t[i + 4] = (uint64_t)s;
+        t[i + 5] += (uint64_t)(s >> 64);
+        const uint64_t m = t[i] * HQ_INV;
+        carry = 0;
+        for (int j = 0; j < 4; j++) {
+            u128h p = (u128h)m * HQ[j] + t[i + j] + carry;
+            t[i + j] = (uint64_t)p;
+            carry = (uint64_t)(p >> 64);
+        }
+        s = (u128h)t[i + 4] + carry;
+        t[i + 4] = (uint64_t)s;
+        t[i + 5] += (uint64_t)(s >> 64);
+    }
+    HFr r = {{t[4], t[5], t[6], t[7]}};
+    hfr_cond_sub(r.l);
+    return r;
+}
+inline HFr hfr_add(const HFr& a, const HFr& b) {
+    HFr r;
+    uint64_t carry = 0;
+    for (int i = 0; i < 4; i++) {
+        u128h s = (u128h)a.l[i] + b.l[i] + carry;
+        r.l[i] = (uint64_t)s;
+        carry = (uint64_t)(s >> 64);
+    }
+    hfr_cond_sub(r.l);  // 2q < 2^256: no carry out
+    return r;
+}
+inline HFr hfr_from_u64(uint64_t v) {
+    HFr x = {{v, 0, 0, 0}};
+    return hfr_mul(x, HR2);
+}
+inline HFr hfr_neg_one() {  // q - 1 in Montgomery form = -(R mod q)
+    HFr one = hfr_from_u64(1), r;
+    uint64_t borrow = 0;
+    for (int i = 0; i < 4; i++) {
+        u128h d = (u128h)HQ[i] - one.l[i] - borrow;
+        r.l[i] = (uint64_t)d;
+        borrow = (uint64_t)(d >> 64) & 1;
+    }
+    return r;
+}
+}  // namespace
+
+// columns (each n x 4 u64, Montgomery): [0..4] QL QR QM QO QC, [5..7] S1 S2 S3, [8..10] A B C; public_out: the public
+// input (canonical limbs).  Same circuit as synthetic.chain_circuit(n, gates, seed).
+extern "C" int bpk_synthetic_chain_circuit(size_t n, size_t gates, uint64_t seed, uint64_t* const columns[11],
+                                           uint64_t public_out[4]) {
+    if (!columns || !public_out || n < 2 || (n & (n - 1)) || gates < 2 || gates > n || n > ((size_t)1 << 32))
+        return BPK_ERR_INVALID_ARG;
+    for (int k = 0; k < 11; k++)
+        if (!columns[k]) return BPK_ERR_INVALID_ARG;
+    const size_t m = gates - 1;
+    HFr* col[11];
+    for (int k = 0; k < 11; k++) {
+        col[k] = reinterpret_cast<HFr*>(columns[k]);
+        memset(col[k], 0, n * sizeof(HFr));
+    }
+    HFr *ql = col[0], *qr = col[1], *qm = col[2], *qo = col[3], *s1 = col[5], *s2 = col[6], *s3 = col[7], *A = col[8],
+        *B = col[9], *C = col[10];
+    // roots of unity: w = ROOT_OF_UNITY^(2^32 / n) (utils.rs:39-43), then sequential powers (utils.rs:45-52)
+    HFr w = {{0xb9b58d8c5f0e466aull, 0x5b1b4c801819d7ecull, 0x0af53ae352a31e64ull, 0x5bf3adda19e9b27bull}};
+    for (size_t k = n; k < ((size_t)1 << 32); k <<= 1) w = hfr_mul(w, w);
+    std::vector<HFr> roots(n);
+    roots[0] = hfr_from_u64(1);
+    for (size_t i = 1; i < n; i++) roots[i] = hfr_mul(roots[i - 1], w);
+    const HFr one = hfr_from_u64(1), minus_one = hfr_neg_one(), two = hfr_from_u64(2), three = hfr_from_u64(3);
+    uint64_t state = seed * 0x9E3779B97F4A7C15ull + 1;
+    HFr c_prev = hfr_from_u64(3 + seed % 1000);
+    for (size_t k = 1; k <= m; k++) {
+        state = state * 6364136223846793005ull + 1442695040888963407ull;
+        const HFr y = hfr_from_u64((state >> 20) + 2);
+        A[k] = c_prev;
+        B[k] = y;
+        if (k & 1) {
+            c_prev = hfr_mul(c_prev, y);
+            qm[k] = minus_one;
+            qo[k] = one;
+        } else {
+            c_prev = hfr_add(c_prev, y);
+            ql[k] = minus_one;
+            qr[k] = minus_one;
+            qo[k] = one;
+        }
+        C[k] = c_prev;
+    }
+    A[0] = c_prev;
+    ql[0] = one;
+    {   // canonical form of the public input
+        HFr raw = {{1, 0, 0, 0}};
+        HFr canon = hfr_mul(c_prev, raw);
+        memcpy(public_out, canon.l, 32);
+    }
+    // sigma: identity labels (col + 1) w^row, then the copy-constraint cycles
+    for (size_t i = 0; i < n; i++) {
+        s1[i] = roots[i];
+        s2[i] = hfr_mul(roots[i], two);
+        s3[i] = hfr_mul(roots[i], three);
+    }
+    HFr* s[3] = {s1, s2, s3};
+    for (size_t k = 1; k < m; k++) {   // c_k: (O, k) <-> (L, k + 1)
+        s[0][k + 1] = hfr_mul(roots[k], three);
+        s[2][k] = roots[k + 1];
+    }
+    s[0][0] = hfr_mul(roots[m], three);   // out: (L, 0) <-> (O, m)
+    s[2][m] = roots[0];
+    // all unused cells form one cycle in the order (R,0), (O,0), then rows m+1.. in row-major order
+    const size_t unused = 2 + 3 * (n - 1 - m);
+    auto cell = [&](size_t i, int& c, size_t& r) {
+        if (i < 2) {
+            c = (int)i + 1;
+            r = 0;
+        } else {
+            c = (int)((i - 2) % 3);
+            r = m + 1 + (i - 2) / 3;
+        }
+    };
+    const HFr mult[3] = {one, two, three};
+    for (size_t i = 0; i < unused; i++) {
+        int c, nc;
+        size_t r, nr;
+        cell(i, c, r);
+        cell((i + 1) % unused, nc, nr);
+        s[nc][nr] = hfr_mul(roots[r], mult[c]);
+    }
+    return BPK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // instrumentation
 // ------------------------------------------------------------------------------------------------
 extern "C" int bpk_profile_enable(bpk_ctx* ctx, int on) {

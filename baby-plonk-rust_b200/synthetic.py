@@ -27,9 +27,22 @@ def mont_array(values) -> np.ndarray:
     return np.frombuffer(raw, dtype=np.uint64).reshape(-1, 4).copy()
 
 
-def chain_circuit(n: int, gates: int, seed: int = 1):
+def chain_circuit(n: int, gates: int, seed: int = 1, native: bool = True):
     """returns dict(selectors=[QL,QR,QM,QO,QC], sigmas=[S1,S2,S3], wires=[A,B,C] (all uint64[n,4] Montgomery),
-    public_inputs=[out], ints=dict of the same columns as Python ints for cross-checks)"""
+    public_inputs=[out]).  native: built by the library's host routine (bpk_synthetic_chain_circuit: seconds at 2^24
+    rows); otherwise by the interpreted generator below, which also returns ints=dict of the same columns as Python
+    ints for cross-checks."""
+    if native:
+        import ctypes
+        from . import load_library
+        lib = load_library()
+        cols = [np.empty((n, 4), dtype=np.uint64) for _ in range(11)]
+        ptrs = (ctypes.c_void_p * 11)(*[c.ctypes.data for c in cols])
+        pub = np.zeros(4, dtype=np.uint64)
+        if lib.bpk_synthetic_chain_circuit(n, gates, seed, ptrs, pub.ctypes.data) != 0:
+            raise ValueError("bad circuit shape")
+        out = int.from_bytes(pub.tobytes(), "little")
+        return dict(selectors=cols[0:5], sigmas=cols[5:8], wires=cols[8:11], public_inputs=[out])
     m = gates - 1                      # arithmetic rows 1..m
     assert 2 <= gates <= n and n & (n - 1) == 0
     roots = roots_of_unity(n)

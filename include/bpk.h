@@ -218,6 +218,12 @@ int bpk_plonk_quotient_evals_shard(bpk_ctx* ctx, const void* d_witness_evals, co
  * it instead of permuting in the interpreter. */
 void bpk_keccak_f1600(uint64_t lanes[25]);
 
+/* The synthetic benchmark circuit of SURVEY 8d (C4: row 0 "out public", rows alternate c_k <== c_{k-1} * y_k and
+ * c_k <== c_{k-1} + y_k, `gates` rows used of n) as the pre-processed columns src/program.rs:51-147 would produce:
+ * columns[0..4] = QL QR QM QO QC, [5..7] = S1 S2 S3, [8..10] = the witness columns A B C (n x 4 u64 Montgomery each,
+ * caller-allocated); public_out = the public input, canonical.  Runs on the host. */
+int bpk_synthetic_chain_circuit(size_t n, size_t gates, uint64_t seed, uint64_t* const columns[11], uint64_t public_out[4]);
+
 /* ---- instrumentation (bench.py, tests) -------------------------------------------------------- */
 /* When enabled, every kernel stage is bracketed by CUDA events on the context's stream. */
 int bpk_profile_enable(bpk_ctx* ctx, int on);

@@ -13,7 +13,7 @@ S = importlib.import_module("baby-plonk-rust_b200.synthetic")
 
 @pytest.mark.parametrize("n,gates", [(8, 3), (16, 16), (64, 41)])
 def test_chain_circuit_columns_match_program_preprocessing(n, gates):
-    circ = S.chain_circuit(n, gates, seed=5)
+    circ = S.chain_circuit(n, gates, seed=5, native=False)
     A, B, C = circ["ints"]["wires"]
     wit = {"x0": A[1], "out": circ["public_inputs"][0]}
     rows = [P.Gate.public_input("out")]
@@ -35,3 +35,16 @@ def test_chain_circuit_columns_match_program_preprocessing(n, gates):
         assert (ql[i] * A[i] + qr[i] * B[i] + qm[i] * A[i] * B[i] + qo[i] * C[i] + qc[i] + pi) % O.Q == 0
     assert bpk.scalars_to_ints(circ["wires"][2]) == C
     assert (S.mont_array(A) == bpk.scalars_from_ints(A)).all()
+
+
+@pytest.mark.parametrize("n,gates,seed", [(2, 2, 1), (8, 3, 5), (16, 16, 2), (64, 41, 7), (1024, 1021, 2), (4096, 100, 1999)])
+def test_native_generator_equals_the_interpreted_one(n, gates, seed):
+    """bpk_synthetic_chain_circuit (host C++, what bench.py and the full-size tests use) == the interpreted generator
+    that the test above pins to the oracle's program pre-processing"""
+    import numpy as np
+    a = S.chain_circuit(n, gates, seed=seed, native=True)
+    b = S.chain_circuit(n, gates, seed=seed, native=False)
+    assert a["public_inputs"] == b["public_inputs"]
+    for key in ("selectors", "sigmas", "wires"):
+        for x, y in zip(a[key], b[key]):
+            assert np.array_equal(x, y), key
