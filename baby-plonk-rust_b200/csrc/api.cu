@@ -356,6 +356,9 @@ extern "C" int bpk_set_option(bpk_ctx* ctx, const char* key, long value) {
     } else if (k == "ntt.direct_max_log2") {
         if (value < 0 || value > 28) return BPK_ERR_INVALID_ARG;
         ctx->opt_ntt_direct_max_log2 = value;
+    } else if (k == "ntt.scratch_mib") {
+        if (value < 1) return BPK_ERR_INVALID_ARG;
+        ctx->opt_ntt_scratch_mib = value;
     } else if (k == "ntt.direct_budget_mib") {
         if (value < 0) return BPK_ERR_INVALID_ARG;
         ctx->opt_ntt_direct_budget_mib = value;
@@ -614,7 +617,11 @@ extern "C" int bpk_msm_g1_dev_batch(bpk_ctx* ctx, uint64_t handle, size_t count,
     }
     BPK_CUDA(cudaSetDevice(ctx->device));
     uint64_t* out = (uint64_t*)d_out_xyz;
-    if (count <= 1 || ctx->opt_msm_lanes <= 1) {
+    // very large MSMs gain nothing from running side by side (their latency-bound stages are a per-mille of the
+    // accumulation) and each lane would hold its own ~20 GB workspace: run them one after the other
+    bool huge = false;
+    for (size_t i = 0; i < count; i++) huge = huge || n[i] >= ((size_t)1 << 23);
+    if (count <= 1 || ctx->opt_msm_lanes <= 1 || huge) {
         for (size_t i = 0; i < count; i++)
             BPK_TRY(msm_run(ctx, msm_points_of(it->second, first[i]), (const fr_t*)d_scalars_mont[i], n[i], 0,
                             normalise != 0, out + 18 * i));

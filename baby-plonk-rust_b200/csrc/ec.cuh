@@ -184,6 +184,27 @@ BPK_HD affine_t affine_add_finish(int kind, const affine_t& p, const affine_t& q
     return r;
 }
 
+// the same with the products left in [0, 2p) ("lazy": five conditional subtractions fewer); den_inv may be anywhere in
+// [0, 2p), the operands are canonical, the result is canonical
+BPK_HD affine_t affine_add_finish_lazy(int kind, const affine_t& p, const affine_t& q, const fp_t& den_inv) {
+    if (kind == AFF_COPY_P) return p;
+    if (kind == AFF_COPY_Q) return q;
+    if (kind == AFF_INF) return affine_t::inf();
+    fp_t lam;
+    if (kind == AFF_ADD) {
+        lam = mul_lazy(sub(q.y, p.y), den_inv);
+    } else {
+        fp_t xx = sqr(p.x);
+        lam = mul_lazy(add(dbl(xx), xx), den_inv);
+    }
+    const fp_t x3 = sub_lazy(sub_lazy(sqr_lazy(lam), p.x), q.x);
+    const fp_t y3 = sub_lazy(mul_lazy(lam, sub_lazy(p.x, x3)), p.y);
+    affine_t r;
+    r.x = reduce_once(x3);
+    r.y = reduce_once(y3);
+    return r;
+}
+
 BPK_HD affine_t affine_neg(const affine_t& a) {
     affine_t r;
     r.x = a.x;

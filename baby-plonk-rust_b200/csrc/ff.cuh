@@ -370,7 +370,10 @@ BPK_HD void final_sub(uint32_t* r) {
 // IMAD.WIDE.U32.X (even / odd limb products), one Montgomery row per limb of b.  On sm_100 every form of IMAD.WIDE
 // retires at 32 / clk / SM; a reduced-radix multiplier without carries and variants that moved chains to the ALU
 // pipe were built, verified and measured slower (profiles/r1_imad_forms.md) -- this is the form that stayed.
-template <class P>
+// REDUCE = false ("lazy"): the final conditional subtraction is left out.  For operands below 2p the result is below
+// (4 p^2 + R p) / R < 2p whenever R > 4p (Fp: R = 2^384, p < 2^381), so values may stay in [0, 2p) across a chain of
+// products; sub_lazy / reduce_once below are the matching subtraction and the way back to the canonical residue.
+template <class P, bool REDUCE = true>
 BPK_HD Fe<P> mul_cc(const Fe<P>& a, const Fe<P>& b) {
     constexpr int N = P::N;
     uint32_t even[N], odd[N];
@@ -388,7 +391,7 @@ BPK_HD Fe<P> mul_cc(const Fe<P>& a, const Fe<P>& b) {
 #pragma unroll
     for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(even[i], odd[i + 1]);
     r.l[N - 1] = ptx::addc(even[N - 1], 0);
-    detail::final_sub<P>(r.l);
+    if (REDUCE) detail::final_sub<P>(r.l);
     return r;
 }
 
@@ -426,7 +429,7 @@ BPK_HD void redc_row(uint32_t* even, uint32_t* odd) {
 // instead of 300); the doubling and the merges run on the ALU pipe, which the multiplier leaves idle.
 // Products at even limb positions accumulate in E, those at odd positions in O (O[k] sits at position
 // k + 1), so that every lo/hi pair is one 64-bit aligned IMAD.WIDE.U32.X as in mul_cc.
-template <class P>
+template <class P, bool REDUCE = true>
 BPK_HD Fe<P> sqr_cc(const Fe<P>& a) {
     constexpr int N = P::N;
     uint32_t E[2 * N], O[2 * N];
@@ -507,7 +510,7 @@ BPK_HD Fe<P> sqr_cc(const Fe<P>& a) {
 #pragma unroll
     for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(r.l[i], T[N + i]);
     r.l[N - 1] = ptx::addc(r.l[N - 1], T[2 * N - 1]);
-    detail::final_sub<P>(r.l);
+    if (REDUCE) detail::final_sub<P>(r.l);
     return r;
 }
 
@@ -519,6 +522,10 @@ static __device__ __noinline__ Fe<FpParams> fp_mul_call(Fe<FpParams> a, Fe<FpPar
     return mul_cc<FpParams>(a, b);
 }
 static __device__ __noinline__ Fe<FpParams> fp_sqr_call(Fe<FpParams> a) { return sqr_cc<FpParams>(a); }
+static __device__ __noinline__ Fe<FpParams> fp_mul_lazy_call(Fe<FpParams> a, Fe<FpParams> b) {
+    return mul_cc<FpParams, false>(a, b);
+}
+static __device__ __noinline__ Fe<FpParams> fp_sqr_lazy_call(Fe<FpParams> a) { return sqr_cc<FpParams, false>(a); }
 template <class P>
 struct MulCall {
     static __device__ __forceinline__ Fe<P> run(const Fe<P>& a, const Fe<P>& b) { return mul_cc<P>(a, b); }
@@ -537,6 +544,22 @@ BPK_HD Fe<P> mul(const Fe<P>& a, const Fe<P>& b) {
     return MulCall<P>::run(a, b);
 #else
     return mul_cc<P>(a, b);
+#endif
+}
+
+// lazy Fp product / square: operands and result in [0, 2p)
+BPK_HD Fe<FpParams> mul_lazy(const Fe<FpParams>& a, const Fe<FpParams>& b) {
+#if defined(__CUDA_ARCH__) && defined(BPK_FP_MUL_CALL)
+    return fp_mul_lazy_call(a, b);
+#else
+    return mul_cc<FpParams, false>(a, b);
+#endif
+}
+BPK_HD Fe<FpParams> sqr_lazy(const Fe<FpParams>& a) {
+#if defined(__CUDA_ARCH__) && defined(BPK_FP_MUL_CALL)
+    return fp_sqr_lazy_call(a);
+#else
+    return sqr_cc<FpParams, false>(a);
 #endif
 }
 
@@ -587,6 +610,37 @@ BPK_HD Fe<P> sub(const Fe<P>& a, const Fe<P>& b) {
 #pragma unroll
     for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(r.l[i], P::mod(i) & borrow);
     r.l[N - 1] = ptx::addc(r.l[N - 1], P::mod(N - 1) & borrow);
+    return r;
+}
+
+// a - b for a, b in [0, 2p): the result is brought back into [0, 2p) by adding 2p on borrow
+template <class P>
+BPK_HD Fe<P> sub_lazy(const Fe<P>& a, const Fe<P>& b) {
+    constexpr int N = P::N;
+    Fe<P> r;
+    r.l[0] = ptx::sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.l[i] = ptx::subc_cc(a.l[i], b.l[i]);
+    uint32_t borrow = ptx::subc(0, 0);  // 0xffffffff on borrow
+    // 2p, limb by limb
+    uint32_t carry = 0, two_p[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        two_p[i] = (P::mod(i) << 1) | carry;
+        carry = P::mod(i) >> 31;
+    }
+    r.l[0] = ptx::add_cc(r.l[0], two_p[0] & borrow);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(r.l[i], two_p[i] & borrow);
+    r.l[N - 1] = ptx::addc(r.l[N - 1], two_p[N - 1] & borrow);
+    return r;
+}
+
+// [0, 2p) -> the canonical residue
+template <class P>
+BPK_HD Fe<P> reduce_once(const Fe<P>& a) {
+    Fe<P> r = a;
+    detail::final_sub<P>(r.l);
     return r;
 }
 

@@ -119,6 +119,7 @@ struct bpk_ctx {
     long opt_ntt_threads = 0;
     long opt_ntt_kernel = 0;  // 0: auto, 1: one radix-2 stage per barrier, 2: register-blocked radix-8 steps
     long opt_ntt_direct_max_log2 = 25;  // largest direct twiddle table (2^25 x 32 B = 1 GiB)
+    long opt_ntt_scratch_mib = 4096;    // scratch of one batched transform; larger batches are transformed a few rows at a time
     long opt_ntt_direct_budget_mib = 3072;  // all direct tables together; beyond it they are dropped and rebuilt on demand
     long opt_imad_mode = 0;
 

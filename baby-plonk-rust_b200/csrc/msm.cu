@@ -28,7 +28,9 @@
 // One shared out-of-line body for the Fp product: the addition loops otherwise inline ~450-instruction
 // multiplications many times over and stall on instruction fetch (14 % "no_instructions" samples in
 // profiles/r1_final_msm_accumulate_ncu.md); measured 79.9 -> 77.3 ms at 2^24 in round 1.
+#ifndef BPK_MSM_INLINE_MUL   // A/B: inline every product (build.py --variant inl BPK_MSM_INLINE_MUL)
 #define BPK_FP_MUL_CALL 1
+#endif
 #include "internal.cuh"
 
 namespace bpk {
@@ -425,6 +427,9 @@ constexpr int AFF_THREADS = 128;
 #ifndef BPK_AFF_STAGE
 #define BPK_AFF_STAGE 1   // 0: plain per-lane loads at the point of use (A/B)
 #endif
+#ifndef BPK_AFF_LAZY
+#define BPK_AFF_LAZY 1    // products of the tree stay in [0, 2p): six conditional subtractions fewer per addition
+#endif
 constexpr int AFF_WARP_SMEM = 64 * 96 + 32 * 48;                       // bytes per warp
 constexpr size_t AFF_SMEM_BYTES = BPK_AFF_STAGE ? (size_t)(AFF_THREADS / 32) * AFF_WARP_SMEM : 0;  // 30 KB per CTA
 
@@ -556,7 +561,7 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
                         }
                         affine_add_prepare(P, Q, den);
                     }
-                    prod = j == 0 ? den : mul(prod, den);
+                    prod = j == 0 ? den : (BPK_AFF_LAZY ? mul_lazy(prod, den) : mul(prod, den));
                     uint4* s = sc + (size_t)j * 3 * T;
                     s[0] = make_uint4(prod.l[0], prod.l[1], prod.l[2], prod.l[3]);
                     s[T] = make_uint4(prod.l[4], prod.l[5], prod.l[6], prod.l[7]);
@@ -627,10 +632,10 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
                 const int kind = affine_add_prepare(P, Q, den);
                 fp_t dinv = acc;
                 if (j > 0) {
-                    dinv = mul(acc, pre);
-                    acc = mul(acc, den);
+                    dinv = BPK_AFF_LAZY ? mul_lazy(acc, pre) : mul(acc, pre);
+                    acc = BPK_AFF_LAZY ? mul_lazy(acc, den) : mul(acc, den);
                 }
-                const affine_t R = affine_add_finish(kind, P, Q, dinv);
+                const affine_t R = BPK_AFF_LAZY ? affine_add_finish_lazy(kind, P, Q, dinv) : affine_add_finish(kind, P, Q, dinv);
                 const uint32_t key = m.x;
                 const uint32_t c0 = a.cnt0[key];
                 const uint32_t cn = (c0 + ((2u << a.level) - 1u)) >> (a.level + 1);  // entries of the bucket at level + 1

@@ -547,6 +547,20 @@ int ntt_run(bpk_ctx* ctx, const fr_t* d_in, fr_t* d_out, size_t n, size_t batch,
     if (batch == 0) return BPK_OK;
     if (batch > 65535) return BPK_ERR_TOO_LARGE;
     const int dir = inverse ? 1 : 0;
+    // the 2- / 3-pass plans need one / two scratch copies of the whole batch: transform large batches a few rows at a
+    // time so that the scratch stays under ntt.scratch_mib (a 10 x 2^26 batch would otherwise pin 43 GB)
+    {
+        const size_t cap = (size_t)ctx->opt_ntt_scratch_mib << 20;
+        const size_t row = n * sizeof(fr_t);
+        if (batch > 1 && n * batch * sizeof(fr_t) > cap) {
+            const size_t rows = cap / row > 1 ? cap / row : 1;
+            for (size_t b = 0; b < batch; b += rows) {
+                const size_t cnt = batch - b < rows ? batch - b : rows;
+                BPK_TRY(ntt_run(ctx, d_in + b * n, d_out + b * n, n, cnt, inverse, shift));
+            }
+            return BPK_OK;
+        }
+    }
     const size_t bytes = n * batch * sizeof(fr_t);
 
     // n^-1 (inverse) and coset tables

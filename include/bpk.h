@@ -251,6 +251,7 @@ int bpk_imad_peak(bpk_ctx* ctx, double* wide_imad_per_s_out, double* seconds_out
  *   "ntt.tile_log2" log2 of the R x C tile per CTA (default 10), "ntt.max_radix_log2" (0 = auto), "ntt.threads",
  *   "ntt.kernel" 0 = auto, 1 = one radix-2 stage per barrier, 2 = register-blocked radix-8 steps, 3 = 4 rows per
  *   thread with two products per call (auto uses it below 2^18 elements),
+ *   "ntt.scratch_mib" scratch bound of a batched transform (larger batches go a few rows at a time),
  *   "ntt.direct_max_log2" largest per-size inter-pass twiddle table, "ntt.direct_budget_mib" HBM budget of all
  *   such tables together (a cache: dropped and rebuilt on demand beyond it, or when an allocation fails), "imad.mode" probe form of bpk_imad_peak,
  *   "host.stage_threads" threads that stage PAGEABLE host inputs through pinned buffers (0 = leave it to the driver).

@@ -32,6 +32,7 @@ template <class F> static int run_field(const std::string& op, std::istringstrea
     F r;
     if (op == "mul") r = mul(a, b);
     else if (op == "mulcc") r = mul_cc(a, b);
+    else if (op == "mullazy") r = reduce_once(mul_cc<typename F::params, false>(a, b));
     else if (op == "sqr") r = sqr(a);
     else if (op == "add") r = add(a, b);
     else if (op == "sub") r = sub(a, b);
@@ -79,6 +80,16 @@ int main() {
                 fp_t den;
                 int kind = affine_add_prepare(p, q, den);
                 affine_t r = affine_add_finish(kind, p, q, inv(den));
+                // the lazy form, fed an inverse that is itself left in [0, 2p)
+                fp_t di = inv(den), di2 = add(di, di);   // (2 di) / 2 ... simply use di + p when it fits below 2p
+                fp_t dil = di;
+                {   // di + p as a non-canonical representative of the same residue
+                    uint64_t c = 0;
+                    for (int i = 0; i < 12; i++) { uint64_t t = (uint64_t)di.l[i] + FpParams::mod(i) + c; dil.l[i] = (uint32_t)t; c = t >> 32; }
+                }
+                (void)di2;
+                affine_t r2 = affine_add_finish_lazy(kind, p, q, dil);
+                if (!(r.x == r2.x) || !(r.y == r2.y)) { printf("LAZY MISMATCH\n"); return 1; }
                 printf("%d ", kind); show(r.x); printf(" "); show(r.y); printf("\n");
             } else if (op == "proj_to_affine") {
                 std::string a, b, c; ss >> a >> b >> c;

@@ -49,6 +49,8 @@ def test_field_ops(exe):
             for b in rng.sample(vals, 6) + [a, mod - 1 - a if a != mod - 1 else 0]:
                 lines.append(f"{name} mul {hx(a)} {hx(b)}"); exp.append(a * b * Rinv % mod)
                 lines.append(f"{name} mulcc {hx(a)} {hx(b)}"); exp.append(a * b * Rinv % mod)
+                if name == "fp":   # lazy product (no final subtraction) on operands up to 2p - 1, then one reduction
+                    lines.append(f"{name} mullazy {hx(a + mod)} {hx(b + mod)}"); exp.append(a * b * Rinv % mod)
                 lines.append(f"{name} add {hx(a)} {hx(b)}"); exp.append((a + b) % mod)
                 lines.append(f"{name} sub {hx(a)} {hx(b)}"); exp.append((a - b) % mod)
             lines.append(f"{name} sqr {hx(a)}"); exp.append(a * a * Rinv % mod)
