@@ -373,6 +373,9 @@ BPK_HD void final_sub(uint32_t* r) {
 // REDUCE = false ("lazy"): the final conditional subtraction is left out.  For operands below 2p the result is below
 // (4 p^2 + R p) / R < 2p whenever R > 4p (Fp: R = 2^384, p < 2^381), so values may stay in [0, 2p) across a chain of
 // products; sub_lazy / reduce_once below are the matching subtraction and the way back to the canonical residue.
+// Fr (R = 2^256 < 4q): the FIRST operand must be canonical -- the running sum of the interleaved rows is bounded by
+// (a + q) 2^32, which only fits the 9-limb accumulators for a < q -- and the second may lie in [0, 2q); the result is
+// then below (2 q^2 + R q) / R < 1.91 q.
 template <class P, bool REDUCE = true>
 BPK_HD Fe<P> mul_cc(const Fe<P>& a, const Fe<P>& b) {
     constexpr int N = P::N;
@@ -633,6 +636,33 @@ BPK_HD Fe<P> sub_lazy(const Fe<P>& a, const Fe<P>& b) {
 #pragma unroll
     for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(r.l[i], two_p[i] & borrow);
     r.l[N - 1] = ptx::addc(r.l[N - 1], two_p[N - 1] & borrow);
+    return r;
+}
+
+// a + b for a, b in [0, 2p), brought back into [0, 2p).  The sum may exceed the limb array (Fr: 4q > 2^256): the
+// carry-out takes part in the decision, and the subtraction of 2p is then exact modulo 2^(32 N).
+template <class P>
+BPK_HD Fe<P> add_lazy(const Fe<P>& a, const Fe<P>& b) {
+    constexpr int N = P::N;
+    uint32_t carry = 0, two_p[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        two_p[i] = (P::mod(i) << 1) | carry;
+        carry = P::mod(i) >> 31;
+    }
+    uint32_t s[N], d[N];
+    s[0] = ptx::add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) s[i] = ptx::addc_cc(a.l[i], b.l[i]);
+    const uint32_t c = ptx::addc(0, 0);                 // 1: the sum is 2^(32 N) + s
+    d[0] = ptx::sub_cc(s[0], two_p[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) d[i] = ptx::subc_cc(s[i], two_p[i]);
+    const uint32_t borrow = ptx::subc(0, 0);            // 0xffffffff: s < 2p
+    const bool take = c != 0 || borrow == 0;
+    Fe<P> r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.l[i] = take ? d[i] : s[i];
     return r;
 }
 

@@ -32,6 +32,7 @@ struct NttPassParams {
     uint32_t logn, logR, logC, logNs;
     int coset_in;   // multiply input element i by cs(i)
     int scale_out;  // 0: none, 1: multiply outputs by `scale`, 2: multiply output i by cs(i)
+    int lazy_out;   // outputs may stay in [0, 2q): set for a pass whose successor is the register-blocked kernel
     fr_t scale;
 };
 
@@ -158,9 +159,23 @@ __global__ void __launch_bounds__(1024) ntt_pass_kernel(NttPassParams p) {
 // instruction cache (same finding as in msm.cu).
 // ---------------------------------------------------------------------------------------------
 static __device__ __noinline__ fr_t fr_mul_nl(fr_t a, fr_t b) { return mul(a, b); }
-#ifndef BPK_NTT_MUL
-#define BPK_NTT_MUL fr_mul_nl
+// Lazy butterflies (register-blocked kernel): values in flight live in [0, 2q).  The product of a canonical twiddle
+// (first operand, see mul_cc) with such a value stays below 1.91 q without its conditional subtraction; sums and
+// differences are folded back below 2q; the transform's outputs are reduced once, in its last pass.
+#ifndef BPK_NTT_LAZY
+#define BPK_NTT_LAZY 1
 #endif
+static __device__ __noinline__ fr_t fr_mul_lazy_nl(fr_t w, fr_t v) { return mul_cc<FrParams, false>(w, v); }
+__device__ __forceinline__ fr_t ntt_twiddle_mul(const fr_t& v, const fr_t& w) {
+    return BPK_NTT_LAZY ? fr_mul_lazy_nl(w, v) : fr_mul_nl(v, w);
+}
+__device__ __forceinline__ fr_t ntt_add(const fr_t& a, const fr_t& b) { return BPK_NTT_LAZY ? add_lazy(a, b) : add(a, b); }
+__device__ __forceinline__ fr_t ntt_sub(const fr_t& a, const fr_t& b) { return BPK_NTT_LAZY ? sub_lazy(a, b) : sub(a, b); }
+// the value a pass hands on: canonical unless the next pass accepts [0, 2q)
+__device__ __forceinline__ fr_t ntt_finish(const fr_t& v, const NttPassParams& p) {
+    if (p.scale_out == 0) return (BPK_NTT_LAZY && !p.lazy_out) ? reduce_once(v) : v;
+    return v;  // scaled outputs go through a reducing product below
+}
 
 template <int T, bool FIRST>
 __device__ __forceinline__ void dit_stage8(fr_t (&x)[8], uint32_t sigma, uint32_t base, uint32_t b0, uint32_t logR,
@@ -172,15 +187,15 @@ __device__ __forceinline__ void dit_stage8(fr_t (&x)[8], uint32_t sigma, uint32_
         fr_t tt = x[a1];
         if (FIRST) {  // stages 1..3 on rows base + a with base a multiple of 8: the exponent depends on a only
             const uint32_t lowb = a & ((1 << T) - 1);
-            if (lowb != 0) tt = BPK_NTT_MUL(tt, ld_sm(t_lo, t_hi, lowb << (logR - sigma)));
+            if (lowb != 0) tt = ntt_twiddle_mul(tt, ld_sm(t_lo, t_hi, lowb << (logR - sigma)));
         } else {
             const uint32_t row = base + ((uint32_t)a << b0);
             const uint32_t lowb = row & ((1u << (sigma - 1)) - 1);
-            tt = BPK_NTT_MUL(tt, ld_sm(t_lo, t_hi, lowb << (logR - sigma)));
+            tt = ntt_twiddle_mul(tt, ld_sm(t_lo, t_hi, lowb << (logR - sigma)));
         }
         const fr_t u = x[a];
-        x[a] = add(u, tt);
-        x[a1] = sub(u, tt);
+        x[a] = ntt_add(u, tt);
+        x[a1] = ntt_sub(u, tt);
     }
 }
 
@@ -221,12 +236,12 @@ __global__ void __launch_bounds__(256) ntt_pass_r8_kernel(NttPassParams p) {
             const uint32_t r = __brev(base + a) >> (32 - logR);
             const uint32_t gi = j + r * stride_in;
             fr_t v = ld_fr(in + gi);
-            if (p.coset_in) v = fr_mul_nl(v, table_pow(p.cs_lo, p.cs_hi, gi));
+            if (p.coset_in) v = ntt_twiddle_mul(v, table_pow(p.cs_lo, p.cs_hi, gi));
             if (logNs) {
                 if (p.tw_direct)
-                    v = fr_mul_nl(v, ld_fr(p.tw_direct + k * r));
+                    v = ntt_twiddle_mul(v, ld_fr(p.tw_direct + k * r));
                 else
-                    v = fr_mul_nl(v, table_pow(p.tw_lo, p.tw_hi, (k * r) << tw_shift));
+                    v = ntt_twiddle_mul(v, table_pow(p.tw_lo, p.tw_hi, (k * r) << tw_shift));
             }
             x[a] = v;
         }
@@ -263,9 +278,9 @@ __global__ void __launch_bounds__(256) ntt_pass_r8_kernel(NttPassParams p) {
         for (int a = 0; a < 8; a++) {
             const uint32_t r = base + ((uint32_t)a << b0);
             const size_t o = o0 + ((size_t)r << logNs);
-            fr_t v = x[a];
-            if (p.scale_out == 1) v = fr_mul_nl(v, p.scale);
-            else if (p.scale_out == 2) v = fr_mul_nl(v, table_pow(p.cs_lo, p.cs_hi, (uint32_t)o));
+            fr_t v = ntt_finish(x[a], p);
+            if (p.scale_out == 1) v = fr_mul_nl(p.scale, v);   // (canonical factor first: v may lie in [0, 2q))
+            else if (p.scale_out == 2) v = fr_mul_nl(table_pow(p.cs_lo, p.cs_hi, (uint32_t)o), v);
             st_fr(out + o, v);
         }
         return;
@@ -278,9 +293,9 @@ __global__ void __launch_bounds__(256) ntt_pass_r8_kernel(NttPassParams p) {
     for (uint32_t idx = tid; idx < RC; idx += nt) {
         const uint32_t r = idx & (R - 1), cc = idx >> logR;
         const size_t o = ((size_t)(j0 + cc) << logR) + r;
-        fr_t v = ld_sm(s_lo, s_hi, (r << logC) + cc);
-        if (p.scale_out == 1) v = fr_mul_nl(v, p.scale);
-        else if (p.scale_out == 2) v = fr_mul_nl(v, table_pow(p.cs_lo, p.cs_hi, (uint32_t)o));
+        fr_t v = ntt_finish(ld_sm(s_lo, s_hi, (r << logC) + cc), p);
+        if (p.scale_out == 1) v = fr_mul_nl(p.scale, v);
+        else if (p.scale_out == 2) v = fr_mul_nl(table_pow(p.cs_lo, p.cs_hi, (uint32_t)o), v);
         st_fr(out + o, v);
     }
 }
@@ -605,14 +620,33 @@ int ntt_run(bpk_ctx* ctx, const fr_t* d_in, fr_t* d_out, size_t n, size_t batch,
     if (np >= 2) BPK_TRY(ws_reserve(ctx, 0, bytes, (void**)&tmp[0]));
     if (np >= 3) BPK_TRY(ws_reserve(ctx, 1, bytes, (void**)&tmp[1]));
 
+    // which kernel runs each pass (0: one stage per barrier, 1: register-blocked 8 rows, 2: 4 rows): a pass may hand
+    // on values in [0, 2q) only to the register-blocked kernel
+    std::vector<int> kind(np);
+    std::vector<uint32_t> tile_c(np);
+    {
+        uint32_t ns = 0;
+        for (size_t pi = 0; pi < np; pi++) {
+            uint32_t logR = plan[pi];
+            uint32_t logC = tile_log - logR;
+            if (logC > logn - logR) logC = logn - logR;
+            if (ns && logC > ns) logC = ns;
+            tile_c[pi] = logC;
+            if ((ctx->opt_ntt_kernel == 3 || small_auto) && logR >= 2 && logR + logC <= 10)
+                kind[pi] = 2;
+            else if (logR >= 3 && logR + logC <= 11 && (ctx->opt_ntt_kernel == 0 ? big : ctx->opt_ntt_kernel == 2))
+                kind[pi] = 1;
+            else
+                kind[pi] = 0;
+            ns += logR;
+        }
+    }
     StageTimer t(ctx, "ntt.pass");
     uint32_t logNs = 0;
     const fr_t* src = d_in;
     for (size_t pi = 0; pi < np; pi++) {
         uint32_t logR = plan[pi];
-        uint32_t logC = tile_log - logR;
-        if (logC > logn - logR) logC = logn - logR;
-        if (logNs && logC > logNs) logC = logNs;
+        uint32_t logC = tile_c[pi];
         fr_t* dst = (pi + 1 == np) ? d_out : tmp[pi & 1];
         NttPassParams p;
         p.in = src;
@@ -663,15 +697,16 @@ int ntt_run(bpk_ctx* ctx, const fr_t* d_in, fr_t* d_out, size_t n, size_t batch,
         p.scale_out = 0;
         p.scale = scale;
         if (pi + 1 == np && inverse) p.scale_out = shift ? 2 : 1;
+        p.lazy_out = (BPK_NTT_LAZY && kind[pi] == 1 && pi + 1 < np && kind[pi + 1] == 1) ? 1 : 0;
         size_t smem = ((size_t)2 << (logR + logC)) * sizeof(uint4) + ((size_t)1 << logR) * sizeof(uint4);
         if (smem > 200 * 1024) return BPK_ERR_INVALID_ARG;
         dim3 grid((unsigned)(n >> (logR + logC)), (unsigned)batch);
         unsigned threads = (unsigned)ctx->opt_ntt_threads;
         if (threads == 0) threads = (logR + logC >= 12) ? 1024 : 256;
         // register-blocked kernel unless the transform is too small to fill the GPU with 128-thread CTAs
-        if ((ctx->opt_ntt_kernel == 3 || small_auto) && logR >= 2 && logR + logC <= 10)
+        if (kind[pi] == 2)
             ntt_pass_r4d_kernel<<<grid, 1u << (logR + logC - 2), smem, ctx->stream>>>(p);
-        else if (logR >= 3 && logR + logC <= 11 && (ctx->opt_ntt_kernel == 0 ? big : ctx->opt_ntt_kernel == 2))
+        else if (kind[pi] == 1)
             ntt_pass_r8_kernel<<<grid, 1u << (logR + logC - 3), smem, ctx->stream>>>(p);
         else
             ntt_pass_kernel<<<grid, threads, smem, ctx->stream>>>(p);

@@ -28,11 +28,13 @@ template <class F> static int run_field(const std::string& op, std::istringstrea
     std::string ha, hb;
     ss >> ha;
     F a = parse<F>(ha), b = F::zero();
-    if (op.substr(0, 3) == "mul" || op == "add" || op == "sub") { ss >> hb; b = parse<F>(hb); }
+    if (op.substr(0, 3) == "mul" || op.substr(0, 3) == "add" || op.substr(0, 3) == "sub") { ss >> hb; b = parse<F>(hb); }
     F r;
     if (op == "mul") r = mul(a, b);
     else if (op == "mulcc") r = mul_cc(a, b);
     else if (op == "mullazy") r = reduce_once(mul_cc<typename F::params, false>(a, b));
+    else if (op == "addlazy") r = reduce_once(add_lazy(a, b));
+    else if (op == "sublazy") r = reduce_once(sub_lazy(a, b));
     else if (op == "sqr") r = sqr(a);
     else if (op == "add") r = add(a, b);
     else if (op == "sub") r = sub(a, b);

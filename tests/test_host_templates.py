@@ -49,6 +49,12 @@ def test_field_ops(exe):
             for b in rng.sample(vals, 6) + [a, mod - 1 - a if a != mod - 1 else 0]:
                 lines.append(f"{name} mul {hx(a)} {hx(b)}"); exp.append(a * b * Rinv % mod)
                 lines.append(f"{name} mulcc {hx(a)} {hx(b)}"); exp.append(a * b * Rinv % mod)
+                # lazy addition / subtraction: operands anywhere in [0, 2 mod), result reduced once
+                for da, db in ((0, 0), (mod, 0), (0, mod), (mod, mod)):
+                    lines.append(f"{name} addlazy {hx(a + da)} {hx(b + db)}"); exp.append((a + b) % mod)
+                    lines.append(f"{name} sublazy {hx(a + da)} {hx(b + db)}"); exp.append((a - b) % mod)
+                if name == "fr":   # lazy product: canonical twiddle FIRST, value in [0, 2q) second (see mul_cc)
+                    lines.append(f"{name} mullazy {hx(b)} {hx(a + mod)}"); exp.append(a * b * Rinv % mod)
                 if name == "fp":   # lazy product (no final subtraction) on operands up to 2p - 1, then one reduction
                     lines.append(f"{name} mullazy {hx(a + mod)} {hx(b + mod)}"); exp.append(a * b * Rinv % mod)
                 lines.append(f"{name} add {hx(a)} {hx(b)}"); exp.append((a + b) % mod)
