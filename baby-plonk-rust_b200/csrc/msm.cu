@@ -514,12 +514,9 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
     // A thread's pairs are g T + tid, g = 0, 1, ..; it works through them in batches of B.  (Starting the CTAs of an SM
     // with first batches of different length, so that their forward / inversion / backward phases interleave, was
     // measured: 59.5 against 58.6 ms -- the warps are not phase-locked, the extra batch only costs an inversion.)
-    uint32_t first_len = 0;
-    for (uint64_t g0 = 0;;) {
-        const uint32_t len = first_len ? first_len : B;
+    for (uint64_t g0 = 0;; g0 += B) {
+        const uint32_t len = B;
         const uint64_t base = g0 * T + tid;
-        g0 += len;
-        first_len = 0;
         const uint64_t base0 = base - lane;               // the warp's first pair of this batch
         if (base0 >= S) break;                            // warp-uniform
         uint32_t nj = 0;

@@ -41,6 +41,10 @@ def main():
     com = mg.ShardedCommitter(bpk, ctx, n + 8, 101, rank, world, precompute=0)
     prover = prover_mod.DeviceProver(com.setup, n, circ["selectors"], circ["sigmas"], committer=com)
     out["chain12"] = prover.prove(circ["wires"], circ["public_inputs"], list(range(11, 22))).sha256()
+    # the same with the per-circuit sub-coset evaluations cached across proofs (second proof served from the cache)
+    cached = prover_mod.DeviceProver(com.setup, n, circ["selectors"], circ["sigmas"], committer=com, cache_preprocessed=True)
+    cached.prove(circ["wires"], circ["public_inputs"], list(range(1, 12)))
+    out["chain12_cached"] = cached.prove(circ["wires"], circ["public_inputs"], list(range(11, 22))).sha256()
     # every rank must hold the same proof
     digest = torch.tensor(list(hashlib.sha256(json.dumps(out, sort_keys=True).encode()).digest()[:8]),
                           dtype=torch.int64, device="cuda")

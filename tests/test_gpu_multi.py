@@ -40,4 +40,5 @@ def test_sharded_prover_matches_single_gpu():
     setup = bpk.Setup.generate_srs(n + 8, 101, ctx)
     prover = prover_mod.DeviceProver(setup, n, circ["selectors"], circ["sigmas"])
     assert prover.prove(circ["wires"], circ["public_inputs"], list(range(11, 22))).sha256() == got["chain12"]
+    assert got["chain12_cached"] == got["chain12"]
     ctx.close()
