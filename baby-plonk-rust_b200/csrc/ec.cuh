@@ -205,6 +205,21 @@ BPK_HD affine_t affine_add_finish_lazy(int kind, const affine_t& p, const affine
     return r;
 }
 
+// a + b for two affine points (neither the identity, a.x != b.x) -> XYZZ: add-2008-s with both ZZ = ZZZ = 1,
+// 4M + 2S instead of 12M + 2S.  Used where both operands are known to be affine (first level of the bucket tree).
+BPK_HD xyzz_t xyzz_from_affine_sum(const fp_t& ax, const fp_t& ay, const fp_t& bx, const fp_t& by) {
+    const fp_t Pd = sub(bx, ax), Rd = sub(by, ay);
+    const fp_t PP = sqr(Pd);
+    const fp_t PPP = mul(Pd, PP);
+    const fp_t Qv = mul(ax, PP);
+    xyzz_t r;
+    r.X = sub(sub(sqr(Rd), PPP), dbl(Qv));
+    r.Y = sub(mul(Rd, sub(Qv, r.X)), mul(ay, PPP));
+    r.ZZ = PP;
+    r.ZZZ = PPP;
+    return r;
+}
+
 BPK_HD affine_t affine_neg(const affine_t& a) {
     affine_t r;
     r.x = a.x;

@@ -904,7 +904,12 @@ __global__ void __launch_bounds__(128, BPK_TREE_MINBLOCKS) msm_plane_tree_level_
     }
     xyzz_t a = ld_xyzz(c0 + s);
     xyzz_t b = ld_xyzz(c1 + s);
-    xyzz_add(a, b);
+    // buckets finished by the affine tree arrive as (x, y, 1, 1): their sum needs a third of the products
+    const fp_t one = fp_t::one();
+    if (k == 1 && a.ZZ == one && a.ZZZ == one && b.ZZ == one && b.ZZZ == one && a.X != b.X)
+        a = xyzz_from_affine_sum(a.X, a.Y, b.X, b.Y);
+    else
+        xyzz_add(a, b);
     st_xyzz(out + t, a);
 }
 

@@ -76,6 +76,10 @@ int main() {
             } else if (op == "to_affine") {
                 xyzz_t p = parse_xyzz(ss); affine_t q = xyzz_to_affine(p);
                 show(q.x); printf(" "); show(q.y); printf("\n");
+            } else if (op == "aff_sum") {    // affine + affine -> XYZZ (generic case only)
+                std::string a, b, c, d; ss >> a >> b >> c >> d;
+                xyzz_t r = xyzz_from_affine_sum(parse<fp_t>(a), parse<fp_t>(b), parse<fp_t>(c), parse<fp_t>(d));
+                show_xyzz(r);
             } else if (op == "aff_add") {    // batched-affine addition of one pair: prepare, invert, finish
                 std::string a, b, c, d; ss >> a >> b >> c >> d;
                 affine_t p, q; p.x = parse<fp_t>(a); p.y = parse<fp_t>(b); q.x = parse<fp_t>(c); q.y = parse<fp_t>(d);

@@ -164,6 +164,21 @@ def test_batched_affine_pair_addition(exe):
         assert ((x, y) if (x, y) != (0, 0) else None) == e, l
 
 
+def test_affine_pair_to_xyzz(exe):
+    """xyzz_from_affine_sum (first level of the bucket-reduction tree: both operands affine, 4M + 2S)"""
+    G = O.G1_GEN
+    pts = [O.g1_mul(G, k) for k in (1, 2, 3, 7, 1000, O.Q - 2, 98765432109876543210)]
+    lines, exp = [], []
+    for a in pts:
+        for b in pts:
+            if a[0] == b[0]:
+                continue
+            lines.append(f"g1 aff_sum {M(a[0])} {M(a[1])} {M(b[0])} {M(b[1])}")
+            exp.append(O.g1_add(a, b))
+    for l, g, e in zip(lines, run(exe, lines), exp):
+        assert parse_xyzz(g) == e, l
+
+
 def test_inversion_terminates_on_non_canonical_limbs(exe):
     """limbs >= the modulus (p, 2p, all ones) must not hang the division-step loop (the binary Euclid did)"""
     lines = [f"fp inv {hx(O.P)}", f"fp inv {hx(2 * O.P)}", f"fp inv {hx((1 << 384) - 1)}",
