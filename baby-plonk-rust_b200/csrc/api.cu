@@ -155,6 +155,37 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(uint64_t* out, uint32_t
 #pragma unroll
         for (int i = 0; i < 14; i++) s ^= ((uint64_t)hi[i] << 32) | lo[i];
         out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+    } else if (mode == 3 || mode == 4) {
+        // the real Fp multiplier on a dependent chain: 3 = the out-of-line body the MSM kernels call, 4 = inlined;
+        // with imad.warps_per_sm this gives the multiplier's duty cycle at the MSM kernels' occupancy
+        fp_t x, y;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            x.l[i] = (a + i) & 0x0fffffffu;
+            y.l[i] = (b + i) & 0x0fffffffu;
+        }
+        for (uint32_t it = 0; it < iters; it++) x = mode == 3 ? mul_lazy(x, y) : mul_cc<FpParams, false>(x, y);
+        uint64_t s = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) s ^= ((uint64_t)x.l[i] << 32) | y.l[i];
+        out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+    } else if (mode == 5) {
+        // two independent inlined products per iteration (ILP 2 inside one thread)
+        fp_t x, y, z;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            x.l[i] = (a + i) & 0x0fffffffu;
+            y.l[i] = (b + i) & 0x0fffffffu;
+            z.l[i] = (a ^ (b + i)) & 0x0fffffffu;
+        }
+        for (uint32_t it = 0; it < iters; it += 2) {
+            x = mul_cc<FpParams, false>(x, y);
+            z = mul_cc<FpParams, false>(z, y);
+        }
+        uint64_t s = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) s ^= ((uint64_t)x.l[i] << 32) | z.l[i];
+        out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
     } else {
         uint32_t x[12], y[12], m[12];
 #pragma unroll
@@ -176,16 +207,17 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(uint64_t* out, uint32_t
 
 int imad_peak_run(bpk_ctx* ctx, double* rate, double* seconds) {
     const int mode = (int)ctx->opt_imad_mode;
-    const uint32_t iters = 1u << 14;
-    const unsigned blocks = (unsigned)ctx->sm_count * 8;
+    const uint32_t iters = mode >= 3 ? 1u << 10 : 1u << 14;
+    const unsigned threads = 128;
+    const unsigned blocks = (unsigned)ctx->sm_count * (unsigned)(ctx->opt_imad_warps_per_sm / 4);   // one wave, all resident
     uint64_t* d_out;
-    BPK_TRY(ws_reserve(ctx, 7, (size_t)blocks * 256 * sizeof(uint64_t), (void**)&d_out));
+    BPK_TRY(ws_reserve(ctx, 7, (size_t)blocks * threads * sizeof(uint64_t), (void**)&d_out));
     cudaEvent_t e0, e1;
     BPK_CUDA(cudaEventCreate(&e0));
     BPK_CUDA(cudaEventCreate(&e1));
-    imad_probe_kernel<<<blocks, 256, 0, ctx->stream>>>(d_out, iters / 16, 1, mode);  // warm-up
+    imad_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters / 16, 1, mode);  // warm-up
     BPK_CUDA(cudaEventRecord(e0, ctx->stream));
-    imad_probe_kernel<<<blocks, 256, 0, ctx->stream>>>(d_out, iters, 2, mode);
+    imad_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 2, mode);
     BPK_CUDA(cudaEventRecord(e1, ctx->stream));
     count_launch(ctx, 2);
     BPK_CUDA(cudaEventSynchronize(e1));
@@ -193,8 +225,9 @@ int imad_peak_run(bpk_ctx* ctx, double* rate, double* seconds) {
     BPK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    double per_thread = mode == 0 ? 8.0 * iters : (mode == 2 ? 14.0 * iters : 12.0 * iters);  // mode 1: 2 chains x 6
-    *rate = per_thread * 256.0 * blocks / (ms * 1e-3);
+    // mode 1: 2 chains x 6; modes 3, 4: one Fp product = 144 + 144 wide IMADs
+    double per_thread = mode == 0 ? 8.0 * iters : mode == 2 ? 14.0 * iters : mode >= 3 ? 288.0 * iters : 12.0 * iters;
+    *rate = per_thread * threads * blocks / (ms * 1e-3);
     *seconds = ms * 1e-3;
     return BPK_OK;
 }
@@ -370,6 +403,10 @@ extern "C" int bpk_set_option(bpk_ctx* ctx, const char* key, long value) {
         if (value < 0 || value > 16) return BPK_ERR_INVALID_ARG;
         ctx->opt_host_stage_threads = value;
     } else if (k == "imad.mode") ctx->opt_imad_mode = value;
+    else if (k == "imad.warps_per_sm") {
+        if (value < 4 || value > 64 || value % 4) return BPK_ERR_INVALID_ARG;
+        ctx->opt_imad_warps_per_sm = value;
+    }
     else return BPK_ERR_INVALID_ARG;
     return BPK_OK;
 }

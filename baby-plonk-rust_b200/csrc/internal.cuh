@@ -122,6 +122,7 @@ struct bpk_ctx {
     long opt_ntt_scratch_mib = 4096;    // scratch of one batched transform; larger batches are transformed a few rows at a time
     long opt_ntt_direct_budget_mib = 3072;  // all direct tables together; beyond it they are dropped and rebuilt on demand
     long opt_imad_mode = 0;
+    long opt_imad_warps_per_sm = 64;
 
     // plan of the most recent MSM (window bits, windows, pairs per accumulate thread, buckets)
     unsigned last_c = 0, last_W = 0, last_chunk = 0, last_buckets = 0, last_levels = 0, last_batch = 0;

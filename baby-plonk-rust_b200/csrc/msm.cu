@@ -410,6 +410,7 @@ struct AffLevelArgs {
     const uint32_t* totals;    // slots per level
     xyzz_t* buckets;           // finished buckets, as XYZZ (x, y, 1, 1)
     uint4* scratch;            // prefix products: [bmax][3][threads of the launch]
+    uint32_t* rare_bits;       // one flag per pair: degenerate, left to msm_affine_rare_kernel
     uint32_t level, bmax, out_is_tail;
 };
 
@@ -417,156 +418,213 @@ struct AffLevelArgs {
 #define BPK_AFF_MINBLOCKS 4
 #endif
 constexpr int AFF_THREADS = 128;
-// Operand staging.  What bounds a kernel in which every lane loads its own 96-byte points is not HBM and not the
-// multiplier but the SM's single L1TEX queue: a warp-wide 16-byte load whose lanes touch 32 different lines costs 32
-// wavefronts, 6 such loads per point (profiles/r2_affine_ab.md: 64-74 % multiplier duty, and prefetching made it
-// worse).  So the warp gathers COOPERATIVELY: 6 (3 for x only) neighbouring lanes copy the 16-byte pieces of one
-// point, five (ten) points per cp.async instruction, a handful of lines each, straight into shared memory; every
-// lane then reads its own pair from there.  The copies for pair j + 1 are issued while pair j is being added.
-// Per warp: 64 points x 96 B + 32 prefix products x 48 B.
-#ifndef BPK_AFF_STAGE
-#define BPK_AFF_STAGE 1   // 0: plain per-lane loads at the point of use (A/B)
-#endif
+// How the level kernel touches memory (profiles/r2_affine_ab.md, profiles/r2_affine_v2.md):
+//  * operands: what bounds a kernel in which every lane loads its own 96-byte points is the SM's single L1TEX queue (a
+//    warp-wide 16-byte load whose lanes touch 32 different lines costs 32 wavefronts), so the warp gathers
+//    COOPERATIVELY: 6 (3 for x only) neighbouring lanes copy the 16-byte pieces of one point with cp.async, five (ten)
+//    points per instruction, into the warp's stage in shared memory;
+//  * nothing is loaded from global or local memory into registers inside the loops: a register load must have landed
+//    before the next out-of-line product is called (the callee may use the register), which exposes its whole latency.
+//    The pair lists, the bucket layout words and the prefix products all arrive through cp.async one step ahead.  The
+//    degenerate pairs (identity operands, doubling, opposite points) are only flagged here and added by
+//    msm_affine_rare_kernel after the level: a call to a function that handles them -- even on a branch that is never
+//    taken -- puts every value that lives across it into local memory;
+//  * the operands stay in the stage and are read where they are used (x1, x2 twice) instead of living in registers
+//    across the six products of an addition, and the values that would otherwise be carried across most of them have a
+//    place in shared memory -- the running inverse and the slope a home of their own, y1 stays where it was copied and
+//    x1 - x3 is parked where Q.y was: an out-of-line product leaves the caller ~55 registers, and a value spilled to
+//    local memory comes back with L2 latency (the hot spill slots of 16 warps do not fit L1; measured: 25 % of all
+//    stall samples).  The x copies for the next pair are issued after the last read of x1, x2 (before the last
+//    product), the y copies at the end of the step.
+// Per warp: 32 pairs x 208 B (P.x P.y Q.x Q.y + 16 B so that the lanes' 16-byte reads fall into different banks), 32
+// prefix products, 32 pair-list words x 16 B, 32 x (count, offsets) x 16 B, 32 running inverses, 32 slopes (48 B each,
+// as [3][32] 16-byte pieces).
 #ifndef BPK_AFF_LAZY
 #define BPK_AFF_LAZY 1    // products of the tree stay in [0, 2p): six conditional subtractions fewer per addition
 #endif
-constexpr int AFF_WARP_SMEM = 64 * 96 + 32 * 48;                       // bytes per warp
-constexpr size_t AFF_SMEM_BYTES = BPK_AFF_STAGE ? (size_t)(AFF_THREADS / 32) * AFF_WARP_SMEM : 0;  // 30 KB per CTA
+constexpr uint32_t AFF_PAIR_STRIDE = 208;
+constexpr uint32_t AFF_PRE_OFF = 32 * AFF_PAIR_STRIDE, AFF_META_OFF = AFF_PRE_OFF + 32 * 48, AFF_DEST_OFF = AFF_META_OFF + 32 * 16,
+                   AFF_ACC_OFF = AFF_DEST_OFF + 32 * 16, AFF_LAM_OFF = AFF_ACC_OFF + 32 * 48;
+constexpr int AFF_WARP_SMEM = AFF_LAM_OFF + 32 * 48;                           // 12 KB per warp
+constexpr size_t AFF_SMEM_BYTES = (size_t)(AFF_THREADS / 32) * AFF_WARP_SMEM;  // 48 KB per CTA
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ fp_t lds_fp(const uint4* q) {  // 48 contiguous bytes of shared memory
-    const uint4 a = q[0], b = q[1], c = q[2];
+__device__ __forceinline__ void cp_async_wait_all_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+// shared memory by 32-bit address: one register per pointer, and statements that stay where they are written
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+template <uint32_t STRIDE = 16>
+__device__ __forceinline__ fp_t lds_fp(uint32_t addr) {  // three 16-byte pieces, STRIDE bytes apart
+    const uint4 a = lds128(addr), b = lds128(addr + STRIDE), c = lds128(addr + 2 * STRIDE);
     fp_t r;
     r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
     r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
     r.l[8] = c.x; r.l[9] = c.y; r.l[10] = c.z; r.l[11] = c.w;
     return r;
 }
+template <uint32_t STRIDE = 16>
+__device__ __forceinline__ void sts_fp(uint32_t addr, const fp_t& v) {
+    sts128(addr, make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]));
+    sts128(addr + STRIDE, make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]));
+    sts128(addr + 2 * STRIDE, make_uint4(v.l[8], v.l[9], v.l[10], v.l[11]));
+}
+__device__ __forceinline__ fp_t aff_mul(const fp_t& x, const fp_t& y) { return BPK_AFF_LAZY ? mul_lazy(x, y) : mul(x, y); }
+__device__ __forceinline__ fp_t aff_sqr(const fp_t& x) { return BPK_AFF_LAZY ? sqr_lazy(x) : sqr(x); }
+__device__ __forceinline__ fp_t aff_sub(const fp_t& x, const fp_t& y) { return BPK_AFF_LAZY ? sub_lazy(x, y) : sub(x, y); }
+__device__ __forceinline__ fp_t aff_canon(const fp_t& x) { return BPK_AFF_LAZY ? reduce_once(x) : x; }
+
+constexpr uint32_t AFF_F_PAD = 1, AFF_F_NEG_P = 2, AFF_F_NEG_Q = 4, AFF_F_FINISHED = 8, AFF_F_MARK_PAD = 16, AFF_F_X_ZERO = 32;
 
 template <bool LEVEL0>
-__global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_level_kernel(AffLevelArgs a) {
+__global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_level_kernel(const __grid_constant__ AffLevelArgs a) {
     extern __shared__ uint4 aff_smem[];
     const uint32_t S = a.totals[a.level] >> 1;  // pairs of this level
     if (S == 0) return;
     const uint32_t T = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     // every thread takes batches of B pairs, interleaved with the other threads (pair = base + j T + tid): the lanes of a
-    // warp work on 32 neighbouring pairs at every step; B is the smallest batch that covers the level in whole rounds
-    const uint64_t per_round = (uint64_t)T * a.bmax;
-    const uint32_t rounds = (uint32_t)((S + per_round - 1) / per_round);
-    const uint32_t B = (uint32_t)((S + (uint64_t)T * rounds - 1) / ((uint64_t)T * rounds));
+    // warp work on 32 neighbouring pairs at every step; B is the smallest batch that covers the level in whole rounds.
+    // Pair numbers fit 32 bits: S <= 2^31 and a batch spans B T <= 2^25 pairs.
+    const uint32_t per_round = T * a.bmax;                // <= 2^27
+    const uint32_t rounds = (S - 1) / per_round + 1;
+    const uint32_t B = (S - 1) / (T * rounds) + 1;        // T rounds <= S / bmax + T
     uint4* const sc = a.scratch + tid;
-    // this warp's stage: 64 points of 96 bytes (pair of lane l at 192 l: P.x P.y Q.x Q.y), then [3][32] prefix pieces
-    uint4* const wstage = aff_smem + (threadIdx.x >> 5) * (AFF_WARP_SMEM / 16);
-    const uint32_t wstage_addr = (uint32_t)__cvta_generic_to_shared(wstage);
-    const uint4* const my_pair = wstage + lane * 12;
-    uint4* const pre_stage = wstage + 64 * 6 + lane;
-    const uint32_t pre_addr = wstage_addr + 64 * 96 + lane * 16;
+    // this warp's stage (layout above): the pair of lane l at 208 l, this lane's 16-byte slots of the other arrays at
+    // my16 + the array's offset
+    const uint32_t wstage = (uint32_t)__cvta_generic_to_shared(aff_smem) + (threadIdx.x >> 5) * AFF_WARP_SMEM;
+    const uint32_t my_pair = wstage + lane * AFF_PAIR_STRIDE;
+    const uint32_t my16 = wstage + lane * 16;
+    const uint32_t my_pre = my16 + AFF_PRE_OFF, my_meta = my16 + AFF_META_OFF, my_dest = my16 + AFF_DEST_OFF;
+    const uint32_t my_acc = my16 + AFF_ACC_OFF, my_lam = my16 + AFF_LAM_OFF;
 
-    // meta word of pair p: level 0 (key, val) of both slots; above: the two keys.  A lane without a pair at this step
+    // pair-list word of pair p: level 0 (key, val) of both slots; above: the two keys.  A lane without a pair at this step
     // gets a harmless one (point 0, padded) so that it can take part in the warp's copies.
-    auto load_meta = [&](uint64_t p) -> uint4 {
+    auto load_meta = [&](uint32_t p) -> uint4 {
         if (p >= S) return make_uint4(0, 0, INVALID_KEY, 0);
         if (LEVEL0) return reinterpret_cast<const uint4*>(a.kv0)[p];
         const uint2 kk = reinterpret_cast<const uint2*>(a.keys_in)[p];
         return make_uint4(kk.x, 0, kk.y, 0);
     };
-    auto point_of = [&](uint64_t p, const uint4& m, int which) -> const affine_t* {
-        if (LEVEL0) return a.pts_in + ((which ? m.w : m.y) & 0x7fffffffu);
-        return a.pts_in + 2 * (size_t)p + which;
+    auto stage_meta = [&](uint32_t p) {                   // the same word, into this lane's slot of the stage
+        if (p >= S) sts128(my_meta, LEVEL0 ? make_uint4(0, 0, INVALID_KEY, 0) : make_uint4(0, INVALID_KEY, 0, 0));
+        else if (LEVEL0) cp_async16(my_meta, reinterpret_cast<const uint4*>(a.kv0) + p);
+        else cp_async8(my_meta, reinterpret_cast<const uint2*>(a.keys_in) + p);
     };
-    // Cooperative copy of the operands of the warp's 32 pairs (first pair p0) into the stage.  PIECES = 3: x coordinates
-    // only; 6: whole points.  Point q of the warp (q = 2 lane' + which) goes to byte 96 q.
-    auto stage_points = [&](uint64_t p0, const uint4& m, const int PIECES) {
-        const int per = 30 / PIECES;                       // points per instruction
-        const uint32_t sub = lane / PIECES, piece = lane - sub * PIECES;
-        const uint32_t iP = m.y & 0x7fffffffu, iQ = (m.z == INVALID_KEY ? m.y : m.w) & 0x7fffffffu;
-        for (int i = 0; i * per < 64; i++) {
-            const uint32_t q = i * per + sub;
-            const bool on = lane < 30 && q < 64;
+    auto staged_meta = [&]() -> uint4 {
+        const uint4 s = lds128(my_meta);
+        return LEVEL0 ? s : make_uint4(s.x, 0, s.y, 0);
+    };
+    auto stage_dest = [&](uint32_t key) {                 // where the sum of a pair of bucket `key` goes
+        cp_async4(my_dest, a.cnt0 + key);
+        cp_async4(my_dest + 4, a.off_in + key);
+        cp_async4(my_dest + 8, a.off_out + key);
+    };
+    // Cooperative copy of one coordinate (HALF 0: x, 1: y) of the operands of the warp's 32 pairs (first pair p0) into the
+    // stage: 3 neighbouring lanes copy the 16-byte pieces of one coordinate, 8 points per instruction (even, so that the
+    // destination is linear in i).  Point q of the warp (q = 2 lane' + which) lives at byte 208 lane' + 96 which.  vP, vQ:
+    // this lane's level-0 point words (a padded pair copies P twice).
+    auto stage_points = [&](uint32_t p0, uint32_t vP, uint32_t vQ, const int HALF) {
+        const uint32_t sub = lane / 3, piece = lane - sub * 3;
+        const bool on = sub < 8;                           // 24 lanes copy
+        const uint32_t dst0 = wstage + (sub >> 1) * AFF_PAIR_STRIDE + (sub & 1) * 96 + HALF * 48 + piece * 16;
+        const uint32_t iP = vP & 0x7fffffffu, iQ = vQ & 0x7fffffffu;
+#pragma unroll 4
+        for (int i = 0; i < 8; i++) {
             const affine_t* src;
             if (LEVEL0) {
-                const uint32_t from = (q < 64 ? q : 63) >> 1;
-                const uint32_t vP = __shfl_sync(0xffffffffu, iP, from), vQ = __shfl_sync(0xffffffffu, iQ, from);
-                src = a.pts_in + ((q & 1) ? vQ : vP);
+                const uint32_t from = (i * 4 + (sub >> 1)) & 31u;
+                const uint32_t wP = __shfl_sync(0xffffffffu, iP, from), wQ = __shfl_sync(0xffffffffu, iQ, from);
+                src = a.pts_in + ((sub & 1) ? wQ : wP);
             } else {
-                src = a.pts_in + 2 * (size_t)p0 + q;
+                src = a.pts_in + 2 * (size_t)p0 + i * 8 + sub;
             }
-            if (on) cp_async16(wstage_addr + q * 96 + piece * 16, reinterpret_cast<const uint4*>(src) + piece);
+            if (on) cp_async16(dst0 + i * 4 * AFF_PAIR_STRIDE, reinterpret_cast<const uint4*>(src) + HALF * 3 + piece);
         }
-        cp_async_commit();
     };
     // the running product after pair jj of this thread's batch: scratch (written by the forward pass) -> stage
     auto stage_prefix = [&](uint32_t jj) {
         const uint4* src = sc + (size_t)jj * 3 * T;
-        cp_async16(pre_addr, src);
-        cp_async16(pre_addr + 32 * 16, src + T);
-        cp_async16(pre_addr + 64 * 16, src + 2 * (size_t)T);
-        cp_async_commit();
+        cp_async16(my_pre, src);
+        cp_async16(my_pre + 32 * 16, src + T);
+        cp_async16(my_pre + 64 * 16, src + 2 * (size_t)T);
     };
-    // everything this thread read from the stage has arrived in its registers (volatile asm statements keep their order)
-    auto consumed = [](const fp_t& v) { asm volatile("" ::"r"(v.l[0]), "r"(v.l[4]), "r"(v.l[8]) : "memory"); };
+    // level 0: the sign of an entry is bit 31 of its point word
+    auto signed_y = [&](uint32_t addr, uint32_t minus) -> fp_t {
+        const fp_t y = lds_fp(addr);
+        return LEVEL0 && minus ? neg(y) : y;
+    };
+    auto flags_of = [&](const uint4& m) -> uint32_t {
+        const bool pad = m.z == INVALID_KEY;
+        return (pad ? AFF_F_PAD : 0u) | (LEVEL0 && (m.y >> 31) ? AFF_F_NEG_P : 0u) |
+               (LEVEL0 && !pad && (m.w >> 31) ? AFF_F_NEG_Q : 0u);
+    };
 
     // A thread's pairs are g T + tid, g = 0, 1, ..; it works through them in batches of B.  (Starting the CTAs of an SM
     // with first batches of different length, so that their forward / inversion / backward phases interleave, was
     // measured: 59.5 against 58.6 ms -- the warps are not phase-locked, the extra batch only costs an inversion.)
-    for (uint64_t g0 = 0;; g0 += B) {
-        const uint32_t len = B;
-        const uint64_t base = g0 * T + tid;
-        const uint64_t base0 = base - lane;               // the warp's first pair of this batch
+    for (uint32_t base = tid;; base += B * T) {
+        const uint32_t base0 = base - lane;               // the warp's first pair of this batch
         if (base0 >= S) break;                            // warp-uniform
         uint32_t nj = 0;
         if (base < S) {
-            const uint64_t left = (S - base + T - 1) / T;
-            nj = left < len ? (uint32_t)left : len;
+            const uint32_t left = (S - base + T - 1) / T;
+            nj = left < B ? left : B;
         }
         const uint32_t njw = __shfl_sync(0xffffffffu, nj, 0);   // lane 0 has the most
-        auto pair_at = [&](uint32_t j) { return base + (uint64_t)j * T; };
 
         // ---- forward: denominators and their running product.  Only the x coordinates are needed unless the pair is
-        // degenerate (pad, identity operand, equal x), which is re-examined with the full points.
+        // degenerate (identity operand, equal x), which is re-examined with the full points.
         fp_t prod = fp_t::one();
         {
-            uint4 m_next = load_meta(pair_at(0)), m_next2 = m_next;
-            if (BPK_AFF_STAGE) stage_points(base0, m_next, 3);
-            if (njw > 1) m_next2 = load_meta(pair_at(1));
-            for (uint32_t j = 0; j < njw; j++) {
-                const uint64_t p = pair_at(j);
-                const uint4 m = m_next;
-                m_next = m_next2;
-                const bool pad = m.z == INVALID_KEY;
-                fp_t x1, x2;
-                if (BPK_AFF_STAGE) {
-                    cp_async_wait_all();
-                    __syncwarp();
-                    x1 = lds_fp(my_pair);
-                    x2 = pad ? x1 : lds_fp(my_pair + 6);
-                    consumed(x1);
-                    consumed(x2);
-                    __syncwarp();
-                    if (j + 1 < njw) stage_points(base0 + (uint64_t)(j + 1) * T, m_next, 3);
-                } else if (j < nj) {
-                    x1 = ld_fp(&point_of(p, m, 0)->x);
-                    x2 = pad ? x1 : ld_fp(&point_of(p, m, 1)->x);
+            uint32_t padN;
+            {
+                const uint4 m = load_meta(base);
+                padN = m.z == INVALID_KEY;
+                if (njw > 1) stage_meta(base + T);
+                stage_points(base0, m.y, padN ? m.y : m.w, 0);
+                cp_async_commit();
+            }
+            uint32_t p = base;                             // pair of step j
+            uint4* s = sc;                                 // its slot of the prefix scratch
+            for (uint32_t j = 0; j < njw; j++, p += T, s += 3 * (size_t)T) {
+                const bool pad = padN;
+                cp_async_wait_all();
+                __syncwarp();
+                const fp_t x1 = lds_fp(my_pair);
+                const fp_t x2 = pad ? x1 : lds_fp(my_pair + 96);
+                uint4 mN = make_uint4(0, 0, INVALID_KEY, 0);
+                if (j + 1 < njw) mN = staged_meta();
+                __syncwarp();
+                padN = mN.z == INVALID_KEY;
+                if (j + 1 < njw) {
+                    if (j + 2 < njw) stage_meta(p + 2 * T);
+                    stage_points(p - lane + T, mN.y, padN ? mN.y : mN.w, 0);
+                    cp_async_commit();
                 }
-                if (j + 2 < njw) m_next2 = load_meta(pair_at(j + 2));
                 if (j < nj) {
                     fp_t den = sub(x2, x1);
-                    if (pad || den.is_zero() || x1.is_zero() || x2.is_zero()) {
-                        affine_t P = ld_affine(point_of(p, m, 0)), Q = affine_t::inf();
-                        if (LEVEL0 && (m.y >> 31)) P.y = neg(P.y);
-                        if (!pad) {
-                            Q = ld_affine(point_of(p, m, 1));
-                            if (LEVEL0 && (m.w >> 31)) Q.y = neg(Q.y);
-                        }
-                        affine_add_prepare(P, Q, den);
+                    if (pad) den = fp_t::one();
+                    else if (den.is_zero() || x1.is_zero() || x2.is_zero()) {   // degenerate: not in this product
+                        den = fp_t::one();
+                        atomicOr(a.rare_bits + (p >> 5), 1u << (p & 31));
                     }
-                    prod = j == 0 ? den : (BPK_AFF_LAZY ? mul_lazy(prod, den) : mul(prod, den));
-                    uint4* s = sc + (size_t)j * 3 * T;
+                    prod = j == 0 ? den : aff_mul(prod, den);
                     s[0] = make_uint4(prod.l[0], prod.l[1], prod.l[2], prod.l[3]);
                     s[T] = make_uint4(prod.l[4], prod.l[5], prod.l[6], prod.l[7]);
                     s[2 * (size_t)T] = make_uint4(prod.l[8], prod.l[9], prod.l[10], prod.l[11]);
@@ -574,84 +632,163 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
             }
         }
 
-        fp_t acc = inv(prod);  // 1 / (den_0 ... den_{nj-1})
+        sts_fp<512>(my_acc, inv(prod));  // 1 / (den_0 ... den_{nj-1}): the running inverse, at home in the stage
 
-        // ---- backward: peel the inverses off, finish the additions, place the results
+        // ---- backward: peel the inverses off, finish the additions, place the results.  Two copy groups per step: the x
+        // coordinates, list word, layout words and prefix of the next pair go out once x1, x2 have been read for the last
+        // time (before the last product); its y coordinates after the step's last read of y1 and t (which is parked where
+        // Q.y was), and are waited for only after the next step's first two products.
         {
-            uint4 m_next = load_meta(pair_at(njw - 1)), m_next2 = m_next;
-            if (BPK_AFF_STAGE) {
-                stage_points(base0 + (uint64_t)(njw - 1) * T, m_next, 6);
+            uint32_t keyN, flagsN, vPN, vQN;
+            uint32_t p = base + (njw - 1) * T;             // pair of step j
+            {
+                const uint4 m = load_meta(p);
+                keyN = m.x;
+                flagsN = flags_of(m);
+                vPN = m.y;
+                vQN = (flagsN & AFF_F_PAD) ? m.y : m.w;
+                if (njw > 1) stage_meta(p - T);
+                stage_dest(keyN);
+                stage_points(p - lane, vPN, vQN, 0);
                 if (njw > 1 && nj == njw) stage_prefix(njw - 2);   // needed at the first step if this lane takes part in it
+                cp_async_commit();
+                stage_points(p - lane, vPN, vQN, 1);
+                cp_async_commit();
             }
-            if (njw > 1) m_next2 = load_meta(pair_at(njw - 2));
-            for (uint32_t j = njw; j-- > 0;) {
-                const uint64_t p = pair_at(j);
-                const uint4 m = m_next;
-                m_next = m_next2;
+            for (uint32_t j = njw; j-- > 0; p -= T) {
+                const uint32_t key = keyN;
+                uint32_t flags = flagsN;
                 const bool active = j < nj;
-                affine_t P, Q = affine_t::inf();
-                fp_t pre;
-                if (BPK_AFF_STAGE) {
-                    cp_async_wait_all();
-                    __syncwarp();
-                    P.x = lds_fp(my_pair);
-                    P.y = lds_fp(my_pair + 3);
-                    if (m.z != INVALID_KEY) {
-                        Q.x = lds_fp(my_pair + 6);
-                        Q.y = lds_fp(my_pair + 9);
+                cp_async_wait_all_but_last();
+                __syncwarp();
+                // where the result goes (the layout words of `key` were staged one step ahead)
+                const uint4 d = lds128(my_dest);
+                const uint32_t cn = (d.x + ((2u << a.level) - 1u)) >> (a.level + 1);  // entries of the bucket at level + 1
+                const uint32_t rel = p - (d.y >> 1);
+                const uint32_t slot = d.z + rel;
+                if (cn <= 1) flags |= AFF_F_FINISHED;
+                if (!a.out_is_tail && (cn & 1u) && rel == cn - 1) flags |= AFF_F_MARK_PAD;
+                const bool pad = flags & AFF_F_PAD;
+                // the sum goes to the next level's list, or, when it is the bucket's last, to the bucket (x, y first in both)
+                auto dst_fp = [&](int which) -> fp_t* {
+                    return (flags & AFF_F_FINISHED) ? &a.buckets[key].X + which : &a.pts_out[slot].x + which;
+                };
+
+                fp_t dinv;
+                bool plain = false;
+                if (active) {
+                    const fp_t x1 = lds_fp(my_pair);
+                    const fp_t x2 = pad ? x1 : lds_fp(my_pair + 96);
+                    fp_t den = sub(x2, x1);
+                    if (pad || !(den.is_zero() || x1.is_zero() || x2.is_zero())) {   // else: flagged by the forward pass
+                        plain = true;
+                        if (pad) den = fp_t::one();
+                        if (j > 0) {
+                            dinv = aff_mul(lds_fp<512>(my_acc), lds_fp<512>(my_pre));
+                            sts_fp<512>(my_acc, aff_mul(lds_fp<512>(my_acc), den));
+                        } else {
+                            dinv = lds_fp<512>(my_acc);
+                        }
                     }
-                    if (active && j > 0) {
-                        const uint4 u0 = pre_stage[0], u1 = pre_stage[32], u2 = pre_stage[64];
-                        pre.l[0] = u0.x; pre.l[1] = u0.y; pre.l[2] = u0.z; pre.l[3] = u0.w;
-                        pre.l[4] = u1.x; pre.l[5] = u1.y; pre.l[6] = u1.z; pre.l[7] = u1.w;
-                        pre.l[8] = u2.x; pre.l[9] = u2.y; pre.l[10] = u2.z; pre.l[11] = u2.w;
-                        consumed(pre);
+                }
+                cp_async_wait_all();                       // the y coordinates
+                __syncwarp();
+                if (plain) {
+                    {
+                        const fp_t y1 = signed_y(my_pair + 48, flags & AFF_F_NEG_P);
+                        const fp_t y2 = pad ? y1 : signed_y(my_pair + 144, flags & AFF_F_NEG_Q);
+                        if (LEVEL0 && (flags & AFF_F_NEG_P)) sts_fp(my_pair + 48, y1);   // read back at the end of the step
+                        dinv = aff_mul(sub(y2, y1), dinv);                                // the slope
                     }
-                    consumed(P.x);
-                    consumed(P.y);
-                    consumed(Q.x);
-                    consumed(Q.y);
-                    __syncwarp();
-                    if (j > 0) stage_points(base0 + (uint64_t)(j - 1) * T, m_next, 6);
+                    sts_fp<512>(my_lam, dinv);
+                    const fp_t l2 = aff_sqr(dinv);
+                    const fp_t x1 = lds_fp(my_pair);
+                    const fp_t x2 = pad ? x1 : lds_fp(my_pair + 96);
+                    fp_t x3 = pad ? x1 : aff_sub(aff_sub(l2, x1), x2);   // a padded pair: the sum is P
+                    sts_fp(my_pair + 144, aff_sub(x1, x3));              // x1 - x3, parked where Q.y was
+                    x3 = aff_canon(x3);
+                    if (x3.is_zero()) flags |= AFF_F_X_ZERO;
+                    st_fp(dst_fp(0), x3);
+                }
+                // every lane has read x1, x2 for the last time
+                __syncwarp();
+                if (j > 0) {
+                    const uint4 mN = staged_meta();
+                    keyN = mN.x;
+                    flagsN = flags_of(mN);
+                    vPN = mN.y;
+                    vQN = (flagsN & AFF_F_PAD) ? mN.y : mN.w;
+                    if (j > 1) stage_meta(p - 2 * T);
+                    stage_dest(keyN);
+                    stage_points(p - lane - T, vPN, vQN, 0);
                     // the prefix needed at step j - 1 is the product after pair j - 2 (own slots: no other lane reads them)
                     if (j > 1 && j - 1 < nj) stage_prefix(j - 2);
-                } else if (active) {
-                    P = ld_affine(point_of(p, m, 0));
-                    if (m.z != INVALID_KEY) Q = ld_affine(point_of(p, m, 1));
-                    if (j > 0) {
-                        const uint4* s = sc + (size_t)(j - 1) * 3 * T;
-                        const uint4 u0 = s[0], u1 = s[T], u2 = s[2 * (size_t)T];
-                        pre.l[0] = u0.x; pre.l[1] = u0.y; pre.l[2] = u0.z; pre.l[3] = u0.w;
-                        pre.l[4] = u1.x; pre.l[5] = u1.y; pre.l[6] = u1.z; pre.l[7] = u1.w;
-                        pre.l[8] = u2.x; pre.l[9] = u2.y; pre.l[10] = u2.z; pre.l[11] = u2.w;
+                }
+                cp_async_commit();
+                if (plain) {
+                    const fp_t lt = aff_mul(lds_fp<512>(my_lam), lds_fp(my_pair + 144));
+                    const fp_t y1 = lds_fp(my_pair + 48);
+                    fp_t y3 = aff_canon(aff_sub(lt, y1));
+                    if (pad) y3 = y1;
+                    st_fp(dst_fp(1), y3);
+                    if (flags & AFF_F_FINISHED) {          // as xyzz_t::from_affine: (x, y, 1, 1), the identity has ZZ = 0
+                        const fp_t zz = (flags & AFF_F_X_ZERO) && y3.is_zero() ? fp_t::zero() : fp_t::one();
+                        st_fp(dst_fp(2), zz);
+                        st_fp(dst_fp(3), zz);
+                    } else {
+                        a.keys_out[slot] = key;
+                        if (flags & AFF_F_MARK_PAD) a.keys_out[slot + 1] = INVALID_KEY;
                     }
                 }
-                if (j > 1) m_next2 = load_meta(pair_at(j - 2));
-                if (!active) continue;
-                if (LEVEL0) {
-                    if (m.y >> 31) P.y = neg(P.y);
-                    if (m.z != INVALID_KEY && (m.w >> 31)) Q.y = neg(Q.y);
-                }
-                fp_t den;
-                const int kind = affine_add_prepare(P, Q, den);
-                fp_t dinv = acc;
-                if (j > 0) {
-                    dinv = BPK_AFF_LAZY ? mul_lazy(acc, pre) : mul(acc, pre);
-                    acc = BPK_AFF_LAZY ? mul_lazy(acc, den) : mul(acc, den);
-                }
-                const affine_t R = BPK_AFF_LAZY ? affine_add_finish_lazy(kind, P, Q, dinv) : affine_add_finish(kind, P, Q, dinv);
-                const uint32_t key = m.x;
-                const uint32_t c0 = a.cnt0[key];
-                const uint32_t cn = (c0 + ((2u << a.level) - 1u)) >> (a.level + 1);  // entries of the bucket at level + 1
-                if (cn <= 1) {
-                    st_xyzz(a.buckets + key, xyzz_t::from_affine(R));
-                } else {
-                    const uint32_t rel = (uint32_t)p - (a.off_in[key] >> 1);
-                    const uint32_t slot = a.off_out[key] + rel;
-                    st_affine(a.pts_out + slot, R);
-                    a.keys_out[slot] = key;
-                    if (!a.out_is_tail && (cn & 1u) && rel == cn - 1) a.keys_out[slot + 1] = INVALID_KEY;
-                }
+                // .. and y1, x1 - x3
+                __syncwarp();
+                if (j > 0) stage_points(p - lane - T, vPN, vQN, 1);
+                cp_async_commit();
+            }
+        }
+    }
+}
+
+// The degenerate pairs of a level, flagged by the level kernel's forward pass (an identity operand, or equal x: a doubling
+// or opposite points): each is added on its own, with its own inversion, and placed like the others.  Clears the flags.
+// Random inputs have none; an SRS whose points coincide (the reference's own tests) goes through here entirely.
+template <bool LEVEL0>
+__global__ void __launch_bounds__(128) msm_affine_rare_kernel(const __grid_constant__ AffLevelArgs a) {
+    const uint32_t S = a.totals[a.level] >> 1;
+    const uint32_t words = (S + 31) >> 5;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
+        uint32_t bits = a.rare_bits[w];
+        if (bits == 0) continue;
+        a.rare_bits[w] = 0;
+        while (bits) {
+            const uint32_t p = (w << 5) + (uint32_t)__ffs((int)bits) - 1;
+            bits &= bits - 1;
+            uint32_t key;
+            affine_t P, Q;
+            if (LEVEL0) {
+                const uint4 m = reinterpret_cast<const uint4*>(a.kv0)[p];
+                key = m.x;
+                P = ld_affine(a.pts_in + (m.y & 0x7fffffffu));
+                Q = ld_affine(a.pts_in + (m.w & 0x7fffffffu));
+                if (m.y >> 31) P.y = neg(P.y);
+                if (m.w >> 31) Q.y = neg(Q.y);
+            } else {
+                key = a.keys_in[2 * (size_t)p];
+                P = ld_affine(a.pts_in + 2 * (size_t)p);
+                Q = ld_affine(a.pts_in + 2 * (size_t)p + 1);
+            }
+            fp_t den;
+            const int kind = affine_add_prepare(P, Q, den);
+            const affine_t R = affine_add_finish(kind, P, Q, kind == AFF_DBL ? inv(den) : den);
+            const uint32_t cn = (a.cnt0[key] + ((2u << a.level) - 1u)) >> (a.level + 1);
+            if (cn <= 1) {
+                st_xyzz(a.buckets + key, xyzz_t::from_affine(R));
+            } else {
+                const uint32_t rel = p - (a.off_in[key] >> 1);
+                const uint32_t slot = a.off_out[key] + rel;
+                st_affine(a.pts_out + slot, R);
+                a.keys_out[slot] = key;
+                if (!a.out_is_tail && (cn & 1u) && rel == cn - 1) a.keys_out[slot + 1] = INVALID_KEY;
             }
         }
     }
@@ -1160,6 +1297,8 @@ struct MsmWork {
     uint32_t* keys_lvl[2];    // [odd levels, even levels >= 2]
     affine_t* pts_lvl[2];
     uint4* scratch;
+    uint32_t* rare_bits;        // flags of the degenerate pairs of the level in flight
+    size_t rare_words;
     uint32_t aff_threads, bmax;
     size_t tail_ub;           // upper bound of the tail list
     uint32_t chunk;
@@ -1206,6 +1345,8 @@ static int msm_workspace(bpk_ctx* ctx, const MsmPlan& pl, size_t n, MsmWork* w) 
     w->keys_lvl[0] = w->keys_lvl[1] = nullptr;
     w->pts_lvl[0] = w->pts_lvl[1] = nullptr;
     w->scratch = nullptr;
+    w->rare_bits = nullptr;
+    w->rare_words = 0;
     w->aff_threads = (uint32_t)ctx->sm_count * BPK_AFF_MINBLOCKS * AFF_THREADS;
     w->bmax = (uint32_t)(ctx->opt_msm_batch < 1 ? 1 : ctx->opt_msm_batch);
     if (L >= 1) {
@@ -1222,6 +1363,8 @@ static int msm_workspace(bpk_ctx* ctx, const MsmPlan& pl, size_t n, MsmWork* w) 
         size_t need = (pairs0 + w->aff_threads - 1) / w->aff_threads;
         if (need < w->bmax) w->bmax = (uint32_t)(need < 1 ? 1 : need);
         BPK_TRY(ws_reserve(ctx, 19, (size_t)w->bmax * 3 * w->aff_threads * sizeof(uint4), (void**)&w->scratch));
+        w->rare_words = pairs0 / 32 + 2;
+        BPK_TRY(ws_reserve(ctx, 21, w->rare_words * sizeof(uint32_t), (void**)&w->rare_bits));
     }
     w->tail_ub = L == 0 ? w->M : level_ub(w->M, w->nb, L);
     w->chunk = msm_chunk(ctx, w->tail_ub);
@@ -1347,6 +1490,7 @@ static int msm_fill_buckets(bpk_ctx* ctx, const MsmPlan& pl, const MsmPoints& pt
     {
         StageTimer t(ctx, "msm.accumulate");
         BPK_CUDA(cudaMemsetAsync(buckets, 0, (size_t)w.nb * sizeof(xyzz_t), ctx->stream));
+        if (L > 0) BPK_CUDA(cudaMemsetAsync(w.rare_bits, 0, w.rare_words * sizeof(uint32_t), ctx->stream));
         for (int l = 0; l < L; l++) {
             AffLevelArgs a;
             a.kv0 = w.kv0;
@@ -1360,15 +1504,19 @@ static int msm_fill_buckets(bpk_ctx* ctx, const MsmPlan& pl, const MsmPoints& pt
             a.totals = w.totals;
             a.buckets = buckets;
             a.scratch = w.scratch;
+            a.rare_bits = w.rare_bits;
             a.level = (uint32_t)l;
             a.bmax = w.bmax;
             a.out_is_tail = l + 1 == L ? 1u : 0u;
             const unsigned grid = w.aff_threads / AFF_THREADS;
-            if (l == 0)
+            if (l == 0) {
                 msm_affine_level_kernel<true><<<grid, AFF_THREADS, AFF_SMEM_BYTES, ctx->stream>>>(a);
-            else
+                msm_affine_rare_kernel<true><<<(unsigned)ctx->sm_count * 4, 128, 0, ctx->stream>>>(a);
+            } else {
                 msm_affine_level_kernel<false><<<grid, AFF_THREADS, AFF_SMEM_BYTES, ctx->stream>>>(a);
-            count_launch(ctx);
+                msm_affine_rare_kernel<false><<<(unsigned)ctx->sm_count * 4, 128, 0, ctx->stream>>>(a);
+            }
+            count_launch(ctx, 2);
         }
         // the XYZZ tail of the tree (everything, when no affine level runs)
         BPK_CUDA(cudaMemsetAsync(w.long_count, 0, 2 * sizeof(uint32_t), ctx->stream));
