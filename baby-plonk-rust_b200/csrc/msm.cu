@@ -521,13 +521,13 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
         const uint2 kk = reinterpret_cast<const uint2*>(a.keys_in)[p];
         return make_uint4(kk.x, 0, kk.y, 0);
     };
-    auto stage_meta = [&](uint32_t p) {                   // the same word, into this lane's slot of the stage
-        if (p >= S) sts128(my_meta, LEVEL0 ? make_uint4(0, 0, INVALID_KEY, 0) : make_uint4(0, INVALID_KEY, 0, 0));
-        else if (LEVEL0) cp_async16(my_meta, reinterpret_cast<const uint4*>(a.kv0) + p);
-        else cp_async8(my_meta, reinterpret_cast<const uint2*>(a.keys_in) + p);
+    auto stage_meta = [&](uint32_t p, uint32_t slot_addr) {   // the same word, into a slot of this lane in the stage
+        if (p >= S) sts128(slot_addr, LEVEL0 ? make_uint4(0, 0, INVALID_KEY, 0) : make_uint4(0, INVALID_KEY, 0, 0));
+        else if (LEVEL0) cp_async16(slot_addr, reinterpret_cast<const uint4*>(a.kv0) + p);
+        else cp_async8(slot_addr, reinterpret_cast<const uint2*>(a.keys_in) + p);
     };
-    auto staged_meta = [&]() -> uint4 {
-        const uint4 s = lds128(my_meta);
+    auto staged_meta = [&](uint32_t slot_addr) -> uint4 {
+        const uint4 s = lds128(slot_addr);
         return LEVEL0 ? s : make_uint4(s.x, 0, s.y, 0);
     };
     auto stage_dest = [&](uint32_t key) {                 // where the sum of a pair of bucket `key` goes
@@ -535,11 +535,12 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
         cp_async4(my_dest + 4, a.off_in + key);
         cp_async4(my_dest + 8, a.off_out + key);
     };
-    // Cooperative copy of one coordinate (HALF 0: x, 1: y) of the operands of the warp's 32 pairs (first pair p0) into the
+    // Cooperative copy of one coordinate (SRC 0: x, 1: y) of the operands of the warp's 32 pairs (first pair p0) into the
     // stage: 3 neighbouring lanes copy the 16-byte pieces of one coordinate, 8 points per instruction (even, so that the
-    // destination is linear in i).  Point q of the warp (q = 2 lane' + which) lives at byte 208 lane' + 96 which.  vP, vQ:
-    // this lane's level-0 point words (a padded pair copies P twice).
-    auto stage_points = [&](uint32_t p0, uint32_t vP, uint32_t vQ, const int HALF) {
+    // destination is linear in i).  Point q of the warp (q = 2 lane' + which) lives at byte 208 lane' + 96 which, the
+    // coordinate in its first (HALF 0) or second 48 bytes.  vP, vQ: this lane's level-0 point words (a padded pair
+    // copies P twice).
+    auto stage_points = [&](uint32_t p0, uint32_t vP, uint32_t vQ, const int SRC, const int HALF) {
         const uint32_t sub = lane / 3, piece = lane - sub * 3;
         const bool on = sub < 8;                           // 24 lanes copy
         const uint32_t dst0 = wstage + (sub >> 1) * AFF_PAIR_STRIDE + (sub & 1) * 96 + HALF * 48 + piece * 16;
@@ -554,7 +555,7 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
             } else {
                 src = a.pts_in + 2 * (size_t)p0 + i * 8 + sub;
             }
-            if (on) cp_async16(dst0 + i * 4 * AFF_PAIR_STRIDE, reinterpret_cast<const uint4*>(src) + HALF * 3 + piece);
+            if (on) cp_async16(dst0 + i * 4 * AFF_PAIR_STRIDE, reinterpret_cast<const uint4*>(src) + SRC * 3 + piece);
         }
     };
     // the running product after pair jj of this thread's batch: scratch (written by the forward pass) -> stage
@@ -588,47 +589,58 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
         }
         const uint32_t njw = __shfl_sync(0xffffffffu, nj, 0);   // lane 0 has the most
 
-        // ---- forward: denominators and their running product.  Only the x coordinates are needed unless the pair is
-        // degenerate (identity operand, equal x), which is re-examined with the full points.
+        // ---- forward: denominators and their running product, two steps per turn: only the x coordinates are needed,
+        // those of the even step sit in the x half of the stage and those of the odd step in the y half, so that the
+        // copies for the next two steps have two products to land (with one step per turn the wait at the top of the
+        // loop was 7 % of all stall samples).  A degenerate pair (identity operand, equal x) is flagged and left out.
         fp_t prod = fp_t::one();
         {
-            uint32_t padN;
+            const uint32_t my_meta2 = my_dest;             // the layout-word slot holds the odd step's list word here
+            uint32_t pad0, pad1;
             {
-                const uint4 m = load_meta(base);
-                padN = m.z == INVALID_KEY;
-                if (njw > 1) stage_meta(base + T);
-                stage_points(base0, m.y, padN ? m.y : m.w, 0);
+                const uint4 m0 = load_meta(base), m1 = load_meta(base + T);
+                pad0 = m0.z == INVALID_KEY;
+                pad1 = m1.z == INVALID_KEY;
+                stage_meta(base + 2 * T, my_meta);
+                stage_meta(base + 3 * T, my_meta2);
+                stage_points(base0, m0.y, pad0 ? m0.y : m0.w, 0, 0);
+                if (njw > 1) stage_points(base0 + T, m1.y, pad1 ? m1.y : m1.w, 0, 1);   // (never past the level's lists)
                 cp_async_commit();
             }
             uint32_t p = base;                             // pair of step j
             uint4* s = sc;                                 // its slot of the prefix scratch
-            for (uint32_t j = 0; j < njw; j++, p += T, s += 3 * (size_t)T) {
-                const bool pad = padN;
+            auto step = [&](uint32_t j, uint32_t pj, uint4* sj, bool pad, const fp_t& x1, const fp_t& x2) {
+                fp_t den = sub(x2, x1);
+                if (pad) {
+                    den = fp_t::one();
+                } else if (den.is_zero() || x1.is_zero() || x2.is_zero()) {   // degenerate: not in this product
+                    den = fp_t::one();
+                    atomicOr(a.rare_bits + (pj >> 5), 1u << (pj & 31));
+                }
+                prod = j == 0 ? den : aff_mul(prod, den);
+                sj[0] = make_uint4(prod.l[0], prod.l[1], prod.l[2], prod.l[3]);
+                sj[T] = make_uint4(prod.l[4], prod.l[5], prod.l[6], prod.l[7]);
+                sj[2 * (size_t)T] = make_uint4(prod.l[8], prod.l[9], prod.l[10], prod.l[11]);
+            };
+            for (uint32_t j = 0; j < njw; j += 2, p += 2 * T, s += 6 * (size_t)T) {
                 cp_async_wait_all();
                 __syncwarp();
-                const fp_t x1 = lds_fp(my_pair);
-                const fp_t x2 = pad ? x1 : lds_fp(my_pair + 96);
-                uint4 mN = make_uint4(0, 0, INVALID_KEY, 0);
-                if (j + 1 < njw) mN = staged_meta();
+                const fp_t x1a = lds_fp(my_pair), x2a = pad0 ? x1a : lds_fp(my_pair + 96);
+                const fp_t x1b = lds_fp(my_pair + 48), x2b = pad1 ? x1b : lds_fp(my_pair + 144);
+                const uint4 mA = staged_meta(my_meta), mB = staged_meta(my_meta2);   // steps j + 2, j + 3
                 __syncwarp();
-                padN = mN.z == INVALID_KEY;
-                if (j + 1 < njw) {
-                    if (j + 2 < njw) stage_meta(p + 2 * T);
-                    stage_points(p - lane + T, mN.y, padN ? mN.y : mN.w, 0);
+                const bool padA = mA.z == INVALID_KEY, padB = mB.z == INVALID_KEY;
+                if (j + 2 < njw) {
+                    stage_meta(p + 4 * T, my_meta);
+                    stage_meta(p + 5 * T, my_meta2);
+                    stage_points(p - lane + 2 * T, mA.y, padA ? mA.y : mA.w, 0, 0);
+                    if (j + 3 < njw) stage_points(p - lane + 3 * T, mB.y, padB ? mB.y : mB.w, 0, 1);
                     cp_async_commit();
                 }
-                if (j < nj) {
-                    fp_t den = sub(x2, x1);
-                    if (pad) den = fp_t::one();
-                    else if (den.is_zero() || x1.is_zero() || x2.is_zero()) {   // degenerate: not in this product
-                        den = fp_t::one();
-                        atomicOr(a.rare_bits + (p >> 5), 1u << (p & 31));
-                    }
-                    prod = j == 0 ? den : aff_mul(prod, den);
-                    s[0] = make_uint4(prod.l[0], prod.l[1], prod.l[2], prod.l[3]);
-                    s[T] = make_uint4(prod.l[4], prod.l[5], prod.l[6], prod.l[7]);
-                    s[2 * (size_t)T] = make_uint4(prod.l[8], prod.l[9], prod.l[10], prod.l[11]);
-                }
+                if (j < nj) step(j, p, s, pad0, x1a, x2a);
+                if (j + 1 < nj) step(j + 1, p + T, s + 3 * (size_t)T, pad1, x1b, x2b);
+                pad0 = padA;
+                pad1 = padB;
             }
         }
 
@@ -647,12 +659,12 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
                 flagsN = flags_of(m);
                 vPN = m.y;
                 vQN = (flagsN & AFF_F_PAD) ? m.y : m.w;
-                if (njw > 1) stage_meta(p - T);
+                if (njw > 1) stage_meta(p - T, my_meta);
                 stage_dest(keyN);
-                stage_points(p - lane, vPN, vQN, 0);
+                stage_points(p - lane, vPN, vQN, 0, 0);
                 if (njw > 1 && nj == njw) stage_prefix(njw - 2);   // needed at the first step if this lane takes part in it
                 cp_async_commit();
-                stage_points(p - lane, vPN, vQN, 1);
+                stage_points(p - lane, vPN, vQN, 1, 1);
                 cp_async_commit();
             }
             for (uint32_t j = njw; j-- > 0; p -= T) {
@@ -713,14 +725,14 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
                 // every lane has read x1, x2 for the last time
                 __syncwarp();
                 if (j > 0) {
-                    const uint4 mN = staged_meta();
+                    const uint4 mN = staged_meta(my_meta);
                     keyN = mN.x;
                     flagsN = flags_of(mN);
                     vPN = mN.y;
                     vQN = (flagsN & AFF_F_PAD) ? mN.y : mN.w;
-                    if (j > 1) stage_meta(p - 2 * T);
+                    if (j > 1) stage_meta(p - 2 * T, my_meta);
                     stage_dest(keyN);
-                    stage_points(p - lane - T, vPN, vQN, 0);
+                    stage_points(p - lane - T, vPN, vQN, 0, 0);
                     // the prefix needed at step j - 1 is the product after pair j - 2 (own slots: no other lane reads them)
                     if (j > 1 && j - 1 < nj) stage_prefix(j - 2);
                 }
@@ -742,7 +754,7 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
                 }
                 // .. and y1, x1 - x3
                 __syncwarp();
-                if (j > 0) stage_points(p - lane - T, vPN, vQN, 1);
+                if (j > 0) stage_points(p - lane - T, vPN, vQN, 1, 1);
                 cp_async_commit();
             }
         }
