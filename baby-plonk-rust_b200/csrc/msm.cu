@@ -1055,6 +1055,8 @@ __global__ void __launch_bounds__(128, BPK_TREE_MINBLOCKS) msm_plane_tree_level_
     xyzz_t b = ld_xyzz(c1 + s);
     // buckets finished by the affine tree arrive as (x, y, 1, 1): their sum needs a third of the products
     const fp_t one = fp_t::one();
+    // (level 1 only: taking the lowest plane of level 2 the same way makes every warp of that level run both paths --
+    // measured 3.25 -> 3.59 ms at 2^21 buckets)
     if (k == 1 && a.ZZ == one && a.ZZZ == one && b.ZZ == one && b.ZZZ == one && a.X != b.X)
         a = xyzz_from_affine_sum(a.X, a.Y, b.X, b.Y);
     else
@@ -1172,6 +1174,40 @@ __global__ void __launch_bounds__(128) msm_finalize_planes_kernel(const xyzz_t* 
     for (int k = (int)W - 2; k >= 0; k--) {
         for (uint32_t i = 0; i < c; i++) xyzz_dbl(acc);
         xyzz_t v = part[(size_t)k * groups];
+        xyzz_add(acc, v);
+    }
+    write_projective(out, acc, normalise != 0);
+}
+
+// The same for at most four windows (precomputed levels: one), by one warp per window: lane p takes plane p and doubles
+// it p times -- all lanes in step, so the serial path is L - 1 doublings instead of L doublings and L additions --, lane
+// 31 takes the plain bucket sum, and a shuffle tree adds the lanes (5 additions).
+__global__ void __launch_bounds__(128) msm_finalize_planes_warp_kernel(const xyzz_t* __restrict__ roots, uint32_t W,
+                                                                        uint32_t L, uint32_t c, int normalise,
+                                                                        uint64_t* out) {
+    __shared__ xyzz_t win[4];
+    const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const xyzz_t* root = roots + (size_t)w * (L + 1);   // [S, T_0 .. T_{L-1}], L <= 31
+    xyzz_t acc = xyzz_t::inf();
+    if (lane < L) acc = ld_xyzz(root + 1 + lane);
+    else if (lane == 31) acc = ld_xyzz(root);
+#pragma unroll 1
+    for (uint32_t i = 0; i + 1 < L; i++)
+        if (i < lane && lane < L) xyzz_dbl(acc);
+    __syncwarp();
+#pragma unroll 1
+    for (int delta = 16; delta >= 1; delta >>= 1) {
+        xyzz_t o = shfl_down_xyzz(acc, delta);
+        xyzz_add(acc, o);
+        __syncwarp();
+    }
+    if (lane == 0) win[w] = acc;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    acc = win[W - 1];
+    for (int k = (int)W - 2; k >= 0; k--) {
+        for (uint32_t i = 0; i < c; i++) xyzz_dbl(acc);
+        xyzz_t v = win[k];
         xyzz_add(acc, v);
     }
     write_projective(out, acc, normalise != 0);
@@ -1600,7 +1636,10 @@ static int msm_reduce_buckets(bpk_ctx* ctx, const MsmPlan& pl, xyzz_t* buckets, 
         StageTimer t(ctx, "msm.finalize");
         uint32_t groups = (L + FIN_GROUP - 1) / FIN_GROUP;
         if (groups == 0 || WB * groups > 128) groups = 1;
-        msm_finalize_planes_kernel<<<1, 128, 0, ctx->stream>>>(roots, WB, L, c, groups, normalise ? 1 : 0, d_out);
+        if (WB <= 4 && L >= 1 && L <= 31)
+            msm_finalize_planes_warp_kernel<<<1, 32 * WB, 0, ctx->stream>>>(roots, WB, L, c, normalise ? 1 : 0, d_out);
+        else
+            msm_finalize_planes_kernel<<<1, 128, 0, ctx->stream>>>(roots, WB, L, c, groups, normalise ? 1 : 0, d_out);
         count_launch(ctx);
         BPK_CUDA(cudaGetLastError());
         t.end();

@@ -15,7 +15,11 @@ logns = [int(x) for x in sys.argv[2:]] or [16, 18, 20, 22]
 rng = np.random.default_rng(5)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 res = []
-WINDOWS = {16: [8, 10, 12, 13, 14], 18: [12, 14, 16, 17, 18], 20: [16, 18, 19, 20], 22: [18, 19, 20, 21], 24: [21, 22]}
+WINDOWS = {16: [8, 10, 12, 13, 14], 18: [12, 14, 16, 17, 18], 20: [16, 18, 19, 20], 21: [19, 20, 21], 22: [18, 19, 20, 21],
+           24: [21, 22]}
+if os.environ.get("SWEEP_WINDOWS"):      # e.g. SWEEP_WINDOWS="16:12,13;20:19,20"
+    WINDOWS = {int(k): [int(x) for x in v.split(",")] for k, v in (kv.split(":") for kv in os.environ["SWEEP_WINDOWS"].split(";"))}
+MIN_PAIRS = [1 << int(x) for x in os.environ.get("SWEEP_MIN_PAIRS", "16,18,20,21,22,23,30").split(",")]
 for logn in logns:
     n = 1 << logn
     a = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
@@ -25,7 +29,7 @@ for logn in logns:
     ref = None
     for c in WINDOWS.get(logn, [0]):
         setup = pkg.Setup.generate_srs(n, 101, ctx).precompute(c)
-        for mp in (1 << 16, 1 << 18, 1 << 20, 1 << 21, 1 << 22, 1 << 23, 1 << 30):
+        for mp in MIN_PAIRS:
             ctx.set_option("msm.min_pairs", mp)
             ts = []
             for it in range(7):
