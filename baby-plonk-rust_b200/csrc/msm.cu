@@ -439,6 +439,10 @@ constexpr int AFF_THREADS = 128;
 // Per warp: 32 pairs x 208 B (P.x P.y Q.x Q.y + 16 B so that the lanes' 16-byte reads fall into different banks), 32
 // prefix products, 32 pair-list words x 16 B, 32 x (count, offsets) x 16 B, 32 running inverses, 32 slopes (48 B each,
 // as [3][32] 16-byte pieces).
+#ifndef BPK_AFF_COPY_UNROLL
+#define BPK_AFF_COPY_UNROLL 4   // of the 8 copy instructions per coordinate (A/B: 8 fully unrolled)
+#endif
+constexpr int AFF_COPY_UNROLL = BPK_AFF_COPY_UNROLL;
 #ifndef BPK_AFF_LAZY
 #define BPK_AFF_LAZY 1    // products of the tree stay in [0, 2p): six conditional subtractions fewer per addition
 #endif
@@ -545,7 +549,7 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
         const bool on = sub < 8;                           // 24 lanes copy
         const uint32_t dst0 = wstage + (sub >> 1) * AFF_PAIR_STRIDE + (sub & 1) * 96 + HALF * 48 + piece * 16;
         const uint32_t iP = vP & 0x7fffffffu, iQ = vQ & 0x7fffffffu;
-#pragma unroll 4
+#pragma unroll AFF_COPY_UNROLL
         for (int i = 0; i < 8; i++) {
             const affine_t* src;
             if (LEVEL0) {
