@@ -795,7 +795,8 @@ __global__ void __launch_bounds__(128) msm_affine_rare_kernel(const __grid_const
             }
             fp_t den;
             const int kind = affine_add_prepare(P, Q, den);
-            const affine_t R = affine_add_finish(kind, P, Q, kind == AFF_DBL ? inv(den) : den);
+            // (a point with x = 0 that is not the identity -- (0, +-2) lies on the curve -- arrives here as a plain addition)
+            const affine_t R = affine_add_finish(kind, P, Q, (kind == AFF_DBL || kind == AFF_ADD) ? inv(den) : den);
             const uint32_t cn = (a.cnt0[key] + ((2u << a.level) - 1u)) >> (a.level + 1);
             if (cn <= 1) {
                 st_xyzz(a.buckets + key, xyzz_t::from_affine(R));

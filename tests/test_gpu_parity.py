@@ -513,6 +513,14 @@ def test_msm_affine_tree_degenerate_points(ctx, levels):
         s.precompute(6)
         assert bpk.point_to_affine(s.commit_scalars(S(sc))) == O.msm_naive(pts, sc)
         s.free()
+        # x = 0 without being the identity: (0, 2) and (0, -2) lie on y^2 = x^3 + 4; the kernels test x == 0 first and must
+        # then tell them from the identity encoding (0, 0)
+        Z2, Z2n = (0, 2), (0, O.P - 2)
+        pts = ([G, Z2, O.g1_double(G), Z2n, Z2, None, Z2, G] * 40)[:300]
+        s = bpk.Setup.from_points(bpk.points_from_affine(pts), ctx)
+        for sc in (O.random_fr(9, len(pts)), [3] * len(pts)):
+            assert bpk.point_to_affine(s.commit_scalars(S(sc))) == O.msm_naive(pts, sc)
+        s.free()
 
 
 @pytest.mark.parametrize("levels", [0, 2, 12])
