@@ -218,7 +218,10 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(RecodeArgs a, uint32_t
 // The recoded windows come from the cache the counting pass wrote ([W][n] words, read with the streaming hint), so a phase
 // costs one 4-byte load and a compare per entry.  `skew` (set by the layout scan when one bucket holds a large share
 // of the entries) switches to warp-aggregated cursor updates.
-constexpr uint32_t RANGE_ITEMS = 8;  // cached digits per thread and phase (two 16-byte loads)
+#ifndef BPK_RANGE_ITEMS
+#define BPK_RANGE_ITEMS 8
+#endif
+constexpr uint32_t RANGE_ITEMS = BPK_RANGE_ITEMS;  // cached digits per thread and phase (16-byte loads)
 __global__ void __launch_bounds__(256) msm_scatter_range_kernel(RecodeArgs a, uint32_t* __restrict__ cursor,
                                                                  const uint32_t* __restrict__ skew, uint32_t key_lo,
                                                                  uint32_t key_hi, uint2* __restrict__ kv0) {
@@ -229,25 +232,31 @@ __global__ void __launch_bounds__(256) msm_scatter_range_kernel(RecodeArgs a, ui
     uint32_t d[RANGE_ITEMS];
     if (e0 + RANGE_ITEMS <= M) {
         const uint4* q = reinterpret_cast<const uint4*>(a.digits + e0);
-        const uint4 u = __ldcs(q), v = __ldcs(q + 1);
-        d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
-        d[4] = v.x; d[5] = v.y; d[6] = v.z; d[7] = v.w;
+#pragma unroll
+        for (uint32_t k = 0; k < RANGE_ITEMS / 4; k++) {
+            const uint4 u = __ldcs(q + k);
+            d[4 * k] = u.x; d[4 * k + 1] = u.y; d[4 * k + 2] = u.z; d[4 * k + 3] = u.w;
+        }
     } else {
 #pragma unroll
         for (uint32_t k = 0; k < RANGE_ITEMS; k++) d[k] = e0 + k < M ? a.digits[e0 + k] : 0x7fffffffu;
+    }
+    // all cursor updates of the thread first, then its stores: the updates are what the phase waits for (ncu:
+    // `long_scoreboard` 78 per issue), one in flight per thread leaves the L2 idle
+    uint32_t pos[RANGE_ITEMS];
+#pragma unroll
+    for (uint32_t k = 0; k < RANGE_ITEMS; k++) {
+        const uint32_t key = d[k] & 0x7fffffffu;
+        const bool mine = key >= key_lo && key < key_hi;   // a zero digit (0x7fffffff) is above every range
+        if (agg) pos[k] = cursor_take(cursor, key, mine, true, lane);
+        else pos[k] = mine ? atomicAdd(cursor + key, 1u) : 0u;
     }
     uint32_t w = (uint32_t)(e0 / a.n), i = (uint32_t)(e0 - (size_t)w * a.n);
 #pragma unroll
     for (uint32_t k = 0; k < RANGE_ITEMS; k++) {
         const uint32_t key = d[k] & 0x7fffffffu;
-        const bool mine = key >= key_lo && key < key_hi;   // a zero digit (0x7fffffff) is above every range
-        const uint32_t val = (w * a.val_stride + i) | (d[k] & 0x80000000u);
-        if (agg) {
-            const uint32_t pos = cursor_take(cursor, key, mine, true, lane);
-            if (mine) kv0[pos] = make_uint2(key, val);
-        } else if (mine) {
-            kv0[atomicAdd(cursor + key, 1u)] = make_uint2(key, val);
-        }
+        const bool mine = key >= key_lo && key < key_hi;
+        if (mine) kv0[pos[k]] = make_uint2(key, (w * a.val_stride + i) | (d[k] & 0x80000000u));
         if (++i == a.n) {
             i = 0;
             w++;
