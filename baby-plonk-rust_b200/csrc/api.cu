@@ -521,12 +521,14 @@ extern "C" int bpk_srs_precompute(bpk_ctx* ctx, uint64_t handle, unsigned window
     if (e.n == 0) return BPK_OK;
     unsigned c = window_bits;
     if (c == 0) {
-        // measured optimum of the sweep in profiles/r2_msm_plan_sweep.md (c = 8..21 at 2^16..2^22, c = 21..23 at 2^24):
-        // larger windows trade W n pair additions against 2^(c-1) bucket additions and tree depth
+        // measured optimum of the sweeps in profiles/r2_msm_plan_sweep.md (c = 8..21 at 2^16..2^22, c = 20..23 at 2^23, 2^24):
+        // larger windows trade W n pair additions against 2^(c-1) bucket additions and tree depth.  Windows that leave the
+        // top digit only 3 bits (c = 18, 21: 255 = 14 x 18 + 3 = 12 x 21 + 3) put all n entries of that digit into four
+        // buckets -- contended histogram updates and long runs in the tail -- and lose to their neighbours.
         unsigned lg = 0;
         while (((size_t)2 << lg) <= e.n) lg++;          // floor(log2 n)
         if (e.n - ((size_t)1 << lg) >= ((size_t)1 << lg) / 2) lg++;  // nearest power of two
-        c = lg <= 16 ? (lg < 9 ? 6 : lg - 3) : lg == 17 ? 15 : lg == 18 ? 16 : lg == 19 ? 18 : lg <= 22 ? 20 : lg == 23 ? 21 : 22;
+        c = lg <= 16 ? (lg < 9 ? 6 : lg - 3) : lg <= 18 ? 16 : lg == 19 ? 17 : lg <= 23 ? 20 : 22;
     }
     if (c < 2 || c > 24) return BPK_ERR_INVALID_ARG;
     const unsigned W = (256 + c - 1) / c;
