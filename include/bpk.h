@@ -239,7 +239,11 @@ int bpk_msm_last_plan(bpk_ctx* ctx, unsigned out[4]);
  * coordinates by the pairwise tree, additions left to the XYZZ tail, non-empty buckets, tree levels launched,
  * additions per shared inversion}. */
 int bpk_msm_last_stats(bpk_ctx* ctx, uint64_t out[6]);
-/* Register-only IMAD.WIDE throughput probe: returns 32x32+64 multiply-adds per second. */
+/* Register-only IMAD.WIDE throughput probe: returns 32x32+64 multiply-adds per second.  "imad.mode" selects the form: 0
+ * independent accumulates, 1 two 12-limb carry chains, 2 fused accumulates with a 64-bit addend, 3 the Fp product the MSM
+ * kernels call (dependent chain), 4 the same product inlined, 5 two independent inlined products; "imad.warps_per_sm"
+ * (4..64, multiple of 4, default 64) the resident warps per SM -- the pair that showed the multiplier saturates with two
+ * warps per scheduler (profiles/r2_affine_v2.md). */
 int bpk_imad_peak(bpk_ctx* ctx, double* wide_imad_per_s_out, double* seconds_out);
 /* Tunables (A/B measurements and tests; the defaults are the measured optima):
  *   "msm.window" window bits of the non-precomputed MSM (0 = auto), "msm.chunk" pairs per accumulate thread (0 = auto),
@@ -253,7 +257,7 @@ int bpk_imad_peak(bpk_ctx* ctx, double* wide_imad_per_s_out, double* seconds_out
  *   thread with two products per call (auto uses it below 2^18 elements),
  *   "ntt.scratch_mib" scratch bound of a batched transform (larger batches go a few rows at a time),
  *   "ntt.direct_max_log2" largest per-size inter-pass twiddle table, "ntt.direct_budget_mib" HBM budget of all
- *   such tables together (a cache: dropped and rebuilt on demand beyond it, or when an allocation fails), "imad.mode" probe form of bpk_imad_peak,
+ *   such tables together (a cache: dropped and rebuilt on demand beyond it, or when an allocation fails), "imad.mode" / "imad.warps_per_sm" form and occupancy of bpk_imad_peak,
  *   "host.stage_threads" threads that stage PAGEABLE host inputs through pinned buffers (0 = leave it to the driver).
  * Unknown keys and out-of-range values return BPK_ERR_INVALID_ARG. */
 int bpk_set_option(bpk_ctx* ctx, const char* key, long value);
