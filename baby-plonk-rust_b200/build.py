@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libbpk.so")
-SOURCES = ["api.cu", "ntt.cu", "msm.cu", "srs.cu", "polyops.cu"]
+SOURCES = ["api.cu", "ntt.cu", "msm.cu", "msm_tree.cu", "srs.cu", "polyops.cu"]
 HEADERS = ["ff.cuh", "ec.cuh", "internal.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -208,6 +208,8 @@ int msm_run_from_host(bpk_ctx* ctx, const MsmPoints& pts, const uint64_t* h_scal
                       unsigned rshift, bool normalise, uint64_t* d_out_xyz);
 int g1_sum_run(bpk_ctx* ctx, const uint64_t* d_points_xyz, size_t n, uint64_t* d_out_xyz);
 int msm_read_stats(bpk_ctx* ctx, uint64_t out[4]);
+// one wide level of the bucket-reduction tree (msm_tree.cu): nodes_out nodes of k + 1 points from 2 nodes_out of k
+void msm_launch_plane_tree_level(cudaStream_t stream, const xyzz_t* in, xyzz_t* out, uint32_t k, size_t nodes_out);
 
 // ---- srs.cu ----
 int srs_from_projective(bpk_ctx* ctx, const uint64_t* d_xyz, size_t n, affine_t* d_out);

@@ -1048,34 +1048,8 @@ __global__ void __launch_bounds__(MERGE_BLOCK) msm_merge_long_runs_kernel(const 
 // running-sum chains; the wide levels run at arithmetic throughput, each narrow level costs one addition of
 // latency.  2^p is applied once, in the final Horner pass over the root's L plane sums.
 // ------------------------------------------------------------------------------------------
-#ifndef BPK_TREE_MINBLOCKS
-#define BPK_TREE_MINBLOCKS 3
-#endif
-__global__ void __launch_bounds__(128, BPK_TREE_MINBLOCKS) msm_plane_tree_level_kernel(const xyzz_t* __restrict__ in,
-                                                                    xyzz_t* __restrict__ out, uint32_t k,
-                                                                    size_t nodes_out) {
-    // one thread per addition, slot-major (t = s nodes + node): the lanes of a warp do the same kind of work.  The copy
-    // T_{k-1}' = S(c1) is the second operand of the node's s = 0 addition and is written by that thread.  (One thread per
-    // output slot, node-major, left 1 / (k + 1) of the lanes idle: 50 % at the widest level.)
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nodes_out * k) return;
-    const uint32_t s = (uint32_t)(t / nodes_out);
-    const size_t node = t - (size_t)s * nodes_out;
-    const xyzz_t* c0 = in + 2 * node * k;  // children hold k points each
-    const xyzz_t* c1 = c0 + k;
-    xyzz_t* o = out + node * (k + 1);
-    xyzz_t a = ld_xyzz(c0 + s);
-    xyzz_t b = ld_xyzz(c1 + s);
-    if (s == 0) st_xyzz(o + k, b);
-    // buckets finished by the affine tree arrive as (x, y, 1, 1), and so do their copies in the lowest plane of level 2:
-    // their sum needs a third of the products
-    const fp_t one = fp_t::one();
-    if ((k == 1 || (k == 2 && s == 1)) && a.ZZ == one && a.ZZZ == one && b.ZZ == one && b.ZZZ == one && a.X != b.X)
-        a = xyzz_from_affine_sum(a.X, a.Y, b.X, b.Y);
-    else
-        xyzz_add(a, b);
-    st_xyzz(o + s, a);
-}
+// (msm_plane_tree_level_kernel, the wide levels: msm_tree.cu -- the one kernel of the MSM that is faster with its
+// products inlined)
 
 // The narrow top of the same tree in ONE block: from level k_first on, a level has at most 512 (node, slot) additions, so
 // a launch per level is all latency (launch gap + one addition each).  The block keeps the levels in its ping-pong
@@ -1631,7 +1605,7 @@ static int msm_reduce_buckets(bpk_ctx* ctx, const MsmPlan& pl, xyzz_t* buckets, 
             // every later level is narrower still (nodes halve, slots grow by one): finish in one block
             if (ctx->opt_msm_tree_top && threads <= TREE_TOP_THREADS) break;
             xyzz_t* out = (k & 1) ? lvl : lvl + buf_a;
-            msm_plane_tree_level_kernel<<<(unsigned)((nodes * k + 127) / 128), 128, 0, ctx->stream>>>(in, out, k, nodes);
+            msm_launch_plane_tree_level(ctx->stream, in, out, k, nodes);
             count_launch(ctx);
             in = out;
         }
