@@ -430,8 +430,8 @@ constexpr int AFF_THREADS = 128;
 // How the level kernel touches memory (profiles/r2_affine_ab.md, profiles/r2_affine_v2.md):
 //  * operands: what bounds a kernel in which every lane loads its own 96-byte points is the SM's single L1TEX queue (a
 //    warp-wide 16-byte load whose lanes touch 32 different lines costs 32 wavefronts), so the warp gathers
-//    COOPERATIVELY: 6 (3 for x only) neighbouring lanes copy the 16-byte pieces of one point with cp.async, five (ten)
-//    points per instruction, into the warp's stage in shared memory;
+//    COOPERATIVELY: 3 neighbouring lanes copy the 16-byte pieces of one coordinate with cp.async, eight points per
+//    instruction, into the warp's stage in shared memory;
 //  * nothing is loaded from global or local memory into registers inside the loops: a register load must have landed
 //    before the next out-of-line product is called (the callee may use the register), which exposes its whole latency.
 //    The pair lists, the bucket layout words and the prefix products all arrive through cp.async one step ahead.  The
