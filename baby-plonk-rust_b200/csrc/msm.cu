@@ -420,6 +420,7 @@ struct AffLevelArgs {
     xyzz_t* buckets;           // finished buckets, as XYZZ (x, y, 1, 1)
     uint4* scratch;            // prefix products: [bmax][3][threads of the launch]
     uint32_t* rare_bits;       // one flag per pair: degenerate, left to msm_affine_rare_kernel
+    uint32_t* claim;           // pairs of this level handed out so far
     uint32_t level, bmax, out_is_tail;
 };
 
@@ -427,6 +428,10 @@ struct AffLevelArgs {
 #define BPK_AFF_MINBLOCKS 4
 #endif
 constexpr int AFF_THREADS = 128;
+#ifndef BPK_AFF_MIN_BATCH
+#define BPK_AFF_MIN_BATCH 8
+#endif
+constexpr uint32_t AFF_MIN_BATCH = BPK_AFF_MIN_BATCH;   // the shortest batch a warp claims (steps of 32 pairs)
 // How the level kernel touches memory (profiles/r2_affine_ab.md, profiles/r2_affine_v2.md):
 //  * operands: what bounds a kernel in which every lane loads its own 96-byte points is the SM's single L1TEX queue (a
 //    warp-wide 16-byte load whose lanes touch 32 different lines costs 32 wavefronts), so the warp gathers
@@ -511,12 +516,13 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
     if (S == 0) return;
     const uint32_t T = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
-    // every thread takes batches of B pairs, interleaved with the other threads (pair = base + j T + tid): the lanes of a
-    // warp work on 32 neighbouring pairs at every step; B is the smallest batch that covers the level in whole rounds.
-    // Pair numbers fit 32 bits: S <= 2^31 and a batch spans B T <= 2^25 pairs.
-    const uint32_t per_round = T * a.bmax;                // <= 2^27
-    const uint32_t rounds = (S - 1) / per_round + 1;
-    const uint32_t B = (S - 1) / (T * rounds) + 1;        // T rounds <= S / bmax + T
+    // A warp works on 32 neighbouring pairs at every step and shares one inversion per lane over a batch of B steps.  The
+    // batches are CLAIMED from a counter (guided: an even share of what is left, between AFF_MIN_BATCH and bmax steps):
+    // with a fixed share per warp the schedulers' preference for their oldest warp let some warps finish a fifth of the
+    // kernel before others (ncu: 3.17 of 4 warps resident per scheduler on average), and the pipe idles with them.
+    // Pair numbers fit 32 bits: S <= 2^31, and the counter overshoots S by less than 32 bmax per warp.
+    const uint32_t nwarps = T >> 5;
+    constexpr uint32_t PS = 32;                           // pairs per step of a warp
     uint4* const sc = a.scratch + tid;
     // this warp's stage (layout above): the pair of lane l at 208 l, this lane's 16-byte slots of the other arrays at
     // my16 + the array's offset
@@ -589,15 +595,25 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
                (LEVEL0 && !pad && (m.w >> 31) ? AFF_F_NEG_Q : 0u);
     };
 
-    // A thread's pairs are g T + tid, g = 0, 1, ..; it works through them in batches of B.  (Starting the CTAs of an SM
-    // with first batches of different length, so that their forward / inversion / backward phases interleave, was
-    // measured: 59.5 against 58.6 ms -- the warps are not phase-locked, the extra batch only costs an inversion.)
-    for (uint32_t base = tid;; base += B * T) {
-        const uint32_t base0 = base - lane;               // the warp's first pair of this batch
+    // (Starting the CTAs of an SM with first batches of different length, so that their forward / inversion / backward
+    // phases interleave, was measured: 59.5 against 58.6 ms -- the warps are not phase-locked.)
+    for (;;) {
+        uint32_t base0 = 0, B = 0;                        // the warp's first pair of this batch, its steps
+        if (lane == 0) {
+            const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(a.claim);
+            const uint32_t left = seen < S ? S - seen : 0u;
+            B = left / (PS * nwarps);
+            if (B < AFF_MIN_BATCH) B = AFF_MIN_BATCH;
+            if (B > a.bmax) B = a.bmax;                   // (the prefix scratch holds bmax steps per thread)
+            base0 = atomicAdd(a.claim, PS * B);
+        }
+        base0 = __shfl_sync(0xffffffffu, base0, 0);
+        B = __shfl_sync(0xffffffffu, B, 0);
         if (base0 >= S) break;                            // warp-uniform
+        const uint32_t base = base0 + lane;
         uint32_t nj = 0;
         if (base < S) {
-            const uint32_t left = (S - base + T - 1) / T;
+            const uint32_t left = (S - base + PS - 1) / PS;
             nj = left < B ? left : B;
         }
         const uint32_t njw = __shfl_sync(0xffffffffu, nj, 0);   // lane 0 has the most
@@ -611,13 +627,13 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
             const uint32_t my_meta2 = my_dest;             // the layout-word slot holds the odd step's list word here
             uint32_t pad0, pad1;
             {
-                const uint4 m0 = load_meta(base), m1 = load_meta(base + T);
+                const uint4 m0 = load_meta(base), m1 = load_meta(base + PS);
                 pad0 = m0.z == INVALID_KEY;
                 pad1 = m1.z == INVALID_KEY;
-                stage_meta(base + 2 * T, my_meta);
-                stage_meta(base + 3 * T, my_meta2);
+                stage_meta(base + 2 * PS, my_meta);
+                stage_meta(base + 3 * PS, my_meta2);
                 stage_points(base0, m0.y, pad0 ? m0.y : m0.w, 0, 0);
-                if (njw > 1) stage_points(base0 + T, m1.y, pad1 ? m1.y : m1.w, 0, 1);   // (never past the level's lists)
+                if (njw > 1) stage_points(base0 + PS, m1.y, pad1 ? m1.y : m1.w, 0, 1);   // (never past the level's lists)
                 cp_async_commit();
             }
             uint32_t p = base;                             // pair of step j
@@ -635,7 +651,7 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
                 sj[T] = make_uint4(prod.l[4], prod.l[5], prod.l[6], prod.l[7]);
                 sj[2 * (size_t)T] = make_uint4(prod.l[8], prod.l[9], prod.l[10], prod.l[11]);
             };
-            for (uint32_t j = 0; j < njw; j += 2, p += 2 * T, s += 6 * (size_t)T) {
+            for (uint32_t j = 0; j < njw; j += 2, p += 2 * PS, s += 6 * (size_t)T) {
                 cp_async_wait_all();
                 __syncwarp();
                 const fp_t x1a = lds_fp(my_pair), x2a = pad0 ? x1a : lds_fp(my_pair + 96);
@@ -644,14 +660,14 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
                 __syncwarp();
                 const bool padA = mA.z == INVALID_KEY, padB = mB.z == INVALID_KEY;
                 if (j + 2 < njw) {
-                    stage_meta(p + 4 * T, my_meta);
-                    stage_meta(p + 5 * T, my_meta2);
-                    stage_points(p - lane + 2 * T, mA.y, padA ? mA.y : mA.w, 0, 0);
-                    if (j + 3 < njw) stage_points(p - lane + 3 * T, mB.y, padB ? mB.y : mB.w, 0, 1);
+                    stage_meta(p + 4 * PS, my_meta);
+                    stage_meta(p + 5 * PS, my_meta2);
+                    stage_points(p - lane + 2 * PS, mA.y, padA ? mA.y : mA.w, 0, 0);
+                    if (j + 3 < njw) stage_points(p - lane + 3 * PS, mB.y, padB ? mB.y : mB.w, 0, 1);
                     cp_async_commit();
                 }
                 if (j < nj) step(j, p, s, pad0, x1a, x2a);
-                if (j + 1 < nj) step(j + 1, p + T, s + 3 * (size_t)T, pad1, x1b, x2b);
+                if (j + 1 < nj) step(j + 1, p + PS, s + 3 * (size_t)T, pad1, x1b, x2b);
                 pad0 = padA;
                 pad1 = padB;
             }
@@ -665,14 +681,14 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
         // Q.y was), and are waited for only after the next step's first two products.
         {
             uint32_t keyN, flagsN, vPN, vQN;
-            uint32_t p = base + (njw - 1) * T;             // pair of step j
+            uint32_t p = base + (njw - 1) * PS;            // pair of step j
             {
                 const uint4 m = load_meta(p);
                 keyN = m.x;
                 flagsN = flags_of(m);
                 vPN = m.y;
                 vQN = (flagsN & AFF_F_PAD) ? m.y : m.w;
-                if (njw > 1) stage_meta(p - T, my_meta);
+                if (njw > 1) stage_meta(p - PS, my_meta);
                 stage_dest(keyN);
                 stage_points(p - lane, vPN, vQN, 0, 0);
                 if (njw > 1 && nj == njw) stage_prefix(njw - 2);   // needed at the first step if this lane takes part in it
@@ -680,7 +696,7 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
                 stage_points(p - lane, vPN, vQN, 1, 1);
                 cp_async_commit();
             }
-            for (uint32_t j = njw; j-- > 0; p -= T) {
+            for (uint32_t j = njw; j-- > 0; p -= PS) {
                 const uint32_t key = keyN;
                 uint32_t flags = flagsN;
                 const bool active = j < nj;
@@ -743,9 +759,9 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
                     flagsN = flags_of(mN);
                     vPN = mN.y;
                     vQN = (flagsN & AFF_F_PAD) ? mN.y : mN.w;
-                    if (j > 1) stage_meta(p - 2 * T, my_meta);
+                    if (j > 1) stage_meta(p - 2 * PS, my_meta);
                     stage_dest(keyN);
-                    stage_points(p - lane - T, vPN, vQN, 0, 0);
+                    stage_points(p - lane - PS, vPN, vQN, 0, 0);
                     // the prefix needed at step j - 1 is the product after pair j - 2 (own slots: no other lane reads them)
                     if (j > 1 && j - 1 < nj) stage_prefix(j - 2);
                 }
@@ -767,7 +783,7 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
                 }
                 // .. and y1, x1 - x3
                 __syncwarp();
-                if (j > 0) stage_points(p - lane - T, vPN, vQN, 1, 1);
+                if (j > 0) stage_points(p - lane - PS, vPN, vQN, 1, 1);
                 cp_async_commit();
             }
         }
@@ -1398,7 +1414,7 @@ static int msm_workspace(bpk_ctx* ctx, const MsmPlan& pl, size_t n, MsmWork* w) 
         size_t need = (pairs0 + w->aff_threads - 1) / w->aff_threads;
         if (need < w->bmax) w->bmax = (uint32_t)(need < 1 ? 1 : need);
         BPK_TRY(ws_reserve(ctx, 19, (size_t)w->bmax * 3 * w->aff_threads * sizeof(uint4), (void**)&w->scratch));
-        w->rare_words = pairs0 / 32 + 2;
+        w->rare_words = pairs0 / 32 + 2 + MSM_MAX_LEVELS + 1;   // + one claim counter per level
         BPK_TRY(ws_reserve(ctx, 21, w->rare_words * sizeof(uint32_t), (void**)&w->rare_bits));
     }
     w->tail_ub = L == 0 ? w->M : level_ub(w->M, w->nb, L);
@@ -1540,6 +1556,7 @@ static int msm_fill_buckets(bpk_ctx* ctx, const MsmPlan& pl, const MsmPoints& pt
             a.buckets = buckets;
             a.scratch = w.scratch;
             a.rare_bits = w.rare_bits;
+            a.claim = w.rare_bits + (w.rare_words - MSM_MAX_LEVELS - 1) + l;
             a.level = (uint32_t)l;
             a.bmax = w.bmax;
             a.out_is_tail = l + 1 == L ? 1u : 0u;
