@@ -429,7 +429,7 @@ struct AffLevelArgs {
 #endif
 constexpr int AFF_THREADS = 128;
 #ifndef BPK_AFF_MIN_BATCH
-#define BPK_AFF_MIN_BATCH 8
+#define BPK_AFF_MIN_BATCH 32
 #endif
 constexpr uint32_t AFF_MIN_BATCH = BPK_AFF_MIN_BATCH;   // the shortest batch a warp claims (steps of 32 pairs)
 // How the level kernel touches memory (profiles/r2_affine_ab.md, profiles/r2_affine_v2.md):
@@ -517,12 +517,20 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
     const uint32_t T = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     // A warp works on 32 neighbouring pairs at every step and shares one inversion per lane over a batch of B steps.  The
-    // batches are CLAIMED from a counter (guided: an even share of what is left, between AFF_MIN_BATCH and bmax steps):
+    // batches are CLAIMED from a counter (at the large levels with guided sizes between AFF_MIN_BATCH and bmax steps):
     // with a fixed share per warp the schedulers' preference for their oldest warp let some warps finish a fifth of the
     // kernel before others (ncu: 3.17 of 4 warps resident per scheduler on average), and the pipe idles with them.
     // Pair numbers fit 32 bits: S <= 2^31, and the counter overshoots S by less than 32 bmax per warp.
     const uint32_t nwarps = T >> 5;
     constexpr uint32_t PS = 32;                           // pairs per step of a warp
+    // Guided sizes only where a warp's even share is several full batches (the two lowest levels of a large MSM): every
+    // batch costs an inversion (~7 additions), so short batches at the end of a small level cost more than the idle
+    // warps did (measured at 2^24: level 0 26.3 -> 24.1 ms, level 1 12.5 -> 11.8, level 2 with guided sizes 6.44 -> 6.54).
+    // Elsewhere: equal batches, as few per warp as bmax allows.
+    const uint32_t even = (S - 1) / (PS * nwarps) + 1;    // steps per warp of an even split
+    const bool guided = even >= 2 * a.bmax;
+    const uint32_t rounds = (even - 1) / a.bmax + 1;
+    const uint32_t Beq = (even - 1) / rounds + 1;
     uint4* const sc = a.scratch + tid;
     // this warp's stage (layout above): the pair of lane l at 208 l, this lane's 16-byte slots of the other arrays at
     // my16 + the array's offset
@@ -600,10 +608,13 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
     for (;;) {
         uint32_t base0 = 0, B = 0;                        // the warp's first pair of this batch, its steps
         if (lane == 0) {
-            const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(a.claim);
-            const uint32_t left = seen < S ? S - seen : 0u;
-            B = left / (PS * nwarps);
-            if (B < AFF_MIN_BATCH) B = AFF_MIN_BATCH;
+            B = Beq;
+            if (guided) {                                 // twice an even share of what is left
+                const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(a.claim);
+                const uint32_t left = seen < S ? S - seen : 0u;
+                B = 2 * (left / (PS * nwarps));
+                if (B < AFF_MIN_BATCH) B = AFF_MIN_BATCH;
+            }
             if (B > a.bmax) B = a.bmax;                   // (the prefix scratch holds bmax steps per thread)
             base0 = atomicAdd(a.claim, PS * B);
         }
