@@ -431,6 +431,12 @@ constexpr int AFF_THREADS = 128;
 #ifndef BPK_AFF_MIN_BATCH
 #define BPK_AFF_MIN_BATCH 32
 #endif
+#ifndef BPK_AFF_GUIDED_ROUNDS
+#define BPK_AFF_GUIDED_ROUNDS 2u   // guided sizes from this many full batches per warp
+#endif
+#ifndef BPK_AFF_GUIDED_FACTOR
+#define BPK_AFF_GUIDED_FACTOR 2u   // a claim = this many even shares of what is left
+#endif
 constexpr uint32_t AFF_MIN_BATCH = BPK_AFF_MIN_BATCH;   // the shortest batch a warp claims (steps of 32 pairs)
 // How the level kernel touches memory (profiles/r2_affine_ab.md, profiles/r2_affine_v2.md):
 //  * operands: what bounds a kernel in which every lane loads its own 96-byte points is the SM's single L1TEX queue (a
@@ -528,7 +534,7 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
     // warps did (measured at 2^24: level 0 26.3 -> 24.1 ms, level 1 12.5 -> 11.8, level 2 with guided sizes 6.44 -> 6.54).
     // Elsewhere: equal batches, as few per warp as bmax allows.
     const uint32_t even = (S - 1) / (PS * nwarps) + 1;    // steps per warp of an even split
-    const bool guided = even >= 2 * a.bmax;
+    const bool guided = even >= BPK_AFF_GUIDED_ROUNDS * a.bmax;
     const uint32_t rounds = (even - 1) / a.bmax + 1;
     const uint32_t Beq = (even - 1) / rounds + 1;
     uint4* const sc = a.scratch + tid;
@@ -612,7 +618,7 @@ __global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_lev
             if (guided) {                                 // twice an even share of what is left
                 const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(a.claim);
                 const uint32_t left = seen < S ? S - seen : 0u;
-                B = 2 * (left / (PS * nwarps));
+                B = BPK_AFF_GUIDED_FACTOR * (left / (PS * nwarps));
                 if (B < AFF_MIN_BATCH) B = AFF_MIN_BATCH;
             }
             if (B > a.bmax) B = a.bmax;                   // (the prefix scratch holds bmax steps per thread)
