@@ -124,12 +124,45 @@ def gen_scalars(n, seed):
 
 
 class ClockSampler:
+    """SM clock, throttle reasons and power of one GPU DURING the timed region.  NVML in a thread of this process (a sample
+    every 10 ms: the timed region of the default run is ~0.3 s), `nvidia-smi -lms 100` next to it as the fallback (its
+    start-up alone can outlast the region)."""
     FIELDS = ("uuid,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, uuid):
         self.uuid = str(uuid)
+        self.rows = []           # NVML samples: (sm_mhz, reasons bitmask, watts)
+        self.sm_max = None
+        self.halt = threading.Event()
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            name = self.uuid if self.uuid.startswith("GPU-") else "GPU-" + self.uuid
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(name.encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByUUID(name)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+
+            def loop():
+                while not self.halt.is_set():
+                    try:
+                        self.rows.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), int(reasons_fn(h)),
+                                          pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0))
+                    except Exception:
+                        pass
+                    self.halt.wait(0.01)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.thread = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
@@ -139,8 +172,26 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
+        if self.thread is not None:
+            self.halt.set()
+            self.thread.join(timeout=2)
+        smi = self._stop_smi()
+        if self.rows:
+            sm = sorted(r[0] for r in self.rows)
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=self.sm_max, power_w_max=max(r[2] for r in self.rows),
+                       samples=len(self.rows), source="nvml, 10 ms")
+            seen = 0
+            for r in self.rows:
+                seen |= r[1]
+            out["reasons"] = [nm for nm, bit in self.NVML_REASONS if seen & bit]
             return out
+        if smi:
+            out.update(smi)
+        return out
+
+    def _stop_smi(self):
+        if self.p is None:
+            return None
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -155,16 +206,15 @@ class ClockSampler:
             rows.append(parts)
         os.unlink(self.f.name)
         if not rows:
-            return out
+            return None
+        out = {"source": "nvidia-smi -lms 100"}
         sm = sorted(float(r[1]) for r in rows)
         out["sm_mhz"] = sm[len(sm) // 2]
         out["sm_max_mhz"] = float(rows[0][2])
         out["power_w_max"] = max(float(r[3]) for r in rows)
         out["samples"] = len(rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for i, nm in enumerate(names):
-            if any(r[4 + i].lower().startswith("active") for r in rows):
-                out["reasons"].append(nm)
+        out["reasons"] = [nm for i, nm in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in rows)]
         return out
 
 
