@@ -371,6 +371,9 @@ extern "C" int bpk_set_option(bpk_ctx* ctx, const char* key, long value) {
     } else if (k == "msm.batch") {
         if (value < 1 || value > 4096) return BPK_ERR_INVALID_ARG;
         ctx->opt_msm_batch = value;
+    } else if (k == "msm.cta_shape") {
+        if (value < 0 || value > 2) return BPK_ERR_INVALID_ARG;
+        ctx->opt_msm_cta_shape = value;
     } else if (k == "msm.level_mib") {
         if (value < 0) return BPK_ERR_INVALID_ARG;
         ctx->opt_msm_level_mib = value;

@@ -109,6 +109,7 @@ struct bpk_ctx {
     long opt_msm_lanes = bpk::MSM_LANES;  // 1: bpk_msm_g1_dev_batch runs its MSMs one after the other
     long opt_msm_host_slices = 1;  // 0: upload all scalars before the MSM starts
     long opt_msm_affine_levels = -1;  // levels of the batched-affine pairwise tree (-1: from the expected bucket load, 0: XYZZ only)
+    long opt_msm_cta_shape = 0;        // level kernel: 0 = by level size, 1 = four CTAs of 4 warps per SM, 2 = one CTA of 16 (A/B)
     long opt_msm_min_pairs = 1 << 18;  // a tree level expected to hold fewer pairs is left to the XYZZ tail (r2_msm_plan_sweep.md)
     long opt_msm_batch = 256;          // additions that share one inversion (per thread)
     long opt_msm_level_mib = 48 << 10; // budget of the tree's level buffers

@@ -424,10 +424,11 @@ struct AffLevelArgs {
     uint32_t level, bmax, out_is_tail;
 };
 
-#ifndef BPK_AFF_MINBLOCKS
-#define BPK_AFF_MINBLOCKS 4
-#endif
-constexpr int AFF_THREADS = 128;
+// 16 warps per SM either way (128 registers per thread): four CTAs of four warps at the large levels, ONE CTA of sixteen
+// at the small ones (where a warp has a single batch): the same code, measured 4 % faster there (2^21 pairs: accumulate
+// 8.00 -> 7.69 ms) and 2.7 % slower at the levels with guided batches (profiles/r2_affine_v2.md).
+constexpr int AFF_THREADS = 128, AFF_THREADS_SMALL = 512;
+constexpr int AFF_WARPS_PER_SM = 16;
 #ifndef BPK_AFF_MIN_BATCH
 #define BPK_AFF_MIN_BATCH 32
 #endif
@@ -470,7 +471,8 @@ constexpr uint32_t AFF_PAIR_STRIDE = 208;
 constexpr uint32_t AFF_PRE_OFF = 32 * AFF_PAIR_STRIDE, AFF_META_OFF = AFF_PRE_OFF + 32 * 48, AFF_DEST_OFF = AFF_META_OFF + 32 * 16,
                    AFF_ACC_OFF = AFF_DEST_OFF + 32 * 16, AFF_LAM_OFF = AFF_ACC_OFF + 32 * 48;
 constexpr int AFF_WARP_SMEM = AFF_LAM_OFF + 32 * 48;                           // 12 KB per warp
-constexpr size_t AFF_SMEM_BYTES = (size_t)(AFF_THREADS / 32) * AFF_WARP_SMEM;  // 48 KB per CTA
+constexpr size_t AFF_SMEM_BYTES = (size_t)(AFF_THREADS / 32) * AFF_WARP_SMEM;              // 48 KB per CTA
+constexpr size_t AFF_SMEM_BYTES_SMALL = (size_t)(AFF_THREADS_SMALL / 32) * AFF_WARP_SMEM;  // 192 KB per CTA
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -515,8 +517,8 @@ __device__ __forceinline__ fp_t aff_canon(const fp_t& x) { return BPK_AFF_LAZY ?
 
 constexpr uint32_t AFF_F_PAD = 1, AFF_F_NEG_P = 2, AFF_F_NEG_Q = 4, AFF_F_FINISHED = 8, AFF_F_MARK_PAD = 16, AFF_F_X_ZERO = 32;
 
-template <bool LEVEL0>
-__global__ void __launch_bounds__(AFF_THREADS, BPK_AFF_MINBLOCKS) msm_affine_level_kernel(const __grid_constant__ AffLevelArgs a) {
+template <bool LEVEL0, int THREADS>
+__global__ void __launch_bounds__(THREADS, AFF_WARPS_PER_SM * 32 / THREADS) msm_affine_level_kernel(const __grid_constant__ AffLevelArgs a) {
     extern __shared__ uint4 aff_smem[];
     const uint32_t S = a.totals[a.level] >> 1;  // pairs of this level
     if (S == 0) return;
@@ -1415,7 +1417,7 @@ static int msm_workspace(bpk_ctx* ctx, const MsmPlan& pl, size_t n, MsmWork* w) 
     w->scratch = nullptr;
     w->rare_bits = nullptr;
     w->rare_words = 0;
-    w->aff_threads = (uint32_t)ctx->sm_count * BPK_AFF_MINBLOCKS * AFF_THREADS;
+    w->aff_threads = (uint32_t)ctx->sm_count * AFF_WARPS_PER_SM * 32;
     w->bmax = (uint32_t)(ctx->opt_msm_batch < 1 ? 1 : ctx->opt_msm_batch);
     if (L >= 1) {
         // + 66: the cooperative copies of the last warp of a level read up to 31 pairs past its end
@@ -1480,9 +1482,11 @@ static int msm_launch_tail_merge(bpk_ctx* ctx, const MsmWork& w, const TailSrc& 
 
 static int msm_configure_kernels(bpk_ctx* ctx) {  // opt in to > 48 KB of dynamic shared memory, once per process
     static bool done = false;
-    if (done || AFF_SMEM_BYTES <= 48 * 1024) return BPK_OK;
-    BPK_CUDA(cudaFuncSetAttribute(msm_affine_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AFF_SMEM_BYTES));
-    BPK_CUDA(cudaFuncSetAttribute(msm_affine_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AFF_SMEM_BYTES));
+    if (done) return BPK_OK;
+    BPK_CUDA(cudaFuncSetAttribute(msm_affine_level_kernel<true, AFF_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AFF_SMEM_BYTES));
+    BPK_CUDA(cudaFuncSetAttribute(msm_affine_level_kernel<false, AFF_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AFF_SMEM_BYTES));
+    BPK_CUDA(cudaFuncSetAttribute(msm_affine_level_kernel<true, AFF_THREADS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AFF_SMEM_BYTES_SMALL));
+    BPK_CUDA(cudaFuncSetAttribute(msm_affine_level_kernel<false, AFF_THREADS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AFF_SMEM_BYTES_SMALL));
     done = true;
     return BPK_OK;
 }
@@ -1577,12 +1581,19 @@ static int msm_fill_buckets(bpk_ctx* ctx, const MsmPlan& pl, const MsmPoints& pt
             a.level = (uint32_t)l;
             a.bmax = w.bmax;
             a.out_is_tail = l + 1 == L ? 1u : 0u;
-            const unsigned grid = w.aff_threads / AFF_THREADS;
+            // the CTA shape by the level's expected size: large = a warp's even share is at least two full batches (where
+            // the kernel claims guided batch sizes)
+            const size_t pairs_ub = level_ub(w.M, w.nb, l) / 2;
+            const bool large = ctx->opt_msm_cta_shape == 0 ? pairs_ub / (32 * (w.aff_threads / 32)) >= 2 * (size_t)w.bmax
+                                                           : ctx->opt_msm_cta_shape == 1;
+            const unsigned grid = w.aff_threads / (large ? AFF_THREADS : AFF_THREADS_SMALL);
             if (l == 0) {
-                msm_affine_level_kernel<true><<<grid, AFF_THREADS, AFF_SMEM_BYTES, ctx->stream>>>(a);
+                if (large) msm_affine_level_kernel<true, AFF_THREADS><<<grid, AFF_THREADS, AFF_SMEM_BYTES, ctx->stream>>>(a);
+                else msm_affine_level_kernel<true, AFF_THREADS_SMALL><<<grid, AFF_THREADS_SMALL, AFF_SMEM_BYTES_SMALL, ctx->stream>>>(a);
                 msm_affine_rare_kernel<true><<<(unsigned)ctx->sm_count * 4, 128, 0, ctx->stream>>>(a);
             } else {
-                msm_affine_level_kernel<false><<<grid, AFF_THREADS, AFF_SMEM_BYTES, ctx->stream>>>(a);
+                if (large) msm_affine_level_kernel<false, AFF_THREADS><<<grid, AFF_THREADS, AFF_SMEM_BYTES, ctx->stream>>>(a);
+                else msm_affine_level_kernel<false, AFF_THREADS_SMALL><<<grid, AFF_THREADS_SMALL, AFF_SMEM_BYTES_SMALL, ctx->stream>>>(a);
                 msm_affine_rare_kernel<false><<<(unsigned)ctx->sm_count * 4, 128, 0, ctx->stream>>>(a);
             }
             count_launch(ctx, 2);

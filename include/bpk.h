@@ -249,7 +249,8 @@ int bpk_imad_peak(bpk_ctx* ctx, double* wide_imad_per_s_out, double* seconds_out
  *   "msm.window" window bits of the non-precomputed MSM (0 = auto), "msm.chunk" pairs per accumulate thread (0 = auto),
  *   "msm.affine_levels" levels of the batched-affine pairwise tree (-1 = from the expected bucket load, 0 = XYZZ chunks only),
  *   "msm.min_pairs" a tree level expected to hold fewer pairs is left to the XYZZ tail, "msm.batch" additions per shared
- *   inversion, "msm.level_mib" memory budget of the tree's level buffers, "msm.tree_top" 0 = one launch per level of the
+ *   inversion, "msm.level_mib" memory budget of the tree's level buffers, "msm.cta_shape" level kernel as four CTAs of 4 warps
+ *   per SM (1), one CTA of 16 warps (2) or by the level's size (0, default), "msm.tree_top" 0 = one launch per level of the
  *   bucket-reduction tree, "msm.scatter_l2_mib" the sorted list is scattered in phases over bucket ranges of at most this size,
  *   "msm.lanes" 1..3 concurrent MSMs of bpk_msm_g1_dev_batch, "msm.host_slices" 0 = no upload / compute overlap,
  *   "ntt.tile_log2" log2 of the R x C tile per CTA (default 10), "ntt.max_radix_log2" (0 = auto), "ntt.threads",

@@ -447,7 +447,7 @@ def test_msm_precomputed_degenerate_points(ctx):
 class options:
     """set library tunables for a block, restore the defaults afterwards"""
     DEFAULTS = {"msm.affine_levels": -1, "msm.batch": 256, "msm.min_pairs": 1 << 18, "msm.window": 0, "msm.chunk": 0,
-                "msm.tree_top": 1, "msm.level_mib": 48 << 10, "msm.scatter_l2_mib": 400}
+                "msm.tree_top": 1, "msm.level_mib": 48 << 10, "msm.scatter_l2_mib": 400, "msm.cta_shape": 0}
 
     def __init__(self, ctx, **kw):
         self.ctx, self.kw = ctx, {k.replace("_", ".", 1): v for k, v in kw.items()}
@@ -540,6 +540,18 @@ def test_msm_phased_scatter(ctx, levels):
         setup.precompute(8)                 # 128 buckets
         for sc in cases:
             assert bpk.point_to_affine(setup.commit_scalars(S(sc))) == horner_expected(sc, 101)
+    setup.free()
+
+
+@pytest.mark.parametrize("shape", [1, 2])
+def test_msm_level_kernel_cta_shapes(ctx, shape):
+    """the level kernel as four CTAs of 4 warps per SM and as one CTA of 16 (by default chosen per level by its size)"""
+    n = 6000
+    setup = bpk.Setup.generate_srs(n, 101, ctx).precompute(10)
+    sc = O.random_fr(40 + shape, n)
+    want = horner_expected(sc, 101)
+    with options(ctx, msm_cta_shape=shape, msm_affine_levels=5, msm_batch=7):
+        assert bpk.point_to_affine(setup.commit_scalars(S(sc))) == want
     setup.free()
 
 
