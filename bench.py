@@ -630,7 +630,7 @@ DOMINANT_KERNEL = "msm_affine_level_kernel (+ msm_accumulate_kernel tail)"
 def write_imad_peak(chain_rate, fused_rate, clocks, gpu_name):
     """record the measured multiplier peak next to MEASURED_PEAKS.json's numbers: written to
     gpurun_out/ on the GPU box; the copy under profiles/ is the one the repo's roofline figures cite"""
-    rec = {"gpu_name": gpu_name, "how": "bpk_imad_peak (csrc/api.cu imad_probe_kernel): register-only probes, 8 CTAs x 256 "
+    rec = {"gpu_name": gpu_name, "how": "bpk_imad_peak (csrc/api.cu imad_probe_kernel): register-only probes, 16 CTAs x 128 "
            "threads per SM, 2^14 iterations; chain = two independent 12-limb IMAD.WIDE.U32.X carry chains (the shape the Fp "
            "multiplier issues), fused = 14 independent IMAD.WIDE.U32 with 64-bit addend",
            "wide_imad_per_s_chain": chain_rate, "wide_imad_per_s_fused": fused_rate,
