@@ -60,6 +60,7 @@ struct bpk_ctx {
     // (cargo test runs the reference's tests in parallel) are serialised here, not by the caller
     std::recursive_mutex mutex;
     int device = 0;
+    bool msm_kernels_configured = false;   // cudaFuncSetAttribute of the level kernels done on this device
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     std::string last_error;

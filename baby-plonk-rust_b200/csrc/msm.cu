@@ -1480,14 +1480,13 @@ static int msm_launch_tail_merge(bpk_ctx* ctx, const MsmWork& w, const TailSrc& 
     return BPK_OK;
 }
 
-static int msm_configure_kernels(bpk_ctx* ctx) {  // opt in to > 48 KB of dynamic shared memory, once per process
-    static bool done = false;
-    if (done) return BPK_OK;
+static int msm_configure_kernels(bpk_ctx* ctx) {  // opt in to > 48 KB of dynamic shared memory: per device, so per context
+    if (ctx->msm_kernels_configured) return BPK_OK;
     BPK_CUDA(cudaFuncSetAttribute(msm_affine_level_kernel<true, AFF_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AFF_SMEM_BYTES));
     BPK_CUDA(cudaFuncSetAttribute(msm_affine_level_kernel<false, AFF_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AFF_SMEM_BYTES));
     BPK_CUDA(cudaFuncSetAttribute(msm_affine_level_kernel<true, AFF_THREADS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AFF_SMEM_BYTES_SMALL));
     BPK_CUDA(cudaFuncSetAttribute(msm_affine_level_kernel<false, AFF_THREADS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AFF_SMEM_BYTES_SMALL));
-    done = true;
+    ctx->msm_kernels_configured = true;
     return BPK_OK;
 }
 
